@@ -1,0 +1,291 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (build container only).
+
+    python oracle/make_golden.py            # needs /root/reference
+
+Every file stores the seeded inputs and the outputs of the reference's own functions
+(embedder.py, model.py, ray.py, nerf/run.py:render_rays, d_nerf/run_dnerf.py:render_rays,
+torchsearchsorted's numpy_searchsorted).  Network weights are NOT stored: they are
+regenerated from `seed` by oracle.nerf_oracle.make_params (numpy legacy RandomState).
+Gradients are stored as per-tensor norms/sums plus a strided subsample.
+"""
+import os
+import sys
+from argparse import Namespace
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import nerf_oracle as O          # noqa: E402
+from oracle import ref_import                # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+GRAD_STRIDE = 251
+
+
+def grad_summary(named_grads):
+    out = {}
+    for k, g in named_grads.items():
+        g = g.detach().double().reshape(-1)
+        out[f"gnorm/{k}"] = np.float64(g.norm().item())
+        out[f"gsum/{k}"] = np.float64(g.sum().item())
+        out[f"gsub/{k}"] = g[::GRAD_STRIDE].float().numpy()
+    return out
+
+
+def load_params(module, params):
+    sd = module.state_dict()
+    assert set(sd.keys()) == set(params.keys()), (sorted(sd.keys()), sorted(params.keys()))
+    for k in sd:
+        assert tuple(sd[k].shape) == tuple(params[k].shape), k
+    module.load_state_dict({k: v.clone() for k, v in params.items()})
+
+
+def gen_embed(ref):
+    rs = np.random.RandomState(11)
+    d = {}
+    x3 = rs.uniform(-6, 6, size=(37, 3)).astype(np.float32)
+    x1 = rs.uniform(0, 1, size=(19, 1)).astype(np.float32)
+    d["x3"], d["x1"] = x3, x1
+    for L, x, tag in [(10, x3, "L10_d3"), (4, x3, "L4_d3"), (20, x3, "L20_d3"), (10, x1, "L10_d1"),
+                      (8, x1, "L8_d1"), (4, x1, "L4_d1")]:
+        fn, dim = ref.embedder.get_embedder(L, x.shape[1], 0)
+        y = fn(torch.from_numpy(x))
+        assert y.shape[1] == dim
+        d[f"y_{tag}"] = y.numpy()
+    fn, dim = ref.embedder.get_embedder(-1, 3, -1)
+    d["y_identity"] = fn(torch.from_numpy(x3)).numpy()
+    np.savez_compressed(os.path.join(OUT, "embed.npz"), **d)
+
+
+def gen_mlp(ref):
+    rs = np.random.RandomState(12)
+    d = {"seed": np.int64(101)}
+    x = rs.uniform(-1, 1, size=(45, 90)).astype(np.float32)
+    d["x"] = x
+    shapes = O.mlp_param_shapes()
+    params = O.make_params(shapes, 101)
+    m = ref.model.vallina_NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
+    load_params(m, params)
+    d["y_vanilla"] = m(torch.from_numpy(x)).detach().numpy()
+    m2 = ref.model.NeRFOriginal(D=8, W=256, input_ch=63, input_ch_views=27, input_ch_time=21, output_ch=5,
+                                skips=[4], use_viewdirs=True, output_color_ch=3)
+    load_params(m2, params)
+    y2, z2 = m2(torch.from_numpy(x), None)
+    d["y_original"] = y2.detach().numpy()
+    assert float(z2.abs().max()) == 0.0
+    # no-viewdirs head
+    shapes_nv = O.mlp_param_shapes(input_ch_views=0, output_ch=4, use_viewdirs=False)
+    # reference always builds views_linears (model.py:26) even when unused
+    params_nv = O.make_params(shapes_nv, 102)
+    m3 = ref.model.vallina_NeRF(D=8, W=256, input_ch=63, input_ch_views=0, output_ch=4, skips=[4], use_viewdirs=False)
+    load_params(m3, params_nv)
+    d["seed_nv"] = np.int64(102)
+    d["y_noview"] = m3(torch.from_numpy(x[:, :63].copy())).detach().numpy()
+    # D-NeRF direct_temporal
+    shapes_d = O.dnerf_param_shapes()
+    params_d = O.make_params(shapes_d, 103)
+    emb_fn, _ = ref.embedder.get_embedder(10, 3, 0)
+    md = ref.model.DirectTemporalNeRF(D=8, W=256, input_ch=63, input_ch_views=27, input_ch_time=21, output_ch=5,
+                                      skips=[4], use_viewdirs=True, embed_fn=emb_fn, zero_canonical=True)
+    load_params(md, params_d)
+    d["seed_dnerf"] = np.int64(103)
+    pts = rs.uniform(-1.5, 1.5, size=(29, 3)).astype(np.float32)
+    vd = rs.normal(size=(29, 3)).astype(np.float32)
+    vd /= np.linalg.norm(vd, axis=-1, keepdims=True)
+    d["d_pts"], d["d_vd"] = pts, vd
+    embd_fn, _ = ref.embedder.get_embedder(4, 3, 0)
+    embt_fn, _ = ref.embedder.get_embedder(10, 1, 0)
+    for tval, tag in [(0.37, "t037"), (0.0, "t0")]:
+        xin = torch.cat([emb_fn(torch.from_numpy(pts)), embd_fn(torch.from_numpy(vd))], -1)
+        et = embt_fn(torch.full((29, 1), tval))
+        out, dx = md(xin, [et, et])
+        d[f"d_out_{tag}"] = out.detach().numpy()
+        d[f"d_dx_{tag}"] = dx.detach().numpy()
+    np.savez_compressed(os.path.join(OUT, "mlp.npz"), **d)
+
+
+def gen_raw2outputs(ref):
+    rs = np.random.RandomState(13)
+    d = {}
+    for S, tag in [(64, "S64"), (192, "S192"), (5, "S5")]:
+        N = 13
+        raw = (rs.normal(size=(N, S, 4)) * 3.0).astype(np.float32)
+        raw[0, :, 3] = -1.0                       # fully transparent ray -> disp NaN (0/0)
+        raw[1, :, 3] = 50.0                       # opaque at the first sample
+        z = np.sort(rs.uniform(2, 6, size=(N, S)).astype(np.float32), -1)
+        z[2, 3] = z[2, 2]                         # zero-length interval
+        rd = rs.normal(size=(N, 3)).astype(np.float32)
+        d[f"raw_{tag}"], d[f"z_{tag}"], d[f"rd_{tag}"] = raw, z, rd
+        for wb in (False, True):
+            outs = ref.ray.raw2outputs(torch.from_numpy(raw), torch.from_numpy(z), torch.from_numpy(rd), 0, wb)
+            for name, o in zip(["rgb", "disp", "acc", "weights", "depth"], outs):
+                d[f"{name}_{tag}_wb{int(wb)}"] = o.numpy()
+        # noisy variant through the pytest hook (ray.py:180-184: np.random.seed(0); rand * std)
+        outs = ref.ray.raw2outputs(torch.from_numpy(raw), torch.from_numpy(z), torch.from_numpy(rd), 1.0, True, pytest=True)
+        np.random.seed(0)
+        d[f"noise_{tag}"] = (np.random.rand(N, S) * 1.0).astype(np.float32)
+        for name, o in zip(["rgb", "disp", "acc", "weights", "depth"], outs):
+            d[f"{name}_{tag}_noise"] = o.numpy()
+    np.savez_compressed(os.path.join(OUT, "raw2outputs.npz"), **d)
+
+
+def gen_sample_pdf(ref):
+    rs = np.random.RandomState(14)
+    d = {}
+    N = 17
+    bins = np.sort(rs.uniform(2, 6, size=(N, 63)).astype(np.float32), -1)
+    w = rs.uniform(0, 1, size=(N, 62)).astype(np.float32) ** 4
+    w[0] = 0.0                                     # all-zero weights -> uniform pdf
+    w[1, 10:50] = 0.0                              # flat cdf stretch (denom < 1e-5 branch)
+    w[2, :] = 0.0; w[2, 31] = 1.0                  # one dominant bin
+    w[3, :61] = 0.0; w[3, 61] = 5.0                # all mass in the last bin
+    d["bins"], d["weights"] = bins, w
+    d["samples_det128"] = ref.ray.sample_pdf(torch.from_numpy(bins), torch.from_numpy(w), 128, det=True).numpy()
+    d["samples_det64"] = ref.ray.sample_pdf(torch.from_numpy(bins), torch.from_numpy(w), 64, det=True).numpy()
+    d["samples_rand128"] = ref.ray.sample_pdf(torch.from_numpy(bins), torch.from_numpy(w), 128, det=False, pytest=True).numpy()
+    np.random.seed(0)
+    d["u_rand128"] = np.random.rand(N, 128).astype(np.float32)
+    # the cdf the reference builds (ray.py:111-114), for the bit-exact index test
+    wt = torch.from_numpy(w) + 1e-5
+    pdf = wt / torch.sum(wt, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    d["cdf"] = cdf.numpy()
+    u = torch.linspace(0., 1., steps=128).expand(N, 128).contiguous()
+    d["inds_det128"] = torch.searchsorted(cdf, u, right=True).numpy()          # ray.py:136
+    d["inds_rand128"] = torch.searchsorted(cdf, torch.from_numpy(d["u_rand128"]).contiguous(), right=True).numpy()
+    np.savez_compressed(os.path.join(OUT, "sample_pdf.npz"), **d)
+
+
+def gen_searchsorted():
+    f = ref_import.load_reference_searchsorted_numpy()
+    rs = np.random.RandomState(15)
+    d = {}
+    k = 0
+    # the reference's own param grid (test/test_searchsorted.py:27-44), one draw per cell, ties included
+    for Ba in (1, 20):
+        for Bv in (1, 20):
+            for A in (1, 50, 500):
+                for V in (1, 12, 120):
+                    for side in ("left", "right"):
+                        a = np.sort(rs.rand(Ba, A).astype(np.float32), 1)
+                        v = rs.rand(Bv, V).astype(np.float32)
+                        if A > 1 and V > 1:
+                            v[:, 0] = a[:, A // 2] if Ba == Bv else a[0, A // 2]   # exact ties
+                            v[:, -1] = 2.0                                         # beyond the right border
+                        d[f"a{k}"], d[f"v{k}"] = a, v
+                        d[f"side{k}"] = np.int64(side == "left")
+                        d[f"out{k}"] = f(a, v, side=side).astype(np.int64)
+                        k += 1
+    d["n"] = np.int64(k)
+    np.savez_compressed(os.path.join(OUT, "searchsorted.npz"), **d)
+
+
+def _vanilla_kwargs(ref, seed_c, seed_f, perturb, raw_noise_std, white_bkgd=True, lindisp=False):
+    shapes = O.mlp_param_shapes()
+    pc, pf = O.make_params(shapes, seed_c), O.make_params(shapes, seed_f)
+    args = Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
+                     netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4,
+                     ft_path=None, basedir="/tmp/_swnerf_golden", expname="g", no_reload=True, perturb=perturb,
+                     white_bkgd=white_bkgd, raw_noise_std=raw_noise_std, dataset_type="blender", no_ndc=False,
+                     lindisp=lindisp)
+    os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)
+    kw_train, kw_test, start, grad_vars, opt = ref.run.create_nerf(args)
+    load_params(kw_train["network_fn"], pc)
+    load_params(kw_train["network_fine"], pf)
+    return kw_train, kw_test
+
+
+def gen_render_rays(ref):
+    d = {}
+    N = 24
+    rays = O.blender_rays(N, seed=21)
+    target = np.random.RandomState(22).uniform(0, 1, size=(N, 3)).astype(np.float32)
+    d["rays"], d["target"] = rays, target
+    d["seed_coarse"], d["seed_fine"] = np.int64(201), np.int64(202)
+    for tag, perturb, noise, lindisp in [("det", 0.0, 0.0, False), ("pert", 1.0, 0.0, False),
+                                         ("noise", 1.0, 1.0, False), ("lindisp", 0.0, 0.0, True)]:
+        kw_train, kw_test = _vanilla_kwargs(ref, 201, 202, perturb, noise, lindisp=lindisp)
+        kw = dict(kw_train)
+        kw.pop("use_viewdirs"); kw.pop("ndc")
+        for m in (kw["network_fn"], kw["network_fine"]):
+            m.zero_grad()
+        ret = ref.run.render_rays(torch.from_numpy(rays), retraw=True, pytest=True, **kw)
+        loss = torch.mean((ret["rgb_map"] - torch.from_numpy(target)) ** 2) + \
+            torch.mean((ret["rgb0"] - torch.from_numpy(target)) ** 2)           # nerf/run.py:689-697
+        loss.backward()
+        for k, v in ret.items():
+            d[f"{tag}/{k}"] = v.detach().numpy()
+        d[f"{tag}/loss"] = np.float64(loss.item())
+        grads = {"coarse." + k: p.grad for k, p in kw["network_fn"].named_parameters()}
+        grads.update({"fine." + k: p.grad for k, p in kw["network_fine"].named_parameters()})
+        for k, v in grad_summary(grads).items():
+            d[f"{tag}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "render_rays.npz"), **d)
+
+
+def gen_render_rays_dnerf(ref):
+    d = {}
+    N = 10
+    d["seed"] = np.int64(301)
+    shapes = O.dnerf_param_shapes()
+    params = O.make_params(shapes, 301)
+    args = Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
+                     netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4,
+                     ft_path=None, basedir="/tmp/_swnerf_golden", expname="gd", no_reload=True, perturb=1.0,
+                     white_bkgd=True, raw_noise_std=0.0, dataset_type="blender", no_ndc=False, lindisp=False,
+                     nerf_type="direct_temporal", use_two_models_for_fine=False, not_zero_canonical=False,
+                     do_half_precision=False)
+    os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)
+    kw_train, kw_test, _, _, _ = ref.run_dnerf.create_nerf(args)
+    model = kw_train["network_fn"]
+    load_params(model, params)
+    kw = dict(kw_train)
+    kw.pop("use_viewdirs"); kw.pop("ndc")
+    for tval, tag in [(0.37, "t037"), (0.0, "t0")]:
+        rays = O.blender_rays(N, seed=31, frame_time=tval)
+        target = np.random.RandomState(32).uniform(0, 1, size=(N, 3)).astype(np.float32)
+        d[f"{tag}/rays"], d[f"{tag}/target"] = rays, target
+        model.zero_grad()
+        ret = ref.run_dnerf.render_rays(torch.from_numpy(rays), retraw=True, pytest=True, **kw)
+        loss = torch.mean((ret["rgb_map"] - torch.from_numpy(target)) ** 2)
+        # tv-loss second render at a neighbouring time with the same z_vals (run_dnerf.py:690-725)
+        if tval != 0.0:
+            rays2 = rays.copy(); rays2[:, 8] = tval + 0.01
+            ret2 = ref.run_dnerf.render_rays(torch.from_numpy(rays2), retraw=False, pytest=True,
+                                             z_vals=ret["z_vals"].detach(), **kw)
+            tv = torch.sum((ret["position_delta"] - ret2["position_delta"]) ** 2)
+            loss = loss + 0.1 * tv
+            d[f"{tag}/position_delta_next"] = ret2["position_delta"].detach().numpy()
+            d[f"{tag}/rgb_map_next"] = ret2["rgb_map"].detach().numpy()
+        loss.backward()
+        for k, v in ret.items():
+            d[f"{tag}/{k}"] = v.detach().numpy()
+        d[f"{tag}/loss"] = np.float64(loss.item())
+        grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+        for k, v in grad_summary(grads).items():
+            d[f"{tag}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "render_rays_dnerf.npz"), **d)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    ref = ref_import.load_reference()
+    torch.autograd.set_detect_anomaly(False)
+    gen_embed(ref)
+    gen_mlp(ref)
+    gen_raw2outputs(ref)
+    gen_sample_pdf(ref)
+    gen_searchsorted()
+    gen_render_rays(ref)
+    gen_render_rays_dnerf(ref)
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""Benchmark of the SW-NeRF per-ray rendering hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--precision tc|fp32]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Step = one vanilla-NeRF lego training step on one batch of synthetic Blender-shaped rays per GPU
+(configs[1]: N_rand=4096, 64 coarse + 128 fine samples, coarse+fine 8x256 networks, forward +
+backward + gradient all-reduce + Adam), weak scaling (4096 rays per GPU).  Prints ONE JSON line.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_RAND = 4096
+N_SAMPLES, N_IMPORTANCE = 64, 128
+MAC_PER_EVAL = 593408                      # BASELINE.md section 4 (model.py:22-35)
+FLOP_PER_EVAL_FWD = 2 * MAC_PER_EVAL
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"bf16_tflops": d["bf16_tflops"], "bf16_tflops_sustained": d.get("bf16_tflops_sustained"),
+                "hbm_gbs": d["hbm_gbs"], "src": "measured"}
+    return {"bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "hbm_gbs": 6650.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx = float(r[2])
+            except Exception:
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7),
+                              ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_reference_run(steps, warmup, sample_rays, threads):
+    """The reference's algorithm on the host cores: the oracle port (oracle/nerf_oracle.py, pinned to
+    the unmodified reference by tests/golden) - render_rays forward + two-loss backward + Adam."""
+    from oracle import nerf_oracle as O
+    torch.set_num_threads(threads)
+    shapes = O.mlp_param_shapes()
+    pc = {k: v.requires_grad_() for k, v in O.make_params(shapes, 1).items()}
+    pf = {k: v.requires_grad_() for k, v in O.make_params(shapes, 2).items()}
+    opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
+    rays = torch.from_numpy(O.blender_rays(sample_rays, 5))
+    target = torch.from_numpy(np.random.RandomState(6).uniform(0, 1, (sample_rays, 3)).astype(np.float32))
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        ret = O.render_rays(rays, pc, pf, N_SAMPLES, N_IMPORTANCE, perturb=1.0, white_bkgd=True)
+        loss = ((ret["rgb_map"] - target) ** 2).mean() + ((ret["rgb0"] - target) ** 2).mean()
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return sample_rays * len(times) / sum(times), sum(times) / len(times)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="swnerf_b200")
+    ap.add_argument("--precision", default=None, help="tc (fused tcgen05, default when built) or fp32 (check mode)")
+    ap.add_argument("--cpu-sample-rays", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--render-frame", action="store_true", help="also time one 800x800 frame render (config #3)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    threads = os.cpu_count() or 1
+    config = {"workload": "vanilla NeRF lego training step: N_rand=4096 rays/GPU, 64 coarse + 128 fine samples, "
+                          "coarse+fine 8x256 MLP (PE L=10/4), fwd+bwd+Adam, synthetic 800x800 Blender-shaped rays",
+              "rays_per_gpu": N_RAND, "N_samples": N_SAMPLES, "N_importance": N_IMPORTANCE,
+              "parallelism": "ray-sharded dp%d" % world,
+              "l2": "every step streams >126 MB of activations (working set larger than L2)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rps, spp = cpu_reference_run(args.steps, args.warmup, args.cpu_sample_rays, threads)
+        line = {"impl": "reference", "metric": "train_rays_per_s", "value": rps, "unit": "rays/s",
+                "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": spp * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                                 "sample": "%d rays per step (bounded sample of the 4096-ray step), fwd+bwd+Adam, "
+                                           "torch CPU fp32, %d threads" % (args.cpu_sample_rays, threads)},
+                "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch.distributed as dist
+    import swnerf_b200 as S
+    from swnerf_b200 import _lib, tc, parallel
+    from oracle import nerf_oracle as O      # synthetic ray generator + cpu_baseline only
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    _lib.call("swnerf_device_ok")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision or ("tc" if tc.available() else "fp32")
+
+    torch.manual_seed(1234 + rank)
+    shapes = O.mlp_param_shapes()
+    mc = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mc.load_state_dict(O.make_params(shapes, 1)); mc.to(dev)
+    mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(O.make_params(shapes, 2)); mf.to(dev)
+    q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], precision=precision)
+    params = list(mc.parameters()) + list(mf.parameters())
+    flat = parallel.FlatGrads(params)
+    opt = torch.optim.Adam(params, lr=5e-4, betas=(0.9, 0.999), fused=True)
+    n_global = N_RAND * world
+
+    nbatch = 4
+    host_rays = [torch.from_numpy(O.blender_rays(N_RAND, 100 + rank * 10 + i)).pin_memory() for i in range(nbatch)]
+    host_tgt = [torch.from_numpy(np.random.RandomState(200 + rank * 10 + i).uniform(0, 1, (N_RAND, 3))
+                                 .astype(np.float32)).pin_memory() for i in range(nbatch)]
+    dev_rays = [r.to(dev) for r in host_rays]
+    dev_tgt = [t.to(dev) for t in host_tgt]
+    kw = dict(network_fn=mc, network_query_fn=q, N_samples=N_SAMPLES, perturb=1.0, N_importance=N_IMPORTANCE,
+              network_fine=mf, white_bkgd=True, raw_noise_std=0.0)
+
+    def step(rays, tgt):
+        flat.zero_()
+        ret = S.render_rays(rays, **kw)
+        loss = parallel.sharded_mse(ret["rgb_map"], tgt, n_global) + parallel.sharded_mse(ret["rgb0"], tgt, n_global)
+        loss.backward()
+        flat.all_reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def resident(i):
+        step(dev_rays[i % nbatch], dev_tgt[i % nbatch])
+
+    last = {}
+
+    def e2e(i):
+        r = host_rays[i % nbatch].to(dev, non_blocking=True)
+        t = host_tgt[i % nbatch].to(dev, non_blocking=True)
+        last["loss"] = float(step(r, t).item())
+
+    for i in range(args.warmup):
+        resident(i)
+    assert flat.check_views(), "param.grad views were replaced; the flat all-reduce buffer is stale"
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    _lib.launch_count(reset=True)
+    ms = timed(resident, args.steps)
+    launches = _lib.launch_count()
+    clocks = sampler.stop() if rank == 0 else None
+    for i in range(2):
+        e2e(i)
+    ms_e2e = timed(e2e, args.steps)
+
+    # per-kernel device times (CUDA events on the launching stream) over a few instrumented steps
+    _lib.TIMING = {}
+    for i in range(3):
+        resident(i)
+    torch.cuda.synchronize()
+    ktimes = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) * (len(v) / 3.0) for k, v in _lib.TIMING.items()}
+    kcalls = {k: len(v) / 3.0 for k, v in _lib.TIMING.items()}
+    _lib.TIMING = None
+
+    pk = peaks()
+    evals = N_RAND * (N_SAMPLES + N_SAMPLES + N_IMPORTANCE)
+    if precision == "tc":
+        t_fwd = ktimes.get("swnerf_tc_mlp_fwd", 0.0)
+        t_bwd = ktimes.get("swnerf_tc_mlp_bwd", 0.0)
+        # dominant kernel = fused forward (2 launches/step: coarse 64 + fine 192 samples per ray)
+        ach = FLOP_PER_EVAL_FWD * evals / (t_fwd * 1e-3) / 1e12 if t_fwd > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "swnerf_tc_mlp_fwd (fused PE + 8x256 MLP, tcgen05)",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                "peak_src": pk["src"] + " cuBLAS bf16 (sustained: kernel timed inside a long step)",
+                "ms_per_step": t_fwd,
+                "bwd": {"ms_per_step": t_bwd,
+                        "achieved": 2 * FLOP_PER_EVAL_FWD * evals / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0}}
+    else:
+        t_mm = ktimes.get("swnerf_sgemm", 0.0)
+        ach = 3 * FLOP_PER_EVAL_FWD * evals / (t_mm * 1e-3) / 1e12 if t_mm > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "swnerf_sgemm (fp32 SIMT check path; not the tensor-core kernel)",
+                "achieved": ach, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                "peak_src": pk["src"], "ms_per_step": t_mm}
+
+    extra = {}
+    if args.render_frame and rank == 0:
+        H = W = 800
+        frame = torch.from_numpy(O.blender_rays(H * W, 77)).to(dev)
+        kwt = dict(kw); kwt["perturb"] = 0.0
+        with torch.no_grad():
+            def frame_fn(_):
+                lo, hi = parallel.shard_bounds(H * W, 0, 1)
+                return S.batchify_rays(frame[lo:hi], 1024 * 32, **kwt)["rgb_map"]
+            frame_fn(0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); frame_fn(0); frame_fn(1); e1.record(); torch.cuda.synchronize()
+        extra["render_ms_per_frame_800x800_1gpu"] = e0.elapsed_time(e1) / 2
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            rps, spp = cpu_reference_run(3, 1, args.cpu_sample_rays, threads)
+            cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
+                   "sample": "%d rays/step x 3 steps of the same training step (fwd+bwd+Adam), oracle port, torch "
+                             "CPU fp32" % args.cpu_sample_rays}
+        rays_total = N_RAND * world * args.steps
+        line = {"metric": "train_rays_per_s", "value": rays_total / (ms * 1e-3), "unit": "rays/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f16 operands / f32 accumulate (tcgen05)" if precision == "tc" else "f32",
+                "data": "synthetic", "config": config, "precision_mode": precision,
+                "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s",
+                        "h2d_bytes_per_step": N_RAND * (11 + 3) * 4, "d2h_bytes_per_step": 4,
+                        "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
+                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "kernel_ms_per_step": ktimes, "kernel_calls_per_step": kcalls}
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,139 @@
+/* swnerf_b200 - C ABI of the B200-native SW-NeRF per-ray volumetric rendering path.
+ *
+ * Drop-in boundary.  The reference has no FFI of its own for this path: its seam is
+ * the Python surface `embedder.py`, `model.py`, `ray.py` and the runner functions
+ * `run_network / render_rays / create_nerf`; its only native interface is the (dead) torchsearchsorted
+ * extension `void searchsorted_cuda_wrapper(at::Tensor a, at::Tensor v, at::Tensor res, bool side_left)`
+ * (d_nerf/torchsearchsorted/src/cuda/searchsorted_cuda_wrapper.cpp:5-19).  This header is what a
+ * ctypes / pybind binding on the reference side binds instead (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *  - plain pointers and sizes, no torch types.  Every pointer is a DEVICE pointer to fp32 (or int64 /
+ *    fp16 where stated), row-major contiguous; the caller owns and allocates every buffer, exactly like
+ *    the reference extension whose `out` is caller-allocated (searchsorted.py:32-38).
+ *  - `stream` is a cudaStream_t passed as void*; all work is stream-ordered, nothing synchronises.
+ *  - return 0 on success; otherwise an error code, with the message in swnerf_last_error()
+ *    (thread-local).  Bad arguments are rejected, never silently fixed.
+ *  - `rays` is the reference's flat ray batch `[N, ray_stride]` (nerf/run.py:152-158: o3 d3 near far
+ *    [time] viewdir3); columns are addressed by `d_col`, `near_col`, `view_col`.
+ */
+#ifndef SWNERF_B200_H_
+#define SWNERF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SWNERF_B200_VERSION 100
+
+/* ---- library ---- */
+int swnerf_version(void);
+const char* swnerf_last_error(void);
+/* 0 iff the current device is sm_100 (B200). */
+int swnerf_device_ok(void);
+
+/* ---- a13: torchsearchsorted.searchsorted (searchsorted.py:20-52, searchsorted_cuda_kernel.cu:83-107).
+ * a[nrow_a, ncol_a] sorted rows, v[nrow_v, ncol_v]; out[max(nrow_a,nrow_v), ncol_v] int64 ==
+ * np.searchsorted(a[row], v[row], side).  nrow_a / nrow_v may be 1 (row broadcast). */
+int swnerf_searchsorted(const float* a, const float* v, int64_t* out, int64_t nrow_a, int64_t nrow_v,
+                        int64_t ncol_a, int64_t ncol_v, int side_left, void* stream);
+
+/* ---- a2: stratified z-values (nerf/run.py:361-383).  near/far are rays[:, near_col], rays[:, near_col+1].
+ * perturb != 0 consumes t_rand[N, S] in [0,1) (the caller draws it, e.g. torch.rand, so the generator
+ * stream matches the reference's torch.rand(z_vals.shape)). */
+int swnerf_stratified_z(const float* rays, int ray_stride, int near_col, const float* t_rand, float* z_vals,
+                        int64_t n_rays, int n_samples, int lindisp, int perturb, void* stream);
+
+/* ---- a4: Embedder.embed (embedder.py:33-42) and its gradient.  y[rows, dims*(1+2L)]. */
+int swnerf_embed_fwd(const float* x, float* y, int64_t rows, int dims, int L, void* stream);
+int swnerf_embed_bwd(const float* x, const float* dy, float* dx, int64_t rows, int dims, int L, void* stream);
+
+/* ---- a3+a4+a5: points o + d*z, PE of points and of the per-ray unit viewdir, concatenated
+ * (nerf/run.py:385, :76-83) -> out[N*S, out_stride] fp32.  view_col < 0: no viewdirs; L < 0: identity. */
+int swnerf_encode_points(const float* rays, int ray_stride, int view_col, const float* z_vals, float* out,
+                         int64_t n_rays, int n_samples, int L_pos, int L_dir, int out_stride, void* stream);
+
+/* ---- a8: raw2outputs (ray.py:155-198).  raw[N,S,4], z_vals[N,S], rays_d = rays[:, d_col:d_col+3],
+ * noise[N,S] (already scaled by raw_noise_std) or NULL. */
+int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+                         const float* noise, int white_bkgd, int64_t n_rays, int n_samples, float* rgb_map,
+                         float* disp_map, float* acc_map, float* weights, float* depth_map, void* stream);
+/* autograd of the above: any of g_* may be NULL (= zero); g_disp needs the saved acc/depth maps. */
+int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+                         const float* noise, int white_bkgd, int64_t n_rays, int n_samples, const float* g_rgb,
+                         const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
+                         const float* acc_map, const float* depth_map, float* d_raw, void* stream);
+
+/* ---- a9: sample_pdf (ray.py:96-153).  bins[N,n_bins]; give weights[N,n_bins-1] OR a ready cdf[N,n_bins]
+ * (the bit-exact index test entry).  det: u = linspace(0,1,n_samples); else u[N,n_samples] from the caller.
+ * inds (optional) receives torch.searchsorted(cdf, u, right=True) as int64. */
+int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf, const float* u, int det,
+                      int64_t n_rays, int n_bins, int n_samples, float* samples, int64_t* inds, void* stream);
+
+/* ---- a9+a10+a11 fused (nerf/run.py:396-400, 416): z_mid bins, sample_pdf on weights[:,1:-1],
+ * z_fine = sort(cat(z_vals, z_samples)), z_std = std(z_samples, unbiased=False).  z_samples, z_std optional. */
+int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
+                    int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream);
+
+/* ---- a6 (check path): fp32 SIMT GEMM with the nn.Linear epilogue (model.py:43-57).
+ *  op 0: C[M,N] = A[M,K] . B[N,K]^T  (+bias[N]) (+C if accumulate) (relu)          forward  x W^T
+ *  op 1: C[M,N] = A[M,K] . B[K,N]    (+C if accumulate) (zero where mask[m,n] <= 0)  dgrad    dy W
+ *  op 2: C[M,N] (+)= A[K,M]^T . B[K,N]                                              wgrad    dy^T x */
+int swnerf_sgemm(int op, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
+                 int64_t N, int64_t K, const float* bias, int accumulate, int relu, const float* mask,
+                 int64_t ldmask, void* stream);
+/* out[cols] (+)= sum over rows of x[rows, ld]  (bias gradients). */
+int swnerf_colsum(const float* x, int64_t ld, int64_t rows, int cols, float* out, int accumulate, void* stream);
+
+/* ---- a3+a4+a5+a6 fused, tcgen05 (the hot kernel): see the second half of this header. ---- */
+
+/* Geometry of the fused 8x256 skip MLP (model.py:11-37 with D=8, W=256, skips=[4], use_viewdirs=True,
+ * PE L=10/4 -> input_ch 63 / input_ch_views 27).  Other shapes run through swnerf_sgemm. */
+#define SWNERF_TC_TILE 128            /* sample rows per tile */
+#define SWNERF_TC_W 256
+#define SWNERF_TC_NPARAM 24           /* state_dict tensors, order below */
+
+/* Parameter pointer order for `params` / `grads` (state_dict names, model.py:22-37):
+ *   [2i], [2i+1]  pts_linears.i.weight / .bias   (i = 0..7)
+ *   [16],[17]     views_linears.0.weight / .bias
+ *   [18],[19]     feature_linear.weight / .bias
+ *   [20],[21]     alpha_linear.weight / .bias
+ *   [22],[23]     rgb_linear.weight / .bias                                                          */
+
+/* Bytes of the packed fp16 weight image (UMMA-canonical, 128B-swizzled K-major chunks + fp32 biases)
+ * the fused kernels stream; and of the transposed image used by the backward-data kernel. */
+int64_t swnerf_tc_packed_bytes(void);
+/* Repack fp32 master weights (24 device pointers in a HOST array) into the packed image.  Also folds
+ * feature_linear into views_linears (no nonlinearity between them, model.py:50-55). */
+int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream);
+
+/* Workspace bytes per call for n_points sample rows: saved activations (training only). */
+int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training);
+
+/* Fused forward: for every ray n and sample s: p = o + d*z[n,s]; x = [PE10(p) | PE4(viewdir)];
+ * raw[n,s,:] = MLP(x).  rays[N, ray_stride] as in nerf/run.py:152-158.  If training != 0 the
+ * post-ReLU activations needed by the backward are written to `workspace`. */
+int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
+                      int n_samples, const void* packed, float* raw, void* workspace, int training,
+                      void* stream);
+
+/* Fused backward: d_raw[N,S,4] -> fp32 gradients of the 24 parameter tensors, ACCUMULATED into
+ * grads[i] (so coarse+fine passes and the flat all-reduce buffer need no extra copy).  `packed_t`
+ * is the transposed weight image from swnerf_tc_pack_weights_t.  grad_scale multiplies d_raw before
+ * the fp16 conversion (power of two; divided out again in the fp32 epilogue). */
+int64_t swnerf_tc_packed_t_bytes(void);
+int swnerf_tc_pack_weights_t(const float* const* params, void* packed_t, void* stream);
+int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
+                      const void* packed_t, const float* const* params, void* workspace,
+                      float* const* grads, float grad_scale, void* stream);
+
+/* Number of kernels the library has launched on this thread since the last reset (bench.py's
+ * gpu_launches). */
+int64_t swnerf_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SWNERF_B200_H_ */

@@ -388,6 +388,17 @@ def make_params(shapes: Dict[str, Tuple[int, ...]], seed: int, gain: float = 1.0
             fan_in = shapes[wname][1]
         b = gain / math.sqrt(fan_in)
         out[name] = torch.from_numpy(rs.uniform(-b, b, size=sh).astype(np.float32))
+    # The default-init net renders an empty scene (sigma ~ 0 +- 0.05): every map is degenerate.
+    # Scale the two heads so that sigma ~ 0.5 +- 3 and rgb logits ~ +-2: a non-trivial synthetic scene.
+    for name in out:
+        if name.endswith("alpha_linear.weight"):
+            out[name] = out[name] * 24.0
+        elif name.endswith("alpha_linear.bias"):
+            out[name] = out[name] * 0.0 + 0.5
+        elif name.endswith("rgb_linear.weight"):
+            out[name] = out[name] * 6.0
+        elif name.endswith("_time_out.weight"):
+            out[name] = out[name] * 2.0
     return out
 
 

@@ -1,0 +1,53 @@
+// Shared helpers for the swnerf_b200 C-ABI library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define SWNERF_OK 0
+#define SWNERF_ERR_ARG 1
+#define SWNERF_ERR_CUDA 2
+#define SWNERF_ERR_UNSUPPORTED 3
+
+namespace swnerf {
+
+// thread-local last error message (include/swnerf_b200.h: swnerf_last_error)
+char* err_buf();
+int set_err(int code, const char* fmt, ...);
+int check_launch(const char* what);
+int sm_count();
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+#define SW_REQUIRE(cond, ...)                                          \
+  do {                                                                 \
+    if (!(cond)) return swnerf::set_err(SWNERF_ERR_ARG, __VA_ARGS__);  \
+  } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// inclusive warp scan (product / sum)
+__device__ __forceinline__ float warp_scan_mul(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v *= t;
+  }
+  return v;
+}
+__device__ __forceinline__ float warp_scan_add(float v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+}  // namespace swnerf

@@ -1,0 +1,580 @@
+// HBM-bound per-ray kernels: stratified sampling, positional encoding, alpha compositing
+// (forward / backward), hierarchical resampling (pdf -> cdf -> searchsorted -> lerp -> sort)
+// and the torchsearchsorted-compatible batched binary search.
+//
+// Reference behaviour restated (never copied): nerf/run.py:361-385 (sampling, points),
+// embedder.py:12-59, ray.py:96-153 (sample_pdf), ray.py:155-198 (raw2outputs),
+// nerf/run.py:400,416 (sort, z_std), d_nerf/torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu.
+//
+// Mapping: one warp per ray, lanes stride the samples (coalesced float4 / float loads),
+// transmittance and cdf by warp shuffles scans with a running carry, so any S works.
+#include "common.cuh"
+#include "../../include/swnerf_b200.h"
+
+namespace swnerf {
+
+constexpr int kWarpsPerBlock = 8;
+
+// ---------------------------------------------------------------------------------------------
+// a2  stratified z-values                                    nerf/run.py:361-383
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float linspace01(int i, int S) {
+  // torch.linspace(0, 1, S): symmetric evaluation, step = 1/(S-1)
+  if (S == 1) return 0.f;
+  float step = 1.0f / (float)(S - 1);
+  return (i < S / 2) ? __fmul_rn(step, (float)i) : __fsub_rn(1.0f, __fmul_rn(step, (float)(S - 1 - i)));
+}
+
+__device__ __forceinline__ float z_at(float nearv, float farv, int i, int S, int lindisp) {
+  float t = linspace01(i, S);
+  if (!lindisp) return __fadd_rn(__fmul_rn(nearv, __fsub_rn(1.f, t)), __fmul_rn(farv, t));
+  float a = __fmul_rn(__fdiv_rn(1.f, nearv), __fsub_rn(1.f, t));
+  float b = __fmul_rn(__fdiv_rn(1.f, farv), t);
+  return __fdiv_rn(1.f, __fadd_rn(a, b));
+}
+
+__global__ void stratified_kernel(const float* __restrict__ rays, int ray_stride, int near_col,
+                                  const float* __restrict__ t_rand, float* __restrict__ z_out,
+                                  int64_t N, int S, int lindisp, int perturb) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * S) return;
+  int64_t r = idx / S;
+  int i = (int)(idx - r * S);
+  float nearv = rays[r * ray_stride + near_col], farv = rays[r * ray_stride + near_col + 1];
+  float z = z_at(nearv, farv, i, S, lindisp);
+  if (perturb) {
+    float zl = (i > 0) ? z_at(nearv, farv, i - 1, S, lindisp) : z;
+    float zu = (i < S - 1) ? z_at(nearv, farv, i + 1, S, lindisp) : z;
+    float lower = (i > 0) ? __fmul_rn(0.5f, __fadd_rn(z, zl)) : z;
+    float upper = (i < S - 1) ? __fmul_rn(0.5f, __fadd_rn(zu, z)) : z;
+    z = __fadd_rn(lower, __fmul_rn(__fsub_rn(upper, lower), t_rand[idx]));
+  }
+  z_out[idx] = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a4  positional encoding, standalone (Embedder drop-in)       embedder.py:33-42
+// ---------------------------------------------------------------------------------------------
+__global__ void embed_fwd_kernel(const float* __restrict__ x, float* __restrict__ y, int64_t M, int d, int L) {
+  int od = d * (1 + 2 * L);
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * od) return;
+  int64_t r = idx / od;
+  int c = (int)(idx - r * od);
+  int blk = c / d, j = c - blk * d;
+  float v = x[r * d + j];
+  if (blk > 0) {
+    int k = (blk - 1) >> 1;
+    float a = v * exp2f((float)k);            // exact power-of-two scaling
+    v = ((blk - 1) & 1) ? cosf(a) : sinf(a);
+  }
+  y[idx] = v;
+}
+
+__global__ void embed_bwd_kernel(const float* __restrict__ x, const float* __restrict__ dy,
+                                 float* __restrict__ dx, int64_t M, int d, int L) {
+  int od = d * (1 + 2 * L);
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= M * d) return;
+  int64_t r = idx / d;
+  int j = (int)(idx - r * d);
+  float v = x[idx];
+  const float* g = dy + r * od;
+  float acc = g[j];
+  for (int k = 0; k < L; ++k) {
+    float f = exp2f((float)k);
+    float s, c;
+    sincosf(v * f, &s, &c);
+    acc += f * (c * g[d * (1 + 2 * k) + j] - s * g[d * (2 + 2 * k) + j]);
+  }
+  dx[idx] = acc;
+}
+
+// a3 + a4 fused for the fp32 layered path: rays + z -> [N*S, in_pts + in_views] embedded rows
+// (nerf/run.py:385 points, :76-83 embed + expand viewdirs + cat).
+__global__ void encode_points_kernel(const float* __restrict__ rays, int ray_stride, int view_col,
+                                     const float* __restrict__ z, float* __restrict__ out,
+                                     int64_t N, int S, int L_pos, int L_dir, int out_stride) {
+  int in_pts = 3 * (1 + 2 * (L_pos < 0 ? 0 : L_pos));
+  int in_views = (view_col >= 0) ? 3 * (1 + 2 * (L_dir < 0 ? 0 : L_dir)) : 0;
+  int od = in_pts + in_views;
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= N * S * od) return;
+  int64_t row = idx / od;
+  int c = (int)(idx - row * od);
+  int64_t r = row / S;
+  const float* ray = rays + r * ray_stride;
+  float v;
+  int L, cc;
+  if (c < in_pts) {
+    cc = c; L = L_pos;
+    int j = cc % 3;
+    v = __fadd_rn(ray[j], __fmul_rn(ray[3 + j], z[row]));   // o + d*z, no fma (matches eager mul,add)
+  } else {
+    cc = c - in_pts; L = L_dir;
+    v = ray[view_col + cc % 3];
+  }
+  int blk = cc / 3;
+  if (blk > 0 && L > 0) {
+    int k = (blk - 1) >> 1;
+    float a = v * exp2f((float)k);
+    v = ((blk - 1) & 1) ? cosf(a) : sinf(a);
+  }
+  out[row * out_stride + c] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8  raw2outputs forward                                     ray.py:168-196
+// ---------------------------------------------------------------------------------------------
+struct RayGeom {
+  float norm;
+};
+
+__device__ __forceinline__ float ray_norm(const float* __restrict__ rays, int64_t r, int ray_stride, int d_col) {
+  const float* d = rays + r * ray_stride + d_col;
+  float x = d[0], y = d[1], z = d[2];
+  return sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z)));
+}
+
+// per-sample quantities shared by forward and backward
+__device__ __forceinline__ void sample_alpha(float sigma, float noise, float zi, float zn, bool last, float norm,
+                                             float& dist, float& e, float& alpha, float& u, bool& on) {
+  dist = last ? 1e10f : __fsub_rn(zn, zi);
+  dist = __fmul_rn(dist, norm);
+  float s = sigma + noise;
+  on = s > 0.f;
+  s = on ? s : 0.f;
+  e = expf(-__fmul_rn(s, dist));          // exp(-relu(sigma)*dists)
+  alpha = __fsub_rn(1.f, e);
+  u = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
+                     int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
+                     float* __restrict__ rgb_map, float* __restrict__ disp_map, float* __restrict__ acc_map,
+                     float* __restrict__ weights, float* __restrict__ depth_map) {
+  int lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
+  const float* zr = z + r * S;
+  const float* nr = noise ? noise + r * S : nullptr;
+  float norm = ray_norm(rays, r, ray_stride, d_col);
+  float carry = 1.f;
+  float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
+  for (int base = 0; base < S; base += 32) {
+    int i = base + lane;
+    bool valid = i < S;
+    float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float zi = valid ? __ldg(zr + i) : 0.f;
+    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
+    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
+    float dist, e, alpha, u; bool on;
+    sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
+    if (!valid) { alpha = 0.f; u = 1.f; }
+    float incl = warp_scan_mul(u, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float T = carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    float w = alpha * T;
+    if (valid) {
+      weights[r * S + i] = w;
+      sr += w * sigmoidf_(q.x);
+      sg += w * sigmoidf_(q.y);
+      sb += w * sigmoidf_(q.z);
+      sd += w * zi;
+      sa += w;
+    }
+  }
+  sr = warp_sum(sr); sg = warp_sum(sg); sb = warp_sum(sb); sd = warp_sum(sd); sa = warp_sum(sa);
+  if (lane == 0) {
+    if (white_bkgd) { float bg = 1.f - sa; sr += bg; sg += bg; sb += bg; }
+    rgb_map[r * 3 + 0] = sr; rgb_map[r * 3 + 1] = sg; rgb_map[r * 3 + 2] = sb;
+    depth_map[r] = sd;
+    acc_map[r] = sa;
+    // torch.max(1e-10, NaN) propagates the 0/0 NaN of an empty ray (ray.py:192); fmaxf would not.
+    float q = sd / sa;
+    disp_map[r] = (q != q) ? q : 1.f / fmaxf(1e-10f, q);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a8  raw2outputs backward (autograd of ray.py:168-196)
+//   G_i = dL/dw_i = g_rgb.c_i + g_depth z_i + g_acc' + g_w[i]
+//   dL/dalpha_i = G_i T_i - R_i / u_i,  R_i = sum_{k>i} G_k w_k   (T_k carries the factor u_i)
+//   dL/dsigma_i = dL/dalpha_i * dist_i * e_i * [sigma_i + noise_i > 0],   e_i = exp(-relu(.) dist_i)
+//   dL/draw_rgb = w_i g_rgb c (1 - c)
+// Two sweeps over the ray (second one hits L1): sweep A gets total = sum_k G_k w_k, sweep B the
+// running prefix so that R_i = total - prefix_i.  e_i/u_i <= 1 is formed first so that a tiny u_i
+// never amplifies the rounding of R_i.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
+                     int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
+                     const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
+                     const float* __restrict__ g_w, const float* __restrict__ g_depth,
+                     const float* __restrict__ acc_map, const float* __restrict__ depth_map,
+                     float* __restrict__ d_raw) {
+  int lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (r >= N) return;
+  const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
+  float4* out4 = reinterpret_cast<float4*>(d_raw) + r * S;
+  const float* zr = z + r * S;
+  const float* nr = noise ? noise + r * S : nullptr;
+  const float* gw = g_w ? g_w + r * S : nullptr;
+  float norm = ray_norm(rays, r, ray_stride, d_col);
+  float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
+  if (g_rgb) { gr = g_rgb[r * 3]; gg = g_rgb[r * 3 + 1]; gb = g_rgb[r * 3 + 2]; }
+  if (g_depth) gd = g_depth[r];
+  if (g_acc) ga = g_acc[r];
+  if (g_disp) {   // disp = 1 / max(1e-10, depth/acc)
+    float acc = acc_map[r], dep = depth_map[r];
+    float q = dep / acc;
+    if (q > 1e-10f) {
+      float gq = -g_disp[r] / (q * q);
+      gd += gq / acc;
+      ga += -gq * dep / (acc * acc);
+    }
+  }
+  if (white_bkgd) ga -= (gr + gg + gb);
+
+  float total = 0.f;
+  for (int sweep = 0; sweep < 2; ++sweep) {
+    float carry = 1.f, pcarry = 0.f, part = 0.f;
+    for (int base = 0; base < S; base += 32) {
+      int i = base + lane;
+      bool valid = i < S;
+      float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      float zi = valid ? __ldg(zr + i) : 0.f;
+      float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
+      float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
+      float dist, e, alpha, u; bool on;
+      sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
+      if (!valid) { alpha = 0.f; u = 1.f; }
+      float incl = warp_scan_mul(u, lane);
+      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+      if (lane == 0) excl = 1.f;
+      float T = carry * excl;
+      carry *= __shfl_sync(0xffffffffu, incl, 31);
+      float w = alpha * T;
+      float cr = sigmoidf_(q.x), cg = sigmoidf_(q.y), cb = sigmoidf_(q.z);
+      float G = gr * cr + gg * cg + gb * cb + gd * zi + ga + ((valid && gw) ? __ldg(gw + i) : 0.f);
+      float Gw = valid ? G * w : 0.f;
+      if (sweep == 0) {
+        part += Gw;
+      } else {
+        float pin = warp_scan_add(Gw, lane);
+        float prefix = pcarry + pin;                 // inclusive prefix of G_k w_k
+        pcarry += __shfl_sync(0xffffffffu, pin, 31);
+        float R = total - prefix;
+        float dalpha_e = G * T * e - R * (e / u);    // dL/dalpha * e
+        float dsig = on ? dalpha_e * dist : 0.f;
+        if (valid) {
+          float4 o;
+          o.x = w * gr * cr * (1.f - cr);
+          o.y = w * gg * cg * (1.f - cg);
+          o.z = w * gb * cb * (1.f - cb);
+          o.w = dsig;
+          out4[i] = o;
+        }
+      }
+    }
+    if (sweep == 0) total = warp_sum(part);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// a9/a10/a11  hierarchical resampling                         ray.py:96-153, nerf/run.py:396-400,416
+// One warp per ray.  smem per warp: cdf[M] | bins[M] | sort buffer[P] (P = pow2 >= S + Ni).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int upper_bound_smem(const float* a, int n, float v) {
+  // number of elements <= v  == torch.searchsorted(right=True)
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] <= v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ int lower_bound_smem(const float* a, int n, float v) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (a[mid] < v) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// build cdf[0..M-1] in smem from weights w[0..M-2]  (ray.py:111-114); all lanes participate
+__device__ void warp_build_cdf(const float* __restrict__ w, int M, float* cdf, int lane) {
+  float part = 0.f;
+  for (int i = lane; i < M - 1; i += 32) part += __fadd_rn(__ldg(w + i), 1e-5f);
+  // torch.sum order differs (pairwise); agreement is to rounding, hence "bit-exact given identical CDFs"
+  float tot = warp_sum(part);
+  float carry = 0.f;
+  if (lane == 0) cdf[0] = 0.f;
+  for (int base = 0; base < M - 1; base += 32) {
+    int i = base + lane;
+    float p = (i < M - 1) ? __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), tot) : 0.f;
+    float inc = warp_scan_add(p, lane);
+    if (i < M - 1) cdf[i + 1] = carry + inc;
+    carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins, int M, float u, int* ind_out) {
+  int ind = upper_bound_smem(cdf, M, u);                       // ray.py:136
+  int below = max(0, ind - 1), above = min(M - 1, ind);        // ray.py:137-138
+  float cb = cdf[below], ca = cdf[above];
+  float bb = bins[below], ba = bins[above];
+  float denom = __fsub_rn(ca, cb);
+  if (denom < 1e-5f) denom = 1.f;                              // ray.py:149
+  float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  *ind_out = ind;
+  return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));       // ray.py:151
+}
+
+__device__ __forceinline__ float det_u(int j, int Ns) { return linspace01(j, Ns); }
+
+// Generic sample_pdf(bins[N,M], weights[N,M-1] | cdf[N,M]) -> samples[N,Ns] (+ inds int64)
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+sample_pdf_kernel(const float* __restrict__ bins, const float* __restrict__ weights, const float* __restrict__ cdf_in,
+                  const float* __restrict__ u_in, int det, int64_t N, int M, int Ns,
+                  float* __restrict__ samples, int64_t* __restrict__ inds) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= N) return;
+  float* cdf = smem + (size_t)warp * 2 * M;
+  float* bs = cdf + M;
+  for (int i = lane; i < M; i += 32) bs[i] = __ldg(bins + r * M + i);
+  if (cdf_in) {
+    for (int i = lane; i < M; i += 32) cdf[i] = __ldg(cdf_in + r * M + i);
+    __syncwarp();
+  } else {
+    warp_build_cdf(weights + r * (M - 1), M, cdf, lane);
+  }
+  __syncwarp();
+  for (int j = lane; j < Ns; j += 32) {
+    float u = u_in ? __ldg(u_in + r * Ns + j) : det_u(j, Ns);
+    int ind;
+    float s = invert_cdf(cdf, bs, M, u, &ind);
+    samples[r * Ns + j] = s;
+    if (inds) inds[r * Ns + j] = (int64_t)ind;
+  }
+  (void)det;
+}
+
+__device__ void warp_bitonic_sort(float* a, int P, int lane) {
+  for (int k = 2; k <= P; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < P / 2; t += 32) {
+        int i = 2 * t - (t & (j - 1));        // index with bit j clear
+        int l = i + j;
+        bool up = ((i & k) == 0);
+        float x = a[i], y = a[l];
+        if ((x > y) == up) { a[i] = y; a[l] = x; }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+// Fused: z_mid bins + sample_pdf on weights[:,1:-1] + sort(cat(z_vals, z_samples)) + z_std
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
+                int64_t N, int S, int Ni, int P, float* __restrict__ z_samples, float* __restrict__ z_fine,
+                float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= N) return;
+  int M = S - 1;                                     // bins = z_mid (S-1), weights[1:-1] (S-2)
+  float* cdf = smem + (size_t)warp * (2 * M + P);
+  float* bs = cdf + M;
+  float* buf = bs + M;
+  const float* zr = z_vals + r * S;
+  for (int i = lane; i < S; i += 32) {
+    float zi = __ldg(zr + i);
+    buf[i] = zi;
+    if (i < M) bs[i] = __fmul_rn(0.5f, __fadd_rn(__ldg(zr + i + 1), zi));    // run.py:396
+  }
+  warp_build_cdf(weights + r * S + 1, M, cdf, lane);
+  __syncwarp();
+  float s1 = 0.f;
+  for (int j = lane; j < Ni; j += 32) {
+    float u = u_in ? __ldg(u_in + r * Ni + j) : det_u(j, Ni);
+    int ind;
+    float s = invert_cdf(cdf, bs, M, u, &ind);
+    buf[S + j] = s;
+    if (z_samples) z_samples[r * Ni + j] = s;
+    s1 += s;
+  }
+  for (int i = S + Ni + lane; i < P; i += 32) buf[i] = __int_as_float(0x7f800000);   // +inf padding
+  // population std (torch.std unbiased=False): two-pass for accuracy
+  float mean = warp_sum(s1) / (float)Ni;
+  __syncwarp();
+  float s2 = 0.f;
+  for (int j = lane; j < Ni; j += 32) { float d = buf[S + j] - mean; s2 += d * d; }
+  s2 = warp_sum(s2);
+  if (lane == 0 && z_std) z_std[r] = sqrtf(s2 / (float)Ni);
+  __syncwarp();
+  warp_bitonic_sort(buf, P, lane);
+  for (int i = lane; i < S + Ni; i += 32) z_fine[r * (S + Ni) + i] = buf[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// a13  torchsearchsorted-compatible batched search              searchsorted_cuda_kernel.cu:83-107
+// ---------------------------------------------------------------------------------------------
+__global__ void searchsorted_kernel(const float* __restrict__ a, const float* __restrict__ v, int64_t* __restrict__ out,
+                                    int64_t nrow_res, int64_t nrow_a, int64_t nrow_v, int64_t ncol_a, int64_t ncol_v,
+                                    int side_left) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= nrow_res * ncol_v) return;
+  int64_t row = idx / ncol_v, col = idx - row * ncol_v;
+  const float* ar = a + ((nrow_a == 1) ? 0 : row) * ncol_a;
+  float val = v[((nrow_v == 1) ? 0 : row) * ncol_v + col];
+  int64_t lo = 0, hi = ncol_a;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    float am = __ldg(ar + mid);
+    bool go_right = side_left ? (am < val) : (am <= val);
+    if (go_right) lo = mid + 1; else hi = mid;
+  }
+  out[idx] = lo;
+}
+
+static inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+}  // namespace swnerf
+
+using namespace swnerf;
+
+extern "C" {
+
+int swnerf_stratified_z(const float* rays, int ray_stride, int near_col, const float* t_rand, float* z_vals,
+                        int64_t n_rays, int n_samples, int lindisp, int perturb, void* stream) {
+  SW_REQUIRE(rays && z_vals, "stratified_z: null pointer");
+  SW_REQUIRE(n_samples >= 1 && n_rays >= 0, "stratified_z: bad sizes");
+  SW_REQUIRE(!perturb || t_rand, "stratified_z: perturb requires t_rand");
+  if (n_rays == 0) return SWNERF_OK;
+  int64_t tot = n_rays * n_samples;
+  stratified_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      rays, ray_stride, near_col, t_rand, z_vals, n_rays, n_samples, lindisp, perturb);
+  return check_launch("stratified_z");
+}
+
+int swnerf_embed_fwd(const float* x, float* y, int64_t rows, int dims, int L, void* stream) {
+  SW_REQUIRE(x && y, "embed_fwd: null pointer");
+  SW_REQUIRE(dims >= 1 && L >= 0 && L <= 32, "embed_fwd: bad dims/L");
+  if (rows == 0) return SWNERF_OK;
+  int64_t tot = rows * dims * (1 + 2 * L);
+  embed_fwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, y, rows, dims, L);
+  return check_launch("embed_fwd");
+}
+
+int swnerf_embed_bwd(const float* x, const float* dy, float* dx, int64_t rows, int dims, int L, void* stream) {
+  SW_REQUIRE(x && dy && dx, "embed_bwd: null pointer");
+  SW_REQUIRE(dims >= 1 && L >= 0 && L <= 32, "embed_bwd: bad dims/L");
+  if (rows == 0) return SWNERF_OK;
+  int64_t tot = rows * dims;
+  embed_bwd_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, dy, dx, rows, dims, L);
+  return check_launch("embed_bwd");
+}
+
+int swnerf_encode_points(const float* rays, int ray_stride, int view_col, const float* z_vals, float* out,
+                         int64_t n_rays, int n_samples, int L_pos, int L_dir, int out_stride, void* stream) {
+  SW_REQUIRE(rays && z_vals && out, "encode_points: null pointer");
+  SW_REQUIRE(L_pos <= 32 && L_dir <= 32, "encode_points: L too large");
+  if (n_rays == 0) return SWNERF_OK;
+  int od = 3 * (1 + 2 * (L_pos < 0 ? 0 : L_pos)) + (view_col >= 0 ? 3 * (1 + 2 * (L_dir < 0 ? 0 : L_dir)) : 0);
+  SW_REQUIRE(out_stride >= od, "encode_points: out_stride < embedded width");
+  int64_t tot = n_rays * n_samples * od;
+  encode_points_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      rays, ray_stride, view_col, z_vals, out, n_rays, n_samples, L_pos, L_dir, out_stride);
+  return check_launch("encode_points");
+}
+
+int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+                         const float* noise, int white_bkgd, int64_t n_rays, int n_samples, float* rgb_map,
+                         float* disp_map, float* acc_map, float* weights, float* depth_map, void* stream) {
+  SW_REQUIRE(raw && z_vals && rays && rgb_map && disp_map && acc_map && weights && depth_map,
+             "composite_fwd: null pointer");
+  SW_REQUIRE(aligned16(raw), "composite_fwd: raw must be 16-byte aligned");
+  SW_REQUIRE(n_samples >= 1, "composite_fwd: n_samples < 1");
+  if (n_rays == 0) return SWNERF_OK;
+  unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, rgb_map, disp_map, acc_map,
+      weights, depth_map);
+  return check_launch("composite_fwd");
+}
+
+int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+                         const float* noise, int white_bkgd, int64_t n_rays, int n_samples, const float* g_rgb,
+                         const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
+                         const float* acc_map, const float* depth_map, float* d_raw, void* stream) {
+  SW_REQUIRE(raw && z_vals && rays && d_raw, "composite_bwd: null pointer");
+  SW_REQUIRE(aligned16(raw) && aligned16(d_raw), "composite_bwd: raw/d_raw must be 16-byte aligned");
+  SW_REQUIRE(!g_disp || (acc_map && depth_map), "composite_bwd: g_disp needs saved acc/depth maps");
+  if (n_rays == 0) return SWNERF_OK;
+  unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  composite_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
+      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, g_rgb, g_disp, g_acc, g_weights,
+      g_depth, acc_map, depth_map, d_raw);
+  return check_launch("composite_bwd");
+}
+
+int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf, const float* u, int det,
+                      int64_t n_rays, int n_bins, int n_samples, float* samples, int64_t* inds, void* stream) {
+  SW_REQUIRE(bins && samples, "sample_pdf: null pointer");
+  SW_REQUIRE((weights != nullptr) != (cdf != nullptr), "sample_pdf: give exactly one of weights / cdf");
+  SW_REQUIRE(det || u, "sample_pdf: random mode needs caller-supplied u");
+  SW_REQUIRE(n_bins >= 2 && n_bins <= 2048 && n_samples >= 1, "sample_pdf: bad sizes");
+  if (n_rays == 0) return SWNERF_OK;
+  size_t smem = (size_t)kWarpsPerBlock * 2 * n_bins * sizeof(float);
+  unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(sample_pdf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  sample_pdf_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      bins, weights, cdf, det ? nullptr : u, det, n_rays, n_bins, n_samples, samples, inds);
+  return check_launch("sample_pdf");
+}
+
+int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
+                    int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream) {
+  SW_REQUIRE(z_vals && weights && z_fine, "resample: null pointer");
+  SW_REQUIRE(det || u, "resample: random mode needs caller-supplied u");
+  SW_REQUIRE(n_samples >= 3 && n_importance >= 1, "resample: need n_samples >= 3 and n_importance >= 1");
+  int P = next_pow2(n_samples + n_importance);
+  SW_REQUIRE(P <= 2048, "resample: n_samples + n_importance > 2048");
+  if (n_rays == 0) return SWNERF_OK;
+  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_samples - 1) + P) * sizeof(float);
+  unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  resample_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+      z_vals, weights, det ? nullptr : u, n_rays, n_samples, n_importance, P, z_samples, z_fine, z_std);
+  return check_launch("resample");
+}
+
+int swnerf_searchsorted(const float* a, const float* v, int64_t* out, int64_t nrow_a, int64_t nrow_v,
+                        int64_t ncol_a, int64_t ncol_v, int side_left, void* stream) {
+  SW_REQUIRE(a && v && out, "searchsorted: null pointer");
+  SW_REQUIRE(nrow_a == nrow_v || nrow_a == 1 || nrow_v == 1,
+             "searchsorted: `a` and `v` must have the same number of rows or one of them must have only one");
+  int64_t rows = nrow_a > nrow_v ? nrow_a : nrow_v;
+  int64_t tot = rows * ncol_v;
+  if (tot == 0) return SWNERF_OK;
+  searchsorted_kernel<<<(unsigned)((tot + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      a, v, out, rows, nrow_a, nrow_v, ncol_a, ncol_v, side_left);
+  return check_launch("searchsorted");
+}
+
+}  // extern "C"

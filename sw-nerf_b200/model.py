@@ -1,0 +1,178 @@
+"""Drop-in for the reference's model.py: vallina_NeRF, NeRFOriginal, DirectTemporalNeRF, NeRF.get_by_name.
+
+Same constructor signatures, same state_dict keys/shapes and the same default initialisation as the
+reference (model.py:10-62, 93-151, 214-296), so reference checkpoints load and vice versa.  The
+modules only HOLD fp32 master parameters (nn.Linear is used as a container); forward runs on the
+library's kernels: the fp32 SIMT GEMM chain here, or - through render.NetworkQuery - the fused
+tcgen05 kernel that takes rays instead of embedded points.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from .ops import MLPSpec
+
+
+class _NerfBase(nn.Module):
+    def _build(self, D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs, output_color_ch=3):
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views = input_ch, input_ch_views
+        self.skips, self.use_viewdirs = skips, use_viewdirs
+        self.pts_linears = nn.ModuleList(
+            [nn.Linear(input_ch, W)] +
+            [nn.Linear(W, W) if i not in self.skips else nn.Linear(W + input_ch, W) for i in range(D - 1)])
+        self.views_linears = nn.ModuleList([nn.Linear(input_ch_views + W, W // 2)])
+        if use_viewdirs:
+            self.feature_linear = nn.Linear(W, W)
+            self.alpha_linear = nn.Linear(W, 1)
+            self.rgb_linear = nn.Linear(W // 2, output_color_ch)
+        else:
+            self.output_linear = nn.Linear(W, output_ch)
+        self.output_ch = output_ch
+
+    @property
+    def spec(self) -> MLPSpec:
+        head = "viewdirs" if self.use_viewdirs else "output"
+        return MLPSpec(self.D, self.W, self.input_ch, 0, self.input_ch_views, tuple(self.skips), head,
+                       self.output_ch)
+
+    def param_list(self):
+        """Parameters in the order of include/swnerf_b200.h (trunk, views, feature, alpha, rgb)."""
+        ps = []
+        for l in self.pts_linears:
+            ps += [l.weight, l.bias]
+        if self.use_viewdirs:
+            ps += [self.views_linears[0].weight, self.views_linears[0].bias,
+                   self.feature_linear.weight, self.feature_linear.bias,
+                   self.alpha_linear.weight, self.alpha_linear.bias,
+                   self.rgb_linear.weight, self.rgb_linear.bias]
+        else:
+            ps += [self.output_linear.weight, self.output_linear.bias]
+        return ps
+
+    def tc_eligible(self) -> bool:
+        """Shape the fused tcgen05 kernels are instantiated for (configs/lego.txt: 8x256, PE 10/4)."""
+        return (self.use_viewdirs and self.D == 8 and self.W == 256 and list(self.skips) == [4]
+                and self.input_ch == 63 and self.input_ch_views == 27 and self.rgb_linear.out_features == 3)
+
+    def _forward_embedded(self, x):
+        x2 = x.reshape(-1, x.shape[-1])
+        if x2.stride(-1) != 1:
+            x2 = x2.contiguous()
+        x_pts = x2[:, :self.input_ch]
+        x_views = x2[:, self.input_ch:self.input_ch + self.input_ch_views] if self.use_viewdirs else None
+        out = ops.mlp_fp32(self.spec, x_pts, None, x_views, self.param_list())
+        return out.reshape(list(x.shape[:-1]) + [out.shape[-1]])
+
+    def load_weights_from_keras(self, weights):                                     # model.py:64-91
+        assert self.use_viewdirs, "Not implemented if use_viewdirs=False"
+        t = lambda a: torch.from_numpy(np.transpose(a))
+        for i in range(self.D):
+            self.pts_linears[i].weight.data = t(weights[2 * i])
+            self.pts_linears[i].bias.data = t(weights[2 * i + 1])
+        k = 2 * self.D
+        self.feature_linear.weight.data, self.feature_linear.bias.data = t(weights[k]), t(weights[k + 1])
+        self.views_linears[0].weight.data, self.views_linears[0].bias.data = t(weights[k + 2]), t(weights[k + 3])
+        self.rgb_linear.weight.data, self.rgb_linear.bias.data = t(weights[k + 4]), t(weights[k + 5])
+        self.alpha_linear.weight.data, self.alpha_linear.bias.data = t(weights[k + 6]), t(weights[k + 7])
+
+
+class vallina_NeRF(_NerfBase):
+    """model.py:10-62."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, output_ch=4, skips=[4], use_viewdirs=False):
+        super().__init__()
+        self._build(D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs)
+
+    def forward(self, x):
+        return self._forward_embedded(x)
+
+
+class NeRFOriginal(_NerfBase):
+    """model.py:227-296: the same network, kaiming-normal weights, forward(x, ts) -> (out, zeros)."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, input_ch_time=1, output_ch=4, skips=[4],
+                 use_viewdirs=False, memory=[], embed_fn=None, output_color_ch=3, zero_canonical=True):
+        super().__init__()
+        if any(i in memory for i in range(D - 1)):
+            raise NotImplementedError
+        self._build(D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs, output_color_ch)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')                 # model.py:270-272
+
+    def forward(self, x, ts):
+        out = self._forward_embedded(x)
+        return out, torch.zeros_like(x[..., :3])
+
+
+class DirectTemporalNeRF(nn.Module):
+    """model.py:93-151: deformation network (x, t) -> dx, then the canonical NeRFOriginal at x + dx."""
+
+    def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, input_ch_time=1, output_ch=4, skips=[4],
+                 use_viewdirs=False, memory=[], embed_fn=None, zero_canonical=True):
+        super().__init__()
+        self.D, self.W = D, W
+        self.input_ch, self.input_ch_views, self.input_ch_time = input_ch, input_ch_views, input_ch_time
+        self.skips, self.use_viewdirs, self.memory = skips, use_viewdirs, memory
+        self.embed_fn, self.zero_canonical = embed_fn, zero_canonical
+        self._occ = NeRFOriginal(D=D, W=W, input_ch=input_ch, input_ch_views=input_ch_views,
+                                 input_ch_time=input_ch_time, output_ch=output_ch, skips=skips,
+                                 use_viewdirs=use_viewdirs, memory=memory, embed_fn=embed_fn, output_color_ch=3)
+        self._time, self._time_out = self.create_time_net()
+
+    def create_time_net(self):                                                     # model.py:112-126
+        layers = [nn.Linear(self.input_ch + self.input_ch_time, self.W)]
+        for i in range(self.D - 1):
+            if i in self.memory:
+                raise NotImplementedError
+            in_channels = self.W + (self.input_ch if i in self.skips else 0)
+            layers += [nn.Linear(in_channels, self.W)]
+        return nn.ModuleList(layers), nn.Linear(self.W, 3)
+
+    @property
+    def time_spec(self) -> MLPSpec:
+        return MLPSpec(self.D, self.W, self.input_ch, self.input_ch_time, 0, tuple(self.skips), "linear", 3)
+
+    def time_param_list(self):
+        ps = []
+        for l in self._time:
+            ps += [l.weight, l.bias]
+        return ps + [self._time_out.weight, self._time_out.bias]
+
+    def query_time(self, new_pts, t, net=None, net_final=None):                    # model.py:128-136
+        return ops.mlp_fp32(self.time_spec, new_pts, t, None, self.time_param_list())
+
+    def forward(self, x, ts, cur_time=None):
+        """x: embedded [pts | views]; ts[0]: embedded time [M, input_ch_time] (all rows equal).
+        `cur_time` lets the caller pass the scalar it already holds on the host, which removes the
+        reference's two device->host syncs per query (model.py:142-144, run_dnerf.py:53-54)."""
+        x = x.reshape(-1, x.shape[-1])
+        input_pts = x[:, :self.input_ch]
+        input_views = x[:, self.input_ch:self.input_ch + self.input_ch_views]
+        t = ts[0]
+        if cur_time is None:
+            assert len(torch.unique(t[:, :1])) == 1, "Only accepts all points from same time"
+            cur_time = float(t[0, 0])
+        if cur_time == 0. and self.zero_canonical:
+            dx = torch.zeros_like(input_pts[:, :3])
+        else:
+            dx = self.query_time(input_pts, t)
+            input_pts = self.embed_fn(input_pts[:, :3] + dx)                       # model.py:148-149
+        occ = self._occ
+        out = ops.mlp_fp32(occ.spec, input_pts, None, input_views if occ.use_viewdirs else None, occ.param_list())
+        return out, dx
+
+
+class NeRF:
+    @staticmethod
+    def get_by_name(type, *args, **kwargs):                                        # model.py:214-225
+        print("NeRF type selected: %s" % type)
+        if type == "original":
+            model = NeRFOriginal(*args, **kwargs)
+        elif type == "direct_temporal":
+            model = DirectTemporalNeRF(*args, **kwargs)
+        else:
+            raise ValueError("Type %s not recognized." % type)
+        return model

@@ -1,0 +1,257 @@
+"""GPU parity of the MLP paths and of render_rays end to end (forward and backward) against the CPU
+oracle and the reference's golden vectors.
+
+Tolerances (north_star): fp32-accumulate check mode: maps <= 1e-5 relative to the map's range,
+flat gradient <= 1e-4 relative L2; fused tcgen05 mode (fp16 operands, fp32 accumulate): maps <= 1e-3,
+flat gradient <= 5e-3 relative L2 (per-element 1e-3 is not attainable with 11-bit operands)."""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+import swnerf_b200 as S
+from swnerf_b200 import ops, dnerf, tc
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def relmax(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    m = ~(torch.isnan(a) & torch.isnan(b))
+    return float((a[m] - b[m]).abs().max() / b[m].abs().max().clamp_min(1e-30))
+
+
+def rel_l2(a, b):
+    a, b = a.detach().cpu().double(), b.detach().cpu().double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def load(module, params):
+    module.load_state_dict({k: v.clone() for k, v in params.items()})
+    return module.to(DEV)
+
+
+def make_vanilla(seed_c, seed_f, precision):
+    shapes = O.mlp_param_shapes()
+    pc, pf = O.make_params(shapes, seed_c), O.make_params(shapes, seed_f)
+    mc = load(S.vallina_NeRF(8, 256, 63, 27, 5, [4], True), pc)
+    mf = load(S.vallina_NeRF(8, 256, 63, 27, 5, [4], True), pf)
+    q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], 65536, precision=precision)
+    return pc, pf, mc, mf, q
+
+
+# ---------------------------------------------------------------- a6 / a7 the MLP modules (embedded input)
+def test_mlp_modules_golden(golden):
+    g = golden("mlp")
+    p = O.make_params(O.mlp_param_shapes(), int(g["seed"]))
+    m = load(S.vallina_NeRF(8, 256, 63, 27, 5, [4], True), p)
+    assert relmax(m(T(g["x"])), torch.from_numpy(g["y_vanilla"])) < 1e-5
+    m2 = load(S.NeRFOriginal(8, 256, 63, 27, 21, 5, [4], True), p)
+    y2, z2 = m2(T(g["x"]), None)
+    assert relmax(y2, torch.from_numpy(g["y_original"])) < 1e-5 and float(z2.abs().max()) == 0
+    pn = O.make_params(O.mlp_param_shapes(input_ch_views=0, output_ch=4, use_viewdirs=False), int(g["seed_nv"]))
+    m3 = load(S.vallina_NeRF(8, 256, 63, 0, 4, [4], False), pn)
+    assert relmax(m3(T(g["x"][:, :63])), torch.from_numpy(g["y_noview"])) < 1e-5
+    pd = O.make_params(O.dnerf_param_shapes(), int(g["seed_dnerf"]))
+    emb = S.get_embedder(10, 3, 0)[0]
+    md = load(S.DirectTemporalNeRF(8, 256, 63, 27, 21, 5, [4], True, embed_fn=emb), pd)
+    pts, vd = T(g["d_pts"]), T(g["d_vd"])
+    x = torch.cat([ops.embed(pts, 10), ops.embed(vd, 4)], -1)
+    for tval, tag in [(0.37, "t037"), (0.0, "t0")]:
+        et = ops.embed(torch.full((pts.shape[0], 1), tval, device=DEV), 10)
+        out, dx = md(x, [et, et])
+        assert relmax(out, torch.from_numpy(g[f"d_out_{tag}"])) < 2e-5
+        assert relmax(dx, torch.from_numpy(g[f"d_dx_{tag}"])) < 2e-5 or tval == 0.0
+
+
+def test_mlp_fp32_backward_vs_oracle():
+    rs = np.random.RandomState(5)
+    p = O.make_params(O.mlp_param_shapes(), 9)
+    x = rs.uniform(-1, 1, size=(777, 90)).astype(np.float32)
+    cot = rs.normal(size=(777, 4)).astype(np.float32)
+    pr = {k: v.clone().requires_grad_() for k, v in p.items()}
+    xr = torch.from_numpy(x).requires_grad_()
+    (O.mlp_forward(pr, xr, 63, 27) * torch.from_numpy(cot)).sum().backward()
+    m = load(S.vallina_NeRF(8, 256, 63, 27, 5, [4], True), p)
+    xc = T(x).requires_grad_()
+    (m(xc) * T(cot)).sum().backward()
+    gp = torch.cat([q.grad.reshape(-1) for q in m.param_list()])
+    names = {id(q): n for n, q in m.named_parameters()}
+    gr = torch.cat([pr[names[id(q)]].grad.reshape(-1) for q in m.param_list()])
+    assert rel_l2(gp, gr) < 1e-5
+    # gradient w.r.t. the embedded points (needed by D-NeRF's PE-inside-the-graph, model.py:148-149)
+    assert rel_l2(xc.grad[:, :63], xr.grad[:, :63]) < 1e-5
+
+
+# ---------------------------------------------------------------- a1 render_rays, fp32 check mode
+def _render_case(g, tag, precision, N=None):
+    rays, target = g["rays"], g["target"]
+    if N is not None:
+        rays, target = rays[:N], target[:N]
+    pc, pf, mc, mf, q = make_vanilla(int(g["seed_coarse"]), int(g["seed_fine"]), precision)
+    perturb = 0.0 if tag in ("det", "lindisp") else 1.0
+    std = 1.0 if tag == "noise" else 0.0
+    ret = S.render_rays(T(rays), mc, q, 64, retraw=True, lindisp=(tag == "lindisp"), perturb=perturb,
+                        N_importance=128, network_fine=mf, white_bkgd=True, raw_noise_std=std, pytest=True)
+    loss = torch.mean((ret["rgb_map"] - T(target)) ** 2) + torch.mean((ret["rgb0"] - T(target)) ** 2)
+    loss.backward()
+    return ret, loss, mc, mf
+
+
+@pytest.mark.parametrize("tag", ["det", "pert", "noise", "lindisp"])
+def test_render_rays_fp32_golden(golden, tag):
+    g = golden("render_rays")
+    ret, loss, mc, mf = _render_case(g, tag, "fp32")
+    for k in ["rgb_map", "acc_map", "rgb0", "acc0", "z_std", "disp_map", "disp0"]:
+        assert relmax(ret[k], torch.from_numpy(g[f"{tag}/{k}"])) < 1e-5 * (20 if "disp" in k or k == "z_std" else 1), k
+    assert relmax(ret["raw"], torch.from_numpy(g[f"{tag}/raw"])) < 2e-4      # z_fine differs by cdf rounding
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-6
+    for pre, m in (("coarse.", mc), ("fine.", mf)):
+        num = den = 0.0
+        for n, p in m.named_parameters():
+            sub = p.grad.reshape(-1)[::251].cpu().double()
+            ref = torch.from_numpy(g[f"{tag}/gsub/{pre}{n}"]).double()
+            num += float((sub - ref).pow(2).sum()); den += float(ref.pow(2).sum())
+            gn = float(g[f"{tag}/gnorm/{pre}{n}"])
+            assert abs(float(p.grad.double().norm()) - gn) <= 1e-3 * gn + 1e-12, n
+        assert (num / den) ** 0.5 < 1e-4, pre
+
+
+def test_render_rays_fp32_vs_oracle_grads():
+    """Same inputs through the CPU oracle (autograd) and the CUDA path; full gradient compared."""
+    N = 96
+    rays = O.blender_rays(N, 41)
+    target = np.random.RandomState(42).uniform(0, 1, (N, 3)).astype(np.float32)
+    pc, pf, mc, mf, q = make_vanilla(7, 8, "fp32")
+    pcr = {k: v.clone().requires_grad_() for k, v in pc.items()}
+    pfr = {k: v.clone().requires_grad_() for k, v in pf.items()}
+    ref = O.render_rays(torch.from_numpy(rays), pcr, pfr, 64, 128, white_bkgd=True)
+    lr = ((ref["rgb_map"] - torch.from_numpy(target)) ** 2).mean() + ((ref["rgb0"] - torch.from_numpy(target)) ** 2).mean()
+    lr.backward()
+    ret = S.render_rays(T(rays), mc, q, 64, perturb=0., N_importance=128, network_fine=mf, white_bkgd=True)
+    lg = ((ret["rgb_map"] - T(target)) ** 2).mean() + ((ret["rgb0"] - T(target)) ** 2).mean()
+    lg.backward()
+    for k in ["rgb_map", "acc_map", "rgb0", "acc0"]:
+        assert relmax(ret[k], ref[k]) < 1e-5, k
+    for m, pr in ((mc, pcr), (mf, pfr)):
+        gg = torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()])
+        gr = torch.cat([pr[n].grad.reshape(-1) for n, _ in m.named_parameters()])
+        assert rel_l2(gg, gr) < 1e-4
+
+
+def test_render_rays_compat_query_fn():
+    """A foreign network_query_fn with the reference signature (nerf/run.py:248) still works."""
+    pc, pf, mc, mf, q = make_vanilla(7, 8, "fp32")
+    rays = T(O.blender_rays(40, 43))
+    plain = lambda inputs, viewdirs, network_fn: S.run_network(inputs, viewdirs, network_fn, q.embed_fn,
+                                                               q.embeddirs_fn, 4096)
+    a = S.render_rays(rays, mc, plain, 64, N_importance=128, network_fine=mf, white_bkgd=True)
+    b = S.render_rays(rays, mc, q, 64, N_importance=128, network_fine=mf, white_bkgd=True)
+    for k in ["rgb_map", "acc_map", "rgb0"]:
+        assert relmax(a[k], b[k]) < 1e-5
+
+
+def test_render_8col_rays_no_viewdirs():
+    """ray batch without viewdirs (width 8, nerf/run.py:357) and use_viewdirs=False network."""
+    pn = O.make_params(O.mlp_param_shapes(input_ch_views=0, output_ch=4, use_viewdirs=False), 3)
+    m = load(S.vallina_NeRF(8, 256, 63, 0, 4, [4], False), pn)
+    q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], None, 65536, precision="fp32")
+    rays = O.blender_rays(31, 44)[:, :8].copy()
+    ret = S.render_rays(T(rays), m, q, 64, N_importance=0, white_bkgd=False)
+    ref = O.render_rays(torch.from_numpy(rays), pn, None, 64, 0, white_bkgd=False)
+    assert relmax(ret["rgb_map"], ref["rgb_map"]) < 1e-5 and "rgb0" not in ret
+
+
+# ---------------------------------------------------------------- a1d D-NeRF render_rays
+def _dnerf_args(tmp):
+    os.makedirs(os.path.join(str(tmp), "e"), exist_ok=True)
+    return Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
+                     netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4,
+                     ft_path=None, basedir=str(tmp), expname="e", no_reload=True, perturb=1.0, white_bkgd=True,
+                     raw_noise_std=0.0, dataset_type="blender", no_ndc=False, lindisp=False,
+                     nerf_type="direct_temporal", use_two_models_for_fine=False, not_zero_canonical=False,
+                     do_half_precision=False)
+
+
+@pytest.mark.parametrize("tag", ["t037", "t0"])
+def test_render_rays_dnerf_golden(golden, tag, tmp_path):
+    g = golden("render_rays_dnerf")
+    kw, _, _, _, _ = dnerf.create_nerf(_dnerf_args(tmp_path), device=torch.device(DEV))
+    model = kw["network_fn"]
+    load(model, O.make_params(O.dnerf_param_shapes(), int(g["seed"])))
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    rays, target = T(g[f"{tag}/rays"]), T(g[f"{tag}/target"])
+    ret = dnerf.render_rays(rays, retraw=True, pytest=True, **kw)
+    loss = torch.mean((ret["rgb_map"] - target) ** 2)
+    if tag == "t037":
+        rays2 = rays.clone(); rays2[:, 8] = 0.37 + 0.01
+        ret2 = dnerf.render_rays(rays2, pytest=True, z_vals=ret["z_vals"].detach(), **kw)
+        assert relmax(ret2["position_delta"], torch.from_numpy(g[f"{tag}/position_delta_next"])) < 5e-5
+        loss = loss + 0.1 * torch.sum((ret["position_delta"] - ret2["position_delta"]) ** 2)
+    loss.backward()
+    for k in ["rgb_map", "acc_map", "z_vals", "position_delta", "z_std"]:
+        assert relmax(ret[k], torch.from_numpy(g[f"{tag}/{k}"])) < 5e-5, k
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-5 * max(1.0, float(g[f"{tag}/loss"]))
+    num = den = 0.0
+    for n, p in model.named_parameters():
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        sub = gr.reshape(-1)[::251].cpu().double()
+        ref = torch.from_numpy(g[f"{tag}/gsub/{n}"]).double()
+        num += float((sub - ref).pow(2).sum()); den += float(ref.pow(2).sum())
+    assert (num / max(den, 1e-30)) ** 0.5 < 2e-4
+
+
+# ---------------------------------------------------------------- fused tcgen05 path
+needs_tc = pytest.mark.skipif(not tc.available(), reason="tcgen05 path not built")
+
+
+@needs_tc
+def test_tc_forward_vs_fp32_and_oracle():
+    N = 200                                              # 200*64 and 200*192 rows: ragged last tile
+    rays = T(O.blender_rays(N, 51))
+    pc, pf, mc, mf, q_tc = make_vanilla(11, 12, "tc")
+    q_32 = S.NetworkQuery(q_tc.embed_fn, q_tc.embeddirs_fn, 65536, precision="fp32")
+    z = ops.stratified_z(rays, 64)
+    with torch.no_grad():
+        a = q_tc.query_rays(rays, z, mc, 8)
+        b = q_32.query_rays(rays, z, mc, 8)
+    assert a.shape == (N, 64, 4)
+    assert relmax(a, b) < 5e-3 and rel_l2(a, b) < 2e-3      # raw logits: fp16 operand rounding through 10 layers
+
+
+@needs_tc
+@pytest.mark.parametrize("tag", ["det", "pert"])
+def test_render_rays_tc_golden(golden, tag):
+    g = golden("render_rays")
+    ret, loss, mc, mf = _render_case(g, tag, "tc")
+    for k in ["rgb_map", "acc_map", "rgb0", "acc0"]:
+        assert relmax(ret[k], torch.from_numpy(g[f"{tag}/{k}"])) < 1e-3, k
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-3 * float(g[f"{tag}/loss"])
+
+
+@needs_tc
+def test_render_rays_tc_grads_vs_oracle():
+    N = 256
+    rays = O.blender_rays(N, 61)
+    target = np.random.RandomState(62).uniform(0, 1, (N, 3)).astype(np.float32)
+    pc, pf, mc, mf, q = make_vanilla(13, 14, "tc")
+    pcr = {k: v.clone().requires_grad_() for k, v in pc.items()}
+    pfr = {k: v.clone().requires_grad_() for k, v in pf.items()}
+    ref = O.render_rays(torch.from_numpy(rays), pcr, pfr, 64, 128, white_bkgd=True)
+    lr = ((ref["rgb_map"] - torch.from_numpy(target)) ** 2).mean() + ((ref["rgb0"] - torch.from_numpy(target)) ** 2).mean()
+    lr.backward()
+    ret = S.render_rays(T(rays), mc, q, 64, perturb=0., N_importance=128, network_fine=mf, white_bkgd=True)
+    lg = ((ret["rgb_map"] - T(target)) ** 2).mean() + ((ret["rgb0"] - T(target)) ** 2).mean()
+    lg.backward()
+    for k in ["rgb_map", "acc_map", "rgb0", "acc0"]:
+        assert relmax(ret[k], ref[k]) < 1e-3, k
+    for m, pr in ((mc, pcr), (mf, pfr)):
+        gg = torch.cat([p.grad.reshape(-1) for _, p in m.named_parameters()])
+        gr = torch.cat([pr[n].grad.reshape(-1) for n, _ in m.named_parameters()])
+        assert rel_l2(gg, gr) < 5e-3
+        assert relmax(gg, gr) < 5e-3

@@ -88,8 +88,8 @@ def cpu_reference_run(steps, warmup, sample_rays, threads):
     from oracle import nerf_oracle as O
     torch.set_num_threads(threads)
     shapes = O.mlp_param_shapes()
-    pc = {k: v.requires_grad_() for k, v in O.make_params(shapes, 1).items()}
-    pf = {k: v.requires_grad_() for k, v in O.make_params(shapes, 2).items()}
+    pc = {k: v.requires_grad_() for k, v in O.make_params(shapes, 21).items()}
+    pf = {k: v.requires_grad_() for k, v in O.make_params(shapes, 55).items()}
     opt = torch.optim.Adam(list(pc.values()) + list(pf.values()), lr=5e-4, betas=(0.9, 0.999))
     rays = torch.from_numpy(O.blender_rays(sample_rays, 5))
     target = torch.from_numpy(np.random.RandomState(6).uniform(0, 1, (sample_rays, 3)).astype(np.float32))
@@ -158,8 +158,8 @@ def main():
 
     torch.manual_seed(1234 + rank)
     shapes = O.mlp_param_shapes()
-    mc = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mc.load_state_dict(O.make_params(shapes, 1)); mc.to(dev)
-    mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(O.make_params(shapes, 2)); mf.to(dev)
+    mc = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mc.load_state_dict(O.make_params(shapes, 21)); mc.to(dev)
+    mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(O.make_params(shapes, 55)); mf.to(dev)
     q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], precision=precision)
     params = list(mc.parameters()) + list(mf.parameters())
     flat = parallel.FlatGrads(params)

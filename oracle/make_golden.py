@@ -61,11 +61,11 @@ def gen_embed(ref):
 
 def gen_mlp(ref):
     rs = np.random.RandomState(12)
-    d = {"seed": np.int64(101)}
+    d = {"seed": np.int64(23)}
     x = rs.uniform(-1, 1, size=(45, 90)).astype(np.float32)
     d["x"] = x
     shapes = O.mlp_param_shapes()
-    params = O.make_params(shapes, 101)
+    params = O.make_params(shapes, 23)
     m = ref.model.vallina_NeRF(D=8, W=256, input_ch=63, input_ch_views=27, output_ch=5, skips=[4], use_viewdirs=True)
     load_params(m, params)
     d["y_vanilla"] = m(torch.from_numpy(x)).detach().numpy()
@@ -85,12 +85,12 @@ def gen_mlp(ref):
     d["y_noview"] = m3(torch.from_numpy(x[:, :63].copy())).detach().numpy()
     # D-NeRF direct_temporal
     shapes_d = O.dnerf_param_shapes()
-    params_d = O.make_params(shapes_d, 103)
+    params_d = O.make_params(shapes_d, 332)
     emb_fn, _ = ref.embedder.get_embedder(10, 3, 0)
     md = ref.model.DirectTemporalNeRF(D=8, W=256, input_ch=63, input_ch_views=27, input_ch_time=21, output_ch=5,
                                       skips=[4], use_viewdirs=True, embed_fn=emb_fn, zero_canonical=True)
     load_params(md, params_d)
-    d["seed_dnerf"] = np.int64(103)
+    d["seed_dnerf"] = np.int64(332)
     pts = rs.uniform(-1.5, 1.5, size=(29, 3)).astype(np.float32)
     vd = rs.normal(size=(29, 3)).astype(np.float32)
     vd /= np.linalg.norm(vd, axis=-1, keepdims=True)
@@ -204,10 +204,10 @@ def gen_render_rays(ref):
     rays = O.blender_rays(N, seed=21)
     target = np.random.RandomState(22).uniform(0, 1, size=(N, 3)).astype(np.float32)
     d["rays"], d["target"] = rays, target
-    d["seed_coarse"], d["seed_fine"] = np.int64(201), np.int64(202)
+    d["seed_coarse"], d["seed_fine"] = np.int64(23), np.int64(43)
     for tag, perturb, noise, lindisp in [("det", 0.0, 0.0, False), ("pert", 1.0, 0.0, False),
                                          ("noise", 1.0, 1.0, False), ("lindisp", 0.0, 0.0, True)]:
-        kw_train, kw_test = _vanilla_kwargs(ref, 201, 202, perturb, noise, lindisp=lindisp)
+        kw_train, kw_test = _vanilla_kwargs(ref, 23, 43, perturb, noise, lindisp=lindisp)
         kw = dict(kw_train)
         kw.pop("use_viewdirs"); kw.pop("ndc")
         for m in (kw["network_fn"], kw["network_fine"]):
@@ -229,9 +229,9 @@ def gen_render_rays(ref):
 def gen_render_rays_dnerf(ref):
     d = {}
     N = 10
-    d["seed"] = np.int64(301)
+    d["seed"] = np.int64(332)
     shapes = O.dnerf_param_shapes()
-    params = O.make_params(shapes, 301)
+    params = O.make_params(shapes, 332)
     args = Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=128, N_samples=64,
                      netdepth=8, netwidth=256, netdepth_fine=8, netwidth_fine=256, netchunk=65536, lrate=5e-4,
                      ft_path=None, basedir="/tmp/_swnerf_golden", expname="gd", no_reload=True, perturb=1.0,

@@ -208,10 +208,22 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 //   dL/dalpha_i = G_i T_i - R_i / u_i,  R_i = sum_{k>i} G_k w_k   (T_k carries the factor u_i)
 //   dL/dsigma_i = dL/dalpha_i * dist_i * e_i * [sigma_i + noise_i > 0],   e_i = exp(-relu(.) dist_i)
 //   dL/draw_rgb = w_i g_rgb c (1 - c)
-// Two sweeps over the ray (second one hits L1): sweep A gets total = sum_k G_k w_k, sweep B the
-// running prefix so that R_i = total - prefix_i.  e_i/u_i <= 1 is formed first so that a tiny u_i
-// never amplifies the rounding of R_i.
+// Sweep A walks the ray forward and keeps the transmittance entering every 32-sample chunk; sweep B
+// walks the chunks BACKWARD (second read hits L1), rebuilds T inside the chunk and forms R_i as a true
+// suffix sum (reverse warp scan + carry), so no cancellation.  e_i/u_i <= 1 is formed first so that a
+// tiny u_i never amplifies the rounding of R_i.
 // ---------------------------------------------------------------------------------------------
+constexpr int kMaxChunks = 64;   // S <= 2048
+
+__device__ __forceinline__ float warp_rscan_add(float v, int lane) {   // inclusive suffix sum
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    float t = __shfl_down_sync(0xffffffffu, v, o);
+    if (lane + o < 32) v += t;
+  }
+  return v;
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
                      int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
@@ -219,8 +231,9 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ g_w, const float* __restrict__ g_depth,
                      const float* __restrict__ acc_map, const float* __restrict__ depth_map,
                      float* __restrict__ d_raw) {
-  int lane = threadIdx.x & 31;
-  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  __shared__ float carries[kWarpsPerBlock][kMaxChunks];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (r >= N) return;
   const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
   float4* out4 = reinterpret_cast<float4*>(d_raw) + r * S;
@@ -243,48 +256,58 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   }
   if (white_bkgd) ga -= (gr + gg + gb);
 
-  float total = 0.f;
-  for (int sweep = 0; sweep < 2; ++sweep) {
-    float carry = 1.f, pcarry = 0.f, part = 0.f;
-    for (int base = 0; base < S; base += 32) {
-      int i = base + lane;
-      bool valid = i < S;
-      float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-      float zi = valid ? __ldg(zr + i) : 0.f;
-      float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
-      float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
-      float dist, e, alpha, u; bool on;
-      sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
-      if (!valid) { alpha = 0.f; u = 1.f; }
-      float incl = warp_scan_mul(u, lane);
-      float excl = __shfl_up_sync(0xffffffffu, incl, 1);
-      if (lane == 0) excl = 1.f;
-      float T = carry * excl;
-      carry *= __shfl_sync(0xffffffffu, incl, 31);
-      float w = alpha * T;
-      float cr = sigmoidf_(q.x), cg = sigmoidf_(q.y), cb = sigmoidf_(q.z);
-      float G = gr * cr + gg * cg + gb * cb + gd * zi + ga + ((valid && gw) ? __ldg(gw + i) : 0.f);
-      float Gw = valid ? G * w : 0.f;
-      if (sweep == 0) {
-        part += Gw;
-      } else {
-        float pin = warp_scan_add(Gw, lane);
-        float prefix = pcarry + pin;                 // inclusive prefix of G_k w_k
-        pcarry += __shfl_sync(0xffffffffu, pin, 31);
-        float R = total - prefix;
-        float dalpha_e = G * T * e - R * (e / u);    // dL/dalpha * e
-        float dsig = on ? dalpha_e * dist : 0.f;
-        if (valid) {
-          float4 o;
-          o.x = w * gr * cr * (1.f - cr);
-          o.y = w * gg * cg * (1.f - cg);
-          o.z = w * gb * cb * (1.f - cb);
-          o.w = dsig;
-          out4[i] = o;
-        }
-      }
+  const int nchunk = (S + 31) >> 5;
+  // sweep A: transmittance entering each chunk
+  float carry = 1.f;
+  for (int c = 0; c < nchunk; ++c) {
+    int i = c * 32 + lane;
+    bool valid = i < S;
+    float sig = valid ? __ldg(reinterpret_cast<const float*>(raw4 + i) + 3) : 0.f;
+    float zi = valid ? __ldg(zr + i) : 0.f;
+    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
+    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
+    float dist, e, alpha, u; bool on;
+    sample_alpha(sig, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
+    if (!valid) u = 1.f;
+    if (lane == 0) carries[warp][c] = carry;
+    float incl = warp_scan_mul(u, lane);
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  // sweep B: chunks in reverse, suffix sums of G_k w_k
+  float rcarry = 0.f;
+  for (int c = nchunk - 1; c >= 0; --c) {
+    int i = c * 32 + lane;
+    bool valid = i < S;
+    float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float zi = valid ? __ldg(zr + i) : 0.f;
+    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
+    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
+    float dist, e, alpha, u; bool on;
+    sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
+    if (!valid) { alpha = 0.f; u = 1.f; }
+    float incl = warp_scan_mul(u, lane);
+    float excl = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) excl = 1.f;
+    float T = carries[warp][c] * excl;
+    float w = alpha * T;
+    float cr = sigmoidf_(q.x), cg = sigmoidf_(q.y), cb = sigmoidf_(q.z);
+    float G = gr * cr + gg * cg + gb * cb + gd * zi + ga + ((valid && gw) ? __ldg(gw + i) : 0.f);
+    float Gw = valid ? G * w : 0.f;
+    float suf = warp_rscan_add(Gw, lane);                       // sum_{k>=i} within the chunk
+    float nxt = __shfl_down_sync(0xffffffffu, suf, 1);
+    float R = ((lane == 31) ? 0.f : nxt) + rcarry;               // sum_{k>i} over the whole ray
+    rcarry += __shfl_sync(0xffffffffu, suf, 0);
+    float dalpha_e = G * T * e - R * (e / u);                    // dL/dalpha * e
+    float dsig = on ? dalpha_e * dist : 0.f;
+    if (valid) {
+      float4 o;
+      o.x = w * gr * cr * (1.f - cr);
+      o.y = w * gg * cg * (1.f - cg);
+      o.z = w * gb * cb * (1.f - cb);
+      o.w = dsig;
+      out4[i] = o;
     }
-    if (sweep == 0) total = warp_sum(part);
   }
 }
 
@@ -523,6 +546,7 @@ int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* ray
   SW_REQUIRE(raw && z_vals && rays && d_raw, "composite_bwd: null pointer");
   SW_REQUIRE(aligned16(raw) && aligned16(d_raw), "composite_bwd: raw/d_raw must be 16-byte aligned");
   SW_REQUIRE(!g_disp || (acc_map && depth_map), "composite_bwd: g_disp needs saved acc/depth maps");
+  SW_REQUIRE(n_samples <= 32 * kMaxChunks, "composite_bwd: n_samples > 2048");
   if (n_rays == 0) return SWNERF_OK;
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
   composite_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(

@@ -240,7 +240,7 @@ class MLPFp32Fn(torch.autograd.Function):
         dev = x_pts.device
         M = x_pts.shape[0]
         W = s.W
-        need_grad = torch.is_grad_enabled() and (any(p.requires_grad for p in params) or x_pts.requires_grad)
+        need_grad = any(ctx.needs_input_grad)    # (grad mode is off inside Function.forward)
         P = [(p.data_ptr(), p.stride(0) if p.dim() == 2 else 0) for p in params]
         for p in params:
             ptr(p, F32, "parameter")

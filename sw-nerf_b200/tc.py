@@ -58,7 +58,7 @@ class TcMlpFn(torch.autograd.Function):
     def forward(ctx, network, ray_batch, z_vals, view_col, grad_scale, *params):
         N, S = z_vals.shape
         dev = z_vals.device
-        training = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        training = any(ctx.needs_input_grad)
         st = packed_weights(network, need_bwd=training)
         raw = torch.empty((N, S, 4), dtype=F32, device=dev)
         ws = None

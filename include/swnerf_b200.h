@@ -129,6 +129,13 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
                       const void* packed_t, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);
 
+/* Hardware self-test of the tcgen05 building blocks (tests only): one 128-row tile on one CTA.
+ *  mode 0: D[128,N] = A[128,K] . B[N,K]^T  (K-major operands, K in {64,128,192,256})
+ *  mode 1: D[128,N] = A[K,128]^T . B[K,N]   (MN-major operands, K = 128 samples)
+ * A, B, D fp32 row-major; scratch >= 256 KiB. */
+int swnerf_tc_selftest(int mode, const float* A, const float* B, float* D, int N, int K, void* scratch,
+                       void* stream);
+
 /* Number of kernels the library has launched on this thread since the last reset (bench.py's
  * gpu_launches). */
 int64_t swnerf_launch_count(int reset);

@@ -1,13 +1,465 @@
-// placeholder until the tcgen05 kernels land (keeps every declared symbol exported)
+// Fused points + positional encoding + 8x256 skip MLP on tcgen05 tensor cores (forward).
+//
+// Reference restated: nerf/run.py:385 (pts = o + d z), embedder.py:33-42 (PE L=10 / L=4),
+// nerf/run.py:76-83 (expand viewdirs, concat), model.py:39-62 (vallina_NeRF.forward).
+//
+// One persistent CTA per SM walks 128-sample tiles.  Per tile the whole network runs on chip:
+//   PE warps      : points + encodings in registers -> fp16 operand images in shared memory
+//   producer warp : streams the packed fp16 weight chunks ([N x 64] K-major images, 32 KB) through a
+//                   3-stage ring with cp.async.bulk + mbarrier (weights stay L2 resident, 1.05 MB)
+//   MMA thread    : tcgen05.mma 128 x N x 16 (fp16 in, fp32 accumulate in TMEM), 4 per chunk
+//   epilogue warps: tcgen05.ld -> +bias, ReLU -> fp16 -> back into the activation image IN PLACE, one
+//                   64-column block at a time, so the next layer's MMAs start on block 0 while blocks 1..3
+//                   are still being drained (two TMEM accumulators of 256 columns ping-pong)
+// The skip connection is an extra K=64 chunk on the retained PE image (column order [pts | h],
+// model.py:46); feature_linear is folded into views_linears at pack time (no nonlinearity between them,
+// model.py:50-55) and alpha_linear rides along as row 128 of that N=144 head; rgb_linear (3 x 128) is
+// evaluated in fp32 in the head epilogue.  Algorithmic work: 593,408 MAC per sample.
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "mlp_tc_layout.cuh"
 #include "../../include/swnerf_b200.h"
-using namespace swnerf;
-extern "C" {
-int64_t swnerf_tc_packed_bytes(void) { return 0; }
-int64_t swnerf_tc_packed_t_bytes(void) { return 0; }
-int64_t swnerf_tc_workspace_bytes(int64_t, int) { return 0; }
-int swnerf_tc_pack_weights(const float* const*, void*, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc path not built"); }
-int swnerf_tc_pack_weights_t(const float* const*, void*, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc path not built"); }
-int swnerf_tc_mlp_fwd(const float*, int, int, const float*, int64_t, int, const void*, float*, void*, int, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc path not built"); }
-int swnerf_tc_mlp_bwd(const float*, int64_t, int, const void*, const void*, const float* const*, void*, float* const*, float, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc path not built"); }
+
+namespace swnerf {
+using namespace tc;
+using namespace tcl;
+
+// ------------------------------------------------------------------------------------------------
+// weight packing
+// ------------------------------------------------------------------------------------------------
+struct ParamPtrs {
+  const float* p[24];
+};
+
+// W_fv = W_v[:, :256] W_f (128 x 256), b_fv = W_v[:, :256] b_f + b_v      -> fold[128][257] fp32
+__global__ void fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
+  int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 128 * 257) return;
+  int r = idx / 257, c = idx % 257;
+  const float* wv = P.p[16] + (size_t)r * 283;
+  float acc = 0.f;
+  if (c < 256) {
+    const float* wf = P.p[18];
+    for (int j = 0; j < 256; ++j) acc = fmaf(wv[j], wf[(size_t)j * 256 + c], acc);
+  } else {
+    const float* bf = P.p[19];
+    for (int j = 0; j < 256; ++j) acc = fmaf(wv[j], bf[j], acc);
+    acc += P.p[17][r];
+  }
+  fold[idx] = acc;
 }
+
+__device__ __forceinline__ float fwd_weight(const ParamPtrs& P, const float* fold, int c, int n, int k) {
+  if (c == 0) return k < 63 ? P.p[0][n * 63 + k] : 0.f;
+  if (c <= 16) { int l = 1 + (c - 1) / 4, kc = (c - 1) % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
+  if (c == 17) return k < 63 ? P.p[10][n * 319 + k] : 0.f;
+  if (c <= 21) return P.p[10][n * 319 + 63 + (c - 18) * 64 + k];
+  if (c <= 29) { int l = 6 + (c - 22) / 4, kc = (c - 22) % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
+  if (c == 30) return (n < 128 && k < 27) ? P.p[16][n * 283 + 256 + k] : 0.f;
+  int kk = (c - 31) * 64 + k;
+  if (n < 128) return fold[n * 257 + kk];
+  if (n == 128) return P.p[20][kk];
+  return 0.f;
+}
+
+__global__ void pack_fwd_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
+  const float* fold = reinterpret_cast<const float*>(packed + PK_FOLD_OFF);
+  int unit = blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit < PK_CHUNK_BYTES / 16) {
+    int byte = unit * 16;
+    int c, in;
+    if (byte < N_FULL_CHUNKS * CHUNK_B) { c = byte / CHUNK_B; in = byte % CHUNK_B; }
+    else { int b2 = byte - N_FULL_CHUNKS * CHUNK_B; c = N_FULL_CHUNKS + b2 / HCHUNK_B; in = b2 % HCHUNK_B; }
+    int n = (in >> 10) * 8 + ((in >> 7) & 7);
+    int pu = (in >> 4) & 7;
+    int k0 = (pu ^ (n & 7)) * 8;
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(fwd_weight(P, fold, c, n, k0 + i));
+    *reinterpret_cast<uint4*>(packed + byte) = *reinterpret_cast<const uint4*>(h);
+  }
+  // fp32 block: biases, head bias, rgb_linear
+  float* f = reinterpret_cast<float*>(packed + PK_F32_OFF);
+  if (unit < F32_COUNT) {
+    float v = 0.f;
+    if (unit < F32_BHEAD) { int l = unit / 256, n = unit % 256; v = P.p[2 * l + 1][n]; }
+    else if (unit < F32_WRGB) { int n = unit - F32_BHEAD; v = n < 128 ? fold[n * 257 + 256] : (n == 128 ? P.p[21][0] : 0.f); }
+    else if (unit < F32_BRGB) { v = P.p[22][unit - F32_WRGB]; }
+    else { int i = unit - F32_BRGB; v = i < 3 ? P.p[23][i] : 0.f; }
+    f[unit] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// fused forward
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+  const float* rays; int ray_stride; int view_col;
+  const float* z; int S; int64_t P;           // P = total sample rows
+  const uint8_t* packed; float* raw;
+  uint8_t* ws; int64_t num_tiles;
+};
+
+__device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
+  // angle = 2*pi*frac((th + tl) * scale): th*scale and the rounding to nearest integer are exact in fp32
+  float a = th * scale;
+  float r = a - rintf(a);
+  r = fmaf(tl, scale, r);
+  float ang = r * 6.283185307179586f;
+  s = __sinf(ang);
+  c = __cosf(ang);
+}
+
+template <int L, int NCOL>
+__device__ __forceinline__ void encode3(const float (&x)[3], float (&f)[NCOL]) {
+  // f[0..3(1+2L)) = [x, sin(2^k x), cos(2^k x)]_k ; the rest stays zero
+#pragma unroll
+  for (int i = 0; i < NCOL; ++i) f[i] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+    f[j] = x[j];
+    const float hi = 0.15915494f, lo = 6.4206e-9f;      // 1/(2 pi) = hi + lo
+    float th = x[j] * hi;
+    float tl = fmaf(x[j], hi, -th) + x[j] * lo;
+#pragma unroll
+    for (int k = 0; k < L; ++k) {
+      float s, c;
+      sincos_turns(th, tl, (float)(1 << k), s, c);
+      f[3 + 6 * k + j] = s;
+      f[6 + 6 * k + j] = c;
+    }
+  }
+}
+
+__device__ __forceinline__ void store_row64(uint8_t* img, int row, const float (&f)[64]) {
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    uint4 q;
+    q.x = pack_half2(f[8 * u + 0], f[8 * u + 1]);
+    q.y = pack_half2(f[8 * u + 2], f[8 * u + 3]);
+    q.z = pack_half2(f[8 * u + 4], f[8 * u + 5]);
+    q.w = pack_half2(f[8 * u + 6], f[8 * u + 7]);
+    *reinterpret_cast<uint4*>(img + tile_unit_off(row, u)) = q;
+  }
+}
+
+template <bool TRAIN>
+__global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_act = smem + SM_ACT;
+  uint8_t* s_pe = smem + SM_PE;
+  uint8_t* s_vw = smem + SM_VW;
+  uint8_t* s_ring = smem + SM_RING;
+  float* s_f32 = reinterpret_cast<float*>(smem + SM_F32);
+  float4* s_scr = reinterpret_cast<float4*>(smem + SM_SCR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint64_t* w_full = bars;            // [3]
+  uint64_t* w_empty = bars + 3;       // [3]
+  uint64_t* pe_full = bars + 6;
+  uint64_t* pe_empty = bars + 7;
+  uint64_t* vw_full = bars + 8;
+  uint64_t* vw_empty = bars + 9;
+  uint64_t* act_full = bars + 10;     // [4]
+  uint64_t* d_full = bars + 14;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    mbar_init(pe_full, 128); mbar_init(pe_empty, 1);
+    mbar_init(vw_full, 128); mbar_init(vw_empty, 1);
+    for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 256);
+    mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  {
+    const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF);
+    for (int i = threadIdx.x; i < F32_COUNT; i += blockDim.x) s_f32[i] = __ldg(src + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
+          uint32_t stage = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+          mbar_wait(&w_empty[stage], ph ^ 1);
+          uint32_t bytes = c < N_FULL_CHUNKS ? CHUNK_B : HCHUNK_B;
+          mbar_expect_tx(&w_full[stage], bytes);
+          bulk_g2s(s_ring + stage * CHUNK_B, g.packed + chunk_off(c), bytes, &w_full[stage]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc256 = umma_idesc_f16(128, 256, 0, 0);
+      const uint32_t idesc144 = umma_idesc_f16(128, HEAD_N, 0, 0);
+      uint32_t cnt = 0, dcnt = 0, alayer = 0, it = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        for (int li = 0; li < 9; ++li, ++dcnt) {
+          const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
+          const uint32_t idesc = (li == 8) ? idesc144 : idesc256;
+          const int nch = (li == 0) ? 1 : ((li == 5 || li == 8) ? 5 : 4);
+          for (int ci = 0; ci < nch; ++ci) {
+            // which A operand feeds this chunk
+            int aj = (li == 5 || li == 8) ? ci - 1 : ci;       // activation block index, -1 = extra input
+            if (li == 0) aj = -1;
+            uint32_t a_base;
+            if (aj < 0) {
+              if (li == 8) { mbar_wait(vw_full, it & 1); a_base = smem_u32(s_vw); }
+              else { if (li == 0) mbar_wait(pe_full, it & 1); a_base = smem_u32(s_pe); }
+            } else {
+              mbar_wait(&act_full[aj], alayer & 1);
+              a_base = smem_u32(s_act) + aj * ACT_BLK;
+            }
+            uint32_t stage = cnt % NSTAGE;
+            mbar_wait(&w_full[stage], (cnt / NSTAGE) & 1);
+            tc_fence_after();
+            const uint32_t b_base = smem_u32(s_ring) + stage * CHUNK_B;
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
+                       (ci > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&w_empty[stage]);
+            ++cnt;
+            if (aj < 0 && li == 5) umma_commit(pe_empty);
+            if (aj < 0 && li == 8) umma_commit(vw_empty);
+          }
+          umma_commit(&d_full[dcnt & 1]);
+          if (li >= 1) ++alayer;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 12) {
+    // ===================== epilogue: TMEM -> bias/ReLU -> fp16 activation image =====================
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool e0 = (threadIdx.x == 128);
+    uint32_t dcnt = 0, it = 0;
+    for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      uint8_t* ws_tile = TRAIN ? g.ws + tile * WS_TILE_BYTES : nullptr;
+      uint32_t* ws_mask = TRAIN ? reinterpret_cast<uint32_t*>(g.ws + g.num_tiles * WS_TILE_BYTES) + tile * (9 * 8 * 128)
+                                : nullptr;
+      for (int li = 0; li < 9; ++li, ++dcnt) {
+        const uint32_t dcol = (dcnt & 1) * 256;
+        mbar_wait(&d_full[dcnt & 1], (dcnt >> 1) & 1);
+        tc_fence_after();
+        if (TRAIN) {     // the previous image may still be read by its bulk store
+          if (e0) bulk_wait_read0();
+          named_bar_sync(1, 256);
+        }
+        if (li < 8) {
+          const float* bias = s_f32 + li * 256;
+#pragma unroll 1
+          for (int j = 0; j < 4; ++j) {
+            uint32_t v[32];
+            const int c0 = j * 64 + hh * 32;
+            tmem_ld32(tmem + lane_addr + dcol + c0, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            uint32_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = __uint_as_float(v[2 * i]) + bias[c0 + 2 * i];
+              float b = __uint_as_float(v[2 * i + 1]) + bias[c0 + 2 * i + 1];
+              if (TRAIN) mask |= (a > 0.f ? 1u : 0u) << (2 * i) | (b > 0.f ? 1u : 0u) << (2 * i + 1);
+              pk[i] = pack_half2_relu(a, b);
+            }
+            uint8_t* blk = s_act + j * ACT_BLK;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+              *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
+                  make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+            if (TRAIN) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = mask;
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(&act_full[j]);
+          }
+          if (TRAIN) {
+            named_bar_sync(1, 256);
+            if (e0) { bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
+          }
+        } else {
+          // head: cols 0..127 = relu -> h9, col 128 = sigma; rgb = W_rgb h9 + b_rgb in fp32
+          const float* bh = s_f32 + F32_BHEAD;
+          const float* wr = s_f32 + F32_WRGB;
+          float pr = 0.f, pg = 0.f, pb = 0.f;
+#pragma unroll 1
+          for (int jj = 0; jj < 2; ++jj) {
+            uint32_t v[32];
+            const int c0 = hh * 64 + jj * 32;
+            tmem_ld32(tmem + lane_addr + dcol + c0, v);
+            tmem_ld_wait();
+            uint32_t pk[16];
+            uint32_t mask = 0;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              float a = fmaxf(__uint_as_float(v[2 * i]) + bh[c0 + 2 * i], 0.f);
+              float b = fmaxf(__uint_as_float(v[2 * i + 1]) + bh[c0 + 2 * i + 1], 0.f);
+              pr = fmaf(wr[c0 + 2 * i], a, pr); pr = fmaf(wr[c0 + 2 * i + 1], b, pr);
+              pg = fmaf(wr[128 + c0 + 2 * i], a, pg); pg = fmaf(wr[128 + c0 + 2 * i + 1], b, pg);
+              pb = fmaf(wr[256 + c0 + 2 * i], a, pb); pb = fmaf(wr[256 + c0 + 2 * i + 1], b, pb);
+              if (TRAIN) {
+                mask |= (a > 0.f ? 1u : 0u) << (2 * i) | (b > 0.f ? 1u : 0u) << (2 * i + 1);
+                pk[i] = pack_half2(a, b);
+              }
+            }
+            if (TRAIN) {
+              uint8_t* blk = s_act + hh * ACT_BLK;
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(blk + tile_unit_off(row, jj * 4 + u)) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              ws_mask[(8 * 8 + hh * 2 + jj) * 128 + row] = mask;
+            }
+          }
+          if (hh == 1) {
+            uint32_t v[32];
+            tmem_ld32(tmem + lane_addr + dcol + 128, v);
+            tmem_ld_wait();
+            s_scr[row] = make_float4(pr, pg, pb, __uint_as_float(v[0]) + bh[128]);
+          }
+          if (TRAIN) fence_async_smem();
+          tc_fence_before();
+          named_bar_sync(1, 256);
+          if (hh == 0) {
+            float4 o = s_scr[row];
+            const float* br = s_f32 + F32_BRGB;
+            int64_t idx = tile * TILE + row;
+            if (idx < g.P)
+              reinterpret_cast<float4*>(g.raw)[idx] = make_float4(pr + o.x + br[0], pg + o.y + br[1], pb + o.z + br[2], o.w);
+          }
+          if (TRAIN && e0) { bulk_s2g(ws_tile + WS_H9_OFF, s_act, 2 * ACT_BLK); bulk_commit(); }
+        }
+      }
+    }
+    if (TRAIN && e0) bulk_wait_all0();
+  } else if (warp >= 12) {
+    // ===================== points + positional encoding =====================
+    const int p = (warp - 12) * 32 + lane;
+    const bool p0 = (p == 0);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+      int64_t idx = tile * TILE + p;
+      bool valid = idx < g.P;
+      float pos[3] = {0.f, 0.f, 0.f}, dir[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        int64_t r = idx / g.S;
+        const float* ray = g.rays + r * g.ray_stride;
+        float zz = __ldg(g.z + idx);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          pos[j] = __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));      // run.py:385
+          dir[j] = __ldg(ray + g.view_col + j);
+        }
+      }
+      float f[64];
+      encode3<10, 64>(pos, f);
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) f[i] = 0.f;
+      }
+      if (it > 0) mbar_wait(pe_empty, (it - 1) & 1);
+      if (TRAIN && it > 0) {
+        if (p0) bulk_wait_read0();
+        named_bar_sync(2, 128);
+      }
+      store_row64(s_pe, p, f);
+      fence_async_smem();
+      mbar_arrive(pe_full);
+      encode3<4, 64>(dir, f);
+      if (!valid) {
+#pragma unroll
+        for (int i = 0; i < 64; ++i) f[i] = 0.f;
+      }
+      if (it > 0) mbar_wait(vw_empty, (it - 1) & 1);
+      store_row64(s_vw, p, f);
+      fence_async_smem();
+      mbar_arrive(vw_full);
+      if (TRAIN) {
+        named_bar_sync(2, 128);
+        if (p0) {
+          uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
+          bulk_s2g(ws_tile + WS_PE_OFF, s_pe, ACT_BLK);
+          bulk_s2g(ws_tile + WS_VW_OFF, s_vw, ACT_BLK);
+          bulk_commit();
+        }
+      }
+    }
+    if (TRAIN && p0) bulk_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+}  // namespace swnerf
+
+using namespace swnerf;
+
+extern "C" {
+
+int64_t swnerf_tc_packed_bytes(void) { return PK_TOTAL_BYTES; }
+
+int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training) {
+  if (!training || n_points <= 0) return 0;
+  int64_t tiles = (n_points + TILE - 1) / TILE;
+  return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES);
+}
+
+int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream) {
+  SW_REQUIRE(params && packed, "tc_pack_weights: null pointer");
+  SW_REQUIRE(aligned16(packed), "tc_pack_weights: packed must be 16-byte aligned");
+  ParamPtrs P;
+  for (int i = 0; i < 24; ++i) {
+    SW_REQUIRE(params[i], "tc_pack_weights: null parameter %d", i);
+    P.p[i] = params[i];
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
+  fold_head_kernel<<<(128 * 257 + 255) / 256, 256, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
+  int rc = check_launch("tc_fold_head");
+  if (rc) return rc;
+  pack_fwd_kernel<<<(PK_CHUNK_BYTES / 16 + 255) / 256, 256, 0, s>>>(P, pk);
+  return check_launch("tc_pack_weights");
+}
+
+int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
+                      int n_samples, const void* packed, float* raw, void* workspace, int training,
+                      void* stream) {
+  SW_REQUIRE(rays && z_vals && packed && raw, "tc_mlp_fwd: null pointer");
+  SW_REQUIRE(view_col >= 0 && view_col + 3 <= ray_stride, "tc_mlp_fwd: the fused kernel needs viewdirs in the ray batch");
+  SW_REQUIRE(!training || workspace, "tc_mlp_fwd: training needs a workspace");
+  SW_REQUIRE(aligned16(raw) && aligned16(packed) && aligned16(workspace), "tc_mlp_fwd: buffers must be 16-byte aligned");
+  SW_REQUIRE(n_samples >= 1 && n_rays >= 0, "tc_mlp_fwd: bad sizes");
+  if (n_rays == 0) return SWNERF_OK;
+  FwdArgs g;
+  g.rays = rays; g.ray_stride = ray_stride; g.view_col = view_col; g.z = z_vals; g.S = n_samples;
+  g.P = n_rays * n_samples; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = raw;
+  g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE;
+  int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
+  cudaStream_t s = (cudaStream_t)stream;
+  if (training) {
+    static thread_local bool attr_t = false;
+    if (!attr_t) { cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL); attr_t = true; }
+    mlp_fwd_kernel<true><<<grid, 512, SM_TOTAL, s>>>(g);
+  } else {
+    static thread_local bool attr_i = false;
+    if (!attr_i) { cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL); attr_i = true; }
+    mlp_fwd_kernel<false><<<grid, 512, SM_TOTAL, s>>>(g);
+  }
+  return check_launch("tc_mlp_fwd");
+}
+
+}  // extern "C"

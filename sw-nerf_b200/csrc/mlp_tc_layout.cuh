@@ -1,0 +1,56 @@
+// Byte layouts shared by the fused tcgen05 kernels: packed weight images, shared memory carve-up,
+// per-tile workspace (saved activations / masks / output gradients).
+#pragma once
+#include <stdint.h>
+
+namespace swnerf {
+namespace tcl {
+
+constexpr int TILE = 128;                 // sample rows per tile (UMMA M)
+constexpr int HEAD_N = 144;               // folded head: 128 view-branch units + sigma + pad to 16
+constexpr int NSTAGE = 3;                 // weight ring depth
+constexpr int CHUNK_B = 256 * 128;        // [256 x 64] fp16 K-major image
+constexpr int HCHUNK_B = HEAD_N * 128;    // [144 x 64]
+constexpr int ACT_BLK = TILE * 128;       // [128 x 64] fp16 image (16 KB)
+constexpr int ACT_BYTES = 4 * ACT_BLK;    // [128 x 256]
+
+// ---- forward weight stream: chunk order per tile (see mlp_tc.cu)
+//  0: L0(pe) | 1-16: L1..L4 | 17: L5(pe) 18-21: L5(h) | 22-29: L6,L7 | 30: head(views) 31-34: head(h7)
+constexpr int N_CHUNKS = 35;
+constexpr int N_FULL_CHUNKS = 30;
+constexpr int PK_CHUNK_BYTES = N_FULL_CHUNKS * CHUNK_B + 5 * HCHUNK_B;       // 1,075,200
+__host__ __device__ constexpr int chunk_off(int c) {
+  return c < N_FULL_CHUNKS ? c * CHUNK_B : N_FULL_CHUNKS * CHUNK_B + (c - N_FULL_CHUNKS) * HCHUNK_B;
+}
+// fp32 block: trunk biases [8][256] | head bias [160] (128 folded + sigma + pad) | rgb weight [3][128] | rgb bias [4]
+constexpr int F32_BHEAD = 8 * 256;
+constexpr int F32_WRGB = F32_BHEAD + 160;
+constexpr int F32_BRGB = F32_WRGB + 384;
+constexpr int F32_COUNT = F32_BRGB + 4;                                       // 2596 floats
+constexpr int PK_F32_OFF = PK_CHUNK_BYTES;
+constexpr int PK_FOLD_OFF = PK_F32_OFF + ((F32_COUNT * 4 + 255) / 256) * 256; // fold scratch [128][257] fp32
+constexpr int PK_TOTAL_BYTES = PK_FOLD_OFF + 128 * 257 * 4;
+
+// ---- shared memory of the forward kernel (offsets from a 1024-aligned base)
+constexpr int SM_ACT = 0;
+constexpr int SM_PE = SM_ACT + ACT_BYTES;
+constexpr int SM_VW = SM_PE + ACT_BLK;
+constexpr int SM_RING = SM_VW + ACT_BLK;
+constexpr int SM_F32 = SM_RING + NSTAGE * CHUNK_B;
+constexpr int SM_SCR = SM_F32 + ((F32_COUNT * 4 + 127) / 128) * 128;
+constexpr int SM_BAR = SM_SCR + TILE * 16;
+constexpr int SM_TOTAL = SM_BAR + 256 + 1024;                                  // + alignment slack
+
+// ---- per-tile workspace written by the training forward
+constexpr int WS_PE_OFF = 0;
+constexpr int WS_VW_OFF = ACT_BLK;
+constexpr int WS_H_OFF = 2 * ACT_BLK;                    // h0..h7, 64 KB each
+constexpr int WS_H9_OFF = WS_H_OFF + 8 * ACT_BYTES;      // h9 [128 x 128]
+constexpr int64_t WS_TILE_BYTES = WS_H9_OFF + 2 * ACT_BLK;       // 589,824
+constexpr int64_t WS_MASK_BYTES = 9 * 8 * 128 * 4;               // ReLU sign bits, 36,864
+// written by the backward-data kernel: dy0..dy7 [128 x 256] and the head gradient [128 x 192]
+constexpr int WS_DYH_OFF = 8 * ACT_BYTES;
+constexpr int64_t WS_DY_BYTES = WS_DYH_OFF + 3 * ACT_BLK;        // 573,440
+
+}  // namespace tcl
+}  // namespace swnerf

@@ -235,12 +235,11 @@ class MLPFp32Fn(torch.autograd.Function):
     """Whole-network forward/backward on the fp32 SIMT GEMM kernels."""
 
     @staticmethod
-    def forward(ctx, spec: MLPSpec, x_pts, x_extra, x_views, *params):
+    def forward(ctx, spec: MLPSpec, need_grad, x_pts, x_extra, x_views, *params):
         s = spec
         dev = x_pts.device
         M = x_pts.shape[0]
         W = s.W
-        need_grad = any(ctx.needs_input_grad)    # (grad mode is off inside Function.forward)
         P = [(p.data_ptr(), p.stride(0) if p.dim() == 2 else 0) for p in params]
         for p in params:
             ptr(p, F32, "parameter")
@@ -369,8 +368,9 @@ class MLPFp32Fn(torch.autograd.Function):
                 _gemm(2, g, hp, GP[2 * i], W, W, M, accumulate=True)
                 _gemm(1, g, wi, g_next, M, W, W, mask=hp)
                 g, g_next = g_next, g
-        return (None, d_pts, None, None) + tuple(G)
+        return (None, None, d_pts, None, None) + tuple(G)
 
 
 def mlp_fp32(spec: MLPSpec, x_pts, x_extra, x_views, params: Sequence[torch.Tensor]):
-    return MLPFp32Fn.apply(spec, x_pts, x_extra, x_views, *params)
+    need_grad = torch.is_grad_enabled() and (x_pts.requires_grad or any(p.requires_grad for p in params))
+    return MLPFp32Fn.apply(spec, need_grad, x_pts, x_extra, x_views, *params)

@@ -59,6 +59,9 @@ class NetworkQuery:
                            embeddirs_fn=self.embeddirs_fn, netchunk=self.netchunk)
 
     def uses_tc(self, network_fn, has_views):
+        if torch.is_grad_enabled() and not tc.bwd_available() and \
+                any(p.requires_grad for p in network_fn.parameters()):
+            return False
         return (self.precision == "tc" and tc.available() and has_views and getattr(network_fn, "tc_eligible", lambda: False)()
                 and getattr(self.embed_fn, "L", None) == 10 and getattr(self.embeddirs_fn, "L", None) == 4)
 

@@ -16,6 +16,10 @@ def available() -> bool:
     return int(_lib.lib().swnerf_tc_packed_bytes()) > 0
 
 
+def bwd_available() -> bool:
+    return int(_lib.lib().swnerf_tc_packed_t_bytes()) > 0
+
+
 class _Packed:
     __slots__ = ("versions", "fwd", "bwd", "bwd_versions")
 
@@ -55,10 +59,9 @@ def packed_weights(network, need_bwd=False):
 
 class TcMlpFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, network, ray_batch, z_vals, view_col, grad_scale, *params):
+    def forward(ctx, network, ray_batch, z_vals, view_col, grad_scale, training, *params):
         N, S = z_vals.shape
         dev = z_vals.device
-        training = any(ctx.needs_input_grad)
         st = packed_weights(network, need_bwd=training)
         raw = torch.empty((N, S, 4), dtype=F32, device=dev)
         ws = None
@@ -84,10 +87,12 @@ class TcMlpFn(torch.autograd.Function):
              ptr_array([p.detach() for p in params]), ctx.ws.data_ptr(), ptr_array(grads),
              float(ctx.grad_scale), stream())
         ctx.ws = None
-        return (None, None, None, None, None) + tuple(grads)
+        return (None, None, None, None, None, None) + tuple(grads)
 
 
 def mlp_query(network, ray_batch, z_vals, view_col, grad_scale=None):
     if grad_scale is None:
         grad_scale = getattr(network, "grad_scale", 1024.0)
-    return TcMlpFn.apply(network, ray_batch, z_vals, view_col, grad_scale, *network.param_list())
+    params = network.param_list()
+    training = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # (grad mode is off inside forward)
+    return TcMlpFn.apply(network, ray_batch, z_vals, view_col, grad_scale, training, *params)

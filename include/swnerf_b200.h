@@ -122,9 +122,11 @@ int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const flo
 /* Fused backward: d_raw[N,S,4] -> fp32 gradients of the 24 parameter tensors, ACCUMULATED into
  * grads[i] (so coarse+fine passes and the flat all-reduce buffer need no extra copy).  `packed_t`
  * is the transposed weight image from swnerf_tc_pack_weights_t.  grad_scale multiplies d_raw before
- * the fp16 conversion (power of two; divided out again in the fp32 epilogue). */
+ * the fp16 conversion and is divided out again in the fp32 flush; 0 = pick a power of two from
+ * max|d_raw| on the device (no host sync). */
 int64_t swnerf_tc_packed_t_bytes(void);
-int swnerf_tc_pack_weights_t(const float* const* params, void* packed_t, void* stream);
+/* `packed` is the forward image of the same parameters (its folded head is reused). */
+int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream);
 int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
                       const void* packed_t, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);

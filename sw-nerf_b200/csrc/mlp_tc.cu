@@ -415,7 +415,7 @@ int64_t swnerf_tc_packed_bytes(void) { return PK_TOTAL_BYTES; }
 int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training) {
   if (!training || n_points <= 0) return 0;
   int64_t tiles = (n_points + TILE - 1) / TILE;
-  return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES);
+  return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES) + WS_TAIL_BYTES;
 }
 
 int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream) {

@@ -1,9 +1,553 @@
-// placeholder: backward of the fused path (implemented next)
+// Backward of the fused 8x256 MLP on tcgen05 tensor cores (autograd of model.py:39-62 at the sample
+// positions of nerf/run.py:385): d_raw[N,S,4] -> fp32 gradients of the 24 parameter tensors.
+//
+//  1. bwd_data kernel (per 128-sample tile, same skeleton as the forward): the chain
+//        d_raw -> dy9 = (d_rgb W_rgb) * mask9 -> dh7 = dy9 W_fv + d_sigma w_alpha -> dy7 = dh7 * mask7 -> dh6 = dy7 W7 ...
+//     runs on tensor cores with transposed fp16 weight chunks; ReLU masks are the sign bits the forward
+//     saved (32 B / row / layer).  Every dy_l tile is written back as an operand image for step 2, and
+//     the bias gradients (column sums of dy_l, fp32, before rounding) are reduced here.
+//  2. bwd_weight kernel: dW_l = dy_l^T x_l, K = all samples.  The saved forward activations and the dy
+//     tiles are the SAME 128B-swizzled images read as MN-major operands.  Each CTA owns one layer ("job")
+//     and a slice of the tiles, accumulates in TMEM (up to 512 columns = a full 256x256 fp32 gradient) and
+//     flushes once with red.add into the caller's (flat) gradient buffers.  HBM-bound: 2 x 64 KB per tile-layer.
+//  3. un-fold: d W_fv, d b_fv -> feature_linear / views_linears gradients (fp32 SIMT GEMMs, tiny).
+// Gradients are scaled by a power of two (from max|d_raw|, on device) before the fp16 conversion and
+// unscaled in the fp32 flush.
 #include "common.cuh"
+#include "tc_common.cuh"
+#include "mlp_tc_layout.cuh"
 #include "../../include/swnerf_b200.h"
-using namespace swnerf;
-extern "C" {
-int64_t swnerf_tc_packed_t_bytes(void) { return 0; }
-int swnerf_tc_pack_weights_t(const float* const*, void*, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc backward not built"); }
-int swnerf_tc_mlp_bwd(const float*, int64_t, int, const void*, const void*, const float* const*, void*, float* const*, float, void*) { return set_err(SWNERF_ERR_UNSUPPORTED, "tc backward not built"); }
+
+namespace swnerf {
+using namespace tc;
+using namespace tcl;
+
+struct ParamPtrsB {
+  const float* p[24];
+};
+
+// ------------------------------------------------------------------------------------------------
+// transposed weight image
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float bwd_weight(const ParamPtrsB& P, const float* fold, int c, int n, int k) {
+  // B[n][k]: n = input channel of the layer (output of the data-gradient GEMM), k = its output unit
+  if (c < 2) return fold[(c * 64 + k) * 257 + n];                 // W_fv[u][n]
+  if (c == 2) return k == 0 ? P.p[20][n] : 0.f;                   // alpha_linear row
+  int t = (c - 3) / 4, kc = (c - 3) % 4;
+  int l = 7 - t;                                                  // 7,6,5,4,3,2,1
+  int ld = (l == 5) ? 319 : 256, off = (l == 5) ? 63 : 0;
+  return P.p[2 * l][(size_t)(kc * 64 + k) * ld + off + n];
 }
+
+__global__ void pack_bwd_kernel(ParamPtrsB P, const uint8_t* __restrict__ packed_fwd, uint8_t* __restrict__ packed_t) {
+  const float* fold = reinterpret_cast<const float*>(packed_fwd + PK_FOLD_OFF);
+  int unit = blockIdx.x * blockDim.x + threadIdx.x;
+  if (unit >= PKT_TOTAL_BYTES / 16) return;
+  int byte = unit * 16;
+  int c = byte / CHUNK_B, in = byte % CHUNK_B;
+  int n = (in >> 10) * 8 + ((in >> 7) & 7);
+  int pu = (in >> 4) & 7;
+  int k0 = (pu ^ (n & 7)) * 8;
+  __align__(16) __half h[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(bwd_weight(P, fold, c, n, k0 + i));
+  *reinterpret_cast<uint4*>(packed_t + byte) = *reinterpret_cast<const uint4*>(h);
+}
+
+__global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < __int_as_float(0x7f800000)) atomicMax(out, __float_as_uint(m));
+}
+
+__device__ __forceinline__ float grad_scale_from(const uint32_t* absmax, float fixed) {
+  if (fixed > 0.f) return fixed;
+  float mx = __uint_as_float(*absmax);
+  if (!(mx > 0.f)) return 1.f;
+  float e = floorf(log2f(256.f / mx));
+  e = fminf(fmaxf(e, -40.f), 40.f);
+  return exp2f(e);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 1. backward data
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  const float* d_raw; int64_t P; int64_t num_tiles;
+  const uint8_t* packed; const uint8_t* packed_t;
+  uint8_t* ws;
+  float* grads[24];
+  float* unfold;
+  const uint32_t* absmax; float fixed_scale;
+};
+
+// 32 values x 32 lanes -> lane l returns the sum over all lanes of v[l]
+__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int i = 0; i < s; ++i) {
+      float send = up ? v[i] : v[i + s];
+      float keep = up ? v[i + s] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+__global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_act = smem + SMB_ACT;
+  uint8_t* s_ring = smem + SMB_RING;
+  float* s_wrgb = reinterpret_cast<float*>(smem + SMB_WRGB);
+  float* s_db = reinterpret_cast<float*>(smem + SMB_DB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMB_BAR);
+  uint64_t* w_full = bars;            // [3]
+  uint64_t* w_empty = bars + 3;       // [3]
+  uint64_t* act_full = bars + 6;      // [4]
+  uint64_t* d_full = bars + 10;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 256);
+    mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  {
+    const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF) + F32_WRGB;
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_wrgb[i] = __ldg(src + i);
+    for (int i = threadIdx.x; i < DB_COUNT; i += blockDim.x) s_db[i] = 0.f;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float scale = grad_scale_from(g.absmax, g.fixed_scale);
+  const int64_t mask_base = g.num_tiles * WS_TILE_BYTES;
+  const int64_t dy_base = mask_base + g.num_tiles * WS_MASK_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        for (int c = 0; c < NT_CHUNKS; ++c, ++cnt) {
+          uint32_t stage = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+          mbar_wait(&w_empty[stage], ph ^ 1);
+          mbar_expect_tx(&w_full[stage], CHUNK_B);
+          bulk_g2s(s_ring + stage * CHUNK_B, g.packed_t + (size_t)c * CHUNK_B, CHUNK_B, &w_full[stage]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
+      uint32_t cnt = 0, dcnt = 0, alayer = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        for (int t = 0; t < 8; ++t, ++dcnt, ++alayer) {
+          const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
+          const int nch = (t == 0) ? 3 : 4;
+          for (int ci = 0; ci < nch; ++ci, ++cnt) {
+            mbar_wait(&act_full[ci], alayer & 1);
+            uint32_t stage = cnt % NSTAGE;
+            mbar_wait(&w_full[stage], (cnt / NSTAGE) & 1);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(s_act) + ci * ACT_BLK;
+            const uint32_t b_base = smem_u32(s_ring) + stage * CHUNK_B;
+            const int nks = (t == 0 && ci == 2) ? 1 : 4;           // sigma block: only the first 16 columns
+            for (int ks = 0; ks < nks; ++ks)
+              umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
+                       (ci > 0 || ks > 0) ? 1u : 0u);
+            umma_commit(&w_empty[stage]);
+          }
+          umma_commit(&d_full[dcnt & 1]);
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3, hh = (warp - 4) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    const bool e0 = (threadIdx.x == 128);
+    uint32_t dcnt = 0;
+    for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      const uint32_t* ws_mask = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + tile * (9 * 8 * 128);
+      uint8_t* ws_dy = g.ws + dy_base + tile * WS_DY_BYTES;
+      // ---- head prep: d_raw -> [dy9 | d_sigma | d_rgb] operand image
+      {
+        if (e0) bulk_wait_read0();
+        named_bar_sync(1, 256);
+        const int64_t idx = tile * TILE + row;
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < g.P) dr = __ldg(reinterpret_cast<const float4*>(g.d_raw) + idx);
+        dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+#pragma unroll 1
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c0 = hh * 64 + jj * 32;
+          const uint32_t m = __ldg(ws_mask + (8 * 8 + hh * 2 + jj) * 128 + row);
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = dr.x * s_wrgb[c0 + i] + dr.y * s_wrgb[128 + c0 + i] + dr.z * s_wrgb[256 + c0 + i];
+            val[i] = ((m >> i) & 1u) ? v : 0.f;
+          }
+          uint8_t* blk = s_act + hh * ACT_BLK;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(blk + tile_unit_off(row, jj * 4 + u)) =
+                make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
+                           pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
+          float cs = warp_transpose_sum(val, lane);
+          atomicAdd(&s_db[DB_HEAD + c0 + lane], cs);
+        }
+        uint8_t* blk = s_act + (2 + hh) * ACT_BLK;
+        uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
+        if (hh == 0) u0.x = pack_half2(dr.w, 0.f);
+        else { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
+        *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 0)) = u0;
+        *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        if (hh == 0) {
+          float s = warp_sum(dr.w);
+          if (lane == 0) atomicAdd(&s_db[DB_ALPHA], s);
+        } else {
+          float sx = warp_sum(dr.x), sy = warp_sum(dr.y), sz = warp_sum(dr.z);
+          if (lane == 0) { atomicAdd(&s_db[DB_RGB], sx); atomicAdd(&s_db[DB_RGB + 1], sy); atomicAdd(&s_db[DB_RGB + 2], sz); }
+        }
+        fence_async_smem();
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mbar_arrive(&act_full[j]);
+        named_bar_sync(1, 256);
+        if (e0) { bulk_s2g(ws_dy + WS_DYH_OFF, s_act, ACT_BYTES); bulk_commit(); }
+      }
+      // ---- layers: dh_l (TMEM) * mask_l -> dy_l
+      for (int t = 0; t < 8; ++t, ++dcnt) {
+        const int l = 7 - t;
+        const uint32_t dcol = (dcnt & 1) * 256;
+        mbar_wait(&d_full[dcnt & 1], (dcnt >> 1) & 1);
+        tc_fence_after();
+        if (e0) bulk_wait_read0();
+        named_bar_sync(1, 256);
+#pragma unroll 1
+        for (int j = 0; j < 4; ++j) {
+          uint32_t v[32];
+          const int c0 = j * 64 + hh * 32;
+          tmem_ld32(tmem + lane_addr + dcol + c0, v);
+          tmem_ld_wait();
+          const uint32_t m = __ldg(ws_mask + (l * 8 + j * 2 + hh) * 128 + row);
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) val[i] = ((m >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+          uint8_t* blk = s_act + j * ACT_BLK;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
+                make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
+                           pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
+          fence_async_smem();
+          tc_fence_before();
+          if (t < 7) mbar_arrive(&act_full[j]);
+          float cs = warp_transpose_sum(val, lane);
+          atomicAdd(&s_db[l * 256 + c0 + lane], cs);
+        }
+        named_bar_sync(1, 256);
+        if (e0) { bulk_s2g(ws_dy + (size_t)l * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
+      }
+    }
+    if (e0) bulk_wait_all0();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+  // flush the bias gradients (fp32, unscaled)
+  const float inv = 1.f / scale;
+  for (int i = threadIdx.x; i < DB_RGB + 3; i += blockDim.x) {
+    float v = s_db[i] * inv;
+    if (v == 0.f) continue;
+    if (i < DB_HEAD) atomicAdd(g.grads[2 * (i >> 8) + 1] + (i & 255), v);
+    else if (i < DB_ALPHA) { atomicAdd(g.unfold + 128 * 256 + (i - DB_HEAD), v); atomicAdd(g.grads[17] + (i - DB_HEAD), v); }
+    else if (i == DB_ALPHA) atomicAdd(g.grads[21], v);
+    else atomicAdd(g.grads[23] + (i - DB_RGB), v);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// 2. backward weights
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_MAX_PIECES = 4, WG_MAX_MMA = 5, WG_JOBS = 9;
+
+struct WgPiece {      // one operand of a job: nblk 64-column blocks of a saved tile image
+  int from_dy;        // 0: forward workspace tile, 1: dy workspace tile
+  int tile_off;       // byte offset of block 0 inside the tile record
+  int nblk;
+  int smem_off;       // inside the stage (each block contributes 8 KB = 64 samples x 128 B)
+};
+struct WgMma {
+  int a_off, b_off;   // stage-relative offsets of the M=128 (two blocks) A operand and of the B operand
+  int N, dcol;
+  int out_param;      // index into grads[], or -1 for the un-fold scratch
+  int out_off;        // element offset added to the base
+  int row_stride, col_stride, ncols;
+};
+struct WgJob {
+  int npieces, nmma, stage_bytes, nstage;
+  WgPiece pc[WG_MAX_PIECES];
+  WgMma mm[WG_MAX_MMA];
+};
+struct WgArgs {
+  uint8_t* ws; int64_t num_tiles;
+  float* grads[24]; float* unfold;
+  const uint32_t* absmax; float fixed_scale;
+  int job_first_cta[WG_JOBS + 1];
+};
+__constant__ WgJob c_jobs[WG_JOBS];
+
+constexpr int HALF_BLK = 64 * 128;     // 64 samples of one 64-column block
+
+__global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t s_full[3], s_empty[3], s_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int job = 0;
+  while (job + 1 < WG_JOBS && (int)blockIdx.x >= g.job_first_cta[job + 1]) ++job;
+  const WgJob& J = c_jobs[job];
+  const int ncta = g.job_first_cta[job + 1] - g.job_first_cta[job];
+  const int cta = blockIdx.x - g.job_first_cta[job];
+  const int64_t t_begin = g.num_tiles * cta / ncta, t_end = g.num_tiles * (cta + 1) / ncta;
+  const int64_t nhalf = (t_end - t_begin) * 2;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+    mbar_init(&s_done, 1);
+    mbar_fence_init();
+  }
+  if (warp == 2) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int64_t mask_base = g.num_tiles * WS_TILE_BYTES;
+  const int64_t dy_base = mask_base + g.num_tiles * WS_MASK_BYTES;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t bytes = 0;
+      for (int p = 0; p < J.npieces; ++p) bytes += J.pc[p].nblk * HALF_BLK;
+      for (int64_t h = 0; h < nhalf; ++h) {
+        uint32_t stage = h % J.nstage, ph = (h / J.nstage) & 1;
+        mbar_wait(&s_empty[stage], ph ^ 1);
+        mbar_expect_tx(&s_full[stage], bytes);
+        const int64_t tile = t_begin + (h >> 1);
+        const int half = h & 1;
+        uint8_t* dst = smem + stage * J.stage_bytes;
+        for (int p = 0; p < J.npieces; ++p) {
+          const WgPiece& pc = J.pc[p];
+          const uint8_t* src = g.ws + (pc.from_dy ? dy_base + tile * WS_DY_BYTES : tile * WS_TILE_BYTES) + pc.tile_off +
+                               half * HALF_BLK;
+          for (int b = 0; b < pc.nblk; ++b)
+            bulk_g2s(dst + pc.smem_off + b * HALF_BLK, src + (size_t)b * ACT_BLK, HALF_BLK, &s_full[stage]);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      for (int64_t h = 0; h < nhalf; ++h) {
+        uint32_t stage = h % J.nstage;
+        mbar_wait(&s_full[stage], (h / J.nstage) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(smem) + stage * J.stage_bytes;
+        for (int m = 0; m < J.nmma; ++m) {
+          const WgMma& mm = J.mm[m];
+          const uint32_t idesc = umma_idesc_f16(128, mm.N, 1, 1);
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem + mm.dcol, umma_desc_mnmajor(base + mm.a_off + ks * 2048, HALF_BLK),
+                     umma_desc_mnmajor(base + mm.b_off + ks * 2048, HALF_BLK), idesc, (h > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&s_empty[stage]);
+      }
+      umma_commit(&s_done);
+    }
+  } else if (warp >= 4) {
+    // flush: TMEM -> scaled red.add into the gradient buffers
+    mbar_wait(&s_done, 0);
+    tc_fence_after();
+    if (nhalf > 0) {
+      const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
+      const int q = warp & 3;
+      const int r = q * 32 + lane;
+      for (int m = 0; m < J.nmma; ++m) {
+        const WgMma& mm = J.mm[m];
+        float* base = (mm.out_param >= 0 ? g.grads[mm.out_param] : g.unfold) + mm.out_off + (size_t)r * mm.row_stride;
+        for (int c0 = 0; c0 < mm.ncols; c0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mm.dcol + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < mm.ncols) atomicAdd(base + (size_t)(c0 + i) * mm.col_stride, __uint_as_float(v[i]) * inv);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem);
+}
+
+// job table ------------------------------------------------------------------------------------
+static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the layer input */, int col_off, int ld) {
+  J.npieces = 2; J.nmma = 2; J.stage_bytes = 8 * HALF_BLK; J.nstage = 3;
+  J.pc[0] = {1, l * ACT_BYTES, 4, 0};
+  J.pc[1] = {0, x_off, 4, 4 * HALF_BLK};
+  for (int m = 0; m < 2; ++m)
+    J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 256, m * 256, 2 * l, m * 128 * ld + col_off, ld, 1, 256};
+}
+
+static void build_jobs(WgJob* jobs) {
+  memset(jobs, 0, sizeof(WgJob) * WG_JOBS);
+  // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :63], dW5[:, :63]
+  {
+    WgJob& J = jobs[0];
+    J.npieces = 3; J.nmma = 4; J.stage_bytes = 9 * HALF_BLK; J.nstage = 3;
+    J.pc[0] = {1, 0 * ACT_BYTES, 4, 0};
+    J.pc[1] = {1, 5 * ACT_BYTES, 4, 4 * HALF_BLK};
+    J.pc[2] = {0, WS_PE_OFF, 1, 8 * HALF_BLK};
+    for (int a = 0; a < 2; ++a)
+      for (int m = 0; m < 2; ++m)
+        J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64, (a * 2 + m) * 64,
+                           a == 0 ? 0 : 10, m * 128 * (a == 0 ? 63 : 319), a == 0 ? 63 : 319, 1, 63};
+  }
+  for (int l = 1; l <= 4; ++l) wg_std_job(jobs[l], l, WS_H_OFF + (l - 1) * ACT_BYTES, 0, 256);
+  wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, 63, 319);
+  wg_std_job(jobs[6], 6, WS_H_OFF + 5 * ACT_BYTES, 0, 256);
+  wg_std_job(jobs[7], 7, WS_H_OFF + 6 * ACT_BYTES, 0, 256);
+  // job 8: head.  stage: dyH (4 blk) | views (1) | h7 (4) | h9 (2)
+  {
+    WgJob& J = jobs[8];
+    J.npieces = 4; J.nmma = 5; J.stage_bytes = 11 * HALF_BLK; J.nstage = 2;
+    J.pc[0] = {1, WS_DYH_OFF, 4, 0};
+    J.pc[1] = {0, WS_VW_OFF, 1, 4 * HALF_BLK};
+    J.pc[2] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, 5 * HALF_BLK};
+    J.pc[3] = {0, WS_H9_OFF, 2, 9 * HALF_BLK};
+    J.mm[0] = {0, 4 * HALF_BLK, 64, 0, 16, 256, 283, 1, 27};                 // dW_v[:, 256:283] = dy9^T views
+    J.mm[1] = {0, 5 * HALF_BLK, 256, 64, -1, 0, 256, 1, 256};                // G = dy9^T h7  (d W_fv)
+    J.mm[2] = {5 * HALF_BLK, 2 * HALF_BLK, 16, 320, 20, 0, 1, 0, 1};         // d w_alpha[0:128]   = h7^T d_sigma
+    J.mm[3] = {7 * HALF_BLK, 2 * HALF_BLK, 16, 336, 20, 128, 1, 0, 1};       // d w_alpha[128:256]
+    J.mm[4] = {9 * HALF_BLK, 3 * HALF_BLK, 16, 352, 22, 0, 1, 128, 3};       // dW_rgb[j][c] = h9^T d_rgb
+  }
+}
+
+static void assign_ctas(int n_cta, int* first) {
+  // CTAs per job in proportion to the bytes a job streams per tile
+  const int w[WG_JOBS] = {144, 128, 128, 128, 128, 128, 128, 128, 176};
+  int tot = 0;
+  for (int j = 0; j < WG_JOBS; ++j) tot += w[j];
+  int cnt[WG_JOBS], used = 0;
+  for (int j = 0; j < WG_JOBS; ++j) { cnt[j] = n_cta * w[j] / tot; if (cnt[j] < 1) cnt[j] = 1; used += cnt[j]; }
+  for (int j = 0; used < n_cta; j = (j + 1) % WG_JOBS) { ++cnt[j]; ++used; }
+  first[0] = 0;
+  for (int j = 0; j < WG_JOBS; ++j) first[j + 1] = first[j] + cnt[j];
+}
+
+}  // namespace swnerf
+
+using namespace swnerf;
+
+extern "C" {
+
+int64_t swnerf_tc_packed_t_bytes(void) { return PKT_TOTAL_BYTES; }
+
+int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
+  SW_REQUIRE(params && packed && packed_t, "tc_pack_weights_t: null pointer");
+  SW_REQUIRE(aligned16(packed_t), "tc_pack_weights_t: packed_t must be 16-byte aligned");
+  ParamPtrsB P;
+  for (int i = 0; i < 24; ++i) {
+    SW_REQUIRE(params[i], "tc_pack_weights_t: null parameter %d", i);
+    P.p[i] = params[i];
+  }
+  pack_bwd_kernel<<<(PKT_TOTAL_BYTES / 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
+      P, reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<uint8_t*>(packed_t));
+  return check_launch("tc_pack_weights_t");
+}
+
+int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
+                      const float* const* params, void* workspace, float* const* grads, float grad_scale,
+                      void* stream) {
+  SW_REQUIRE(d_raw && packed && packed_t && params && workspace && grads, "tc_mlp_bwd: null pointer");
+  SW_REQUIRE(aligned16(d_raw) && aligned16(workspace), "tc_mlp_bwd: buffers must be 16-byte aligned");
+  SW_REQUIRE(grad_scale >= 0.f, "tc_mlp_bwd: grad_scale must be >= 0 (0 = automatic)");
+  if (n_rays == 0) return SWNERF_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t P = n_rays * n_samples;
+  const int64_t tiles = (P + TILE - 1) / TILE;
+  uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
+  uint8_t* tail = ws + tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES);
+  uint32_t* absmax = reinterpret_cast<uint32_t*>(tail);
+  float* unfold = reinterpret_cast<float*>(tail + 256);
+  cudaMemsetAsync(tail, 0, 256 + UNFOLD_FLOATS * sizeof(float), s);
+  if (grad_scale == 0.f) {
+    absmax_kernel<<<sm_count() * 4, 256, 0, s>>>(d_raw, P * 4, absmax);
+    int rc = check_launch("tc_absmax");
+    if (rc) return rc;
+  }
+  for (int i = 0; i < 24; ++i) SW_REQUIRE(grads[i] && params[i], "tc_mlp_bwd: null gradient / parameter %d", i);
+
+  BwdArgs b;
+  b.d_raw = d_raw; b.P = P; b.num_tiles = tiles;
+  b.packed = reinterpret_cast<const uint8_t*>(packed); b.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
+  b.ws = ws; b.unfold = unfold; b.absmax = absmax; b.fixed_scale = grad_scale;
+  for (int i = 0; i < 24; ++i) b.grads[i] = grads[i];
+  static thread_local bool attr = false;
+  static thread_local int wg_smem = 0;
+  if (!attr) {
+    cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
+    WgJob jobs[WG_JOBS];
+    build_jobs(jobs);
+    for (int j = 0; j < WG_JOBS; ++j) {
+      int need = jobs[j].stage_bytes * jobs[j].nstage + 1024;
+      if (need > wg_smem) wg_smem = need;
+    }
+    cudaMemcpyToSymbol(c_jobs, jobs, sizeof(jobs));
+    cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem);
+    attr = true;
+  }
+  int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  mlp_bwd_data_kernel<<<grid, 384, SMB_TOTAL, s>>>(b);
+  int rc = check_launch("tc_mlp_bwd_data");
+  if (rc) return rc;
+
+  WgArgs w;
+  w.ws = ws; w.num_tiles = tiles; w.unfold = unfold; w.absmax = absmax; w.fixed_scale = grad_scale;
+  for (int i = 0; i < 24; ++i) w.grads[i] = grads[i];
+  int n_cta = sm_count();
+  if (n_cta < WG_JOBS) n_cta = WG_JOBS;
+  assign_ctas(n_cta, w.job_first_cta);
+  mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w);
+  rc = check_launch("tc_mlp_bwd_weight");
+  if (rc) return rc;
+
+  // un-fold the head (model.py:50-55): G = d W_fv [128,256], gb = d b_fv [128]
+  //   dW_f += W_v1^T G ; db_f += W_v1^T gb ; dW_v[:, :256] += G W_f^T + gb b_f^T   (db_v += gb done in bwd_data)
+  const float* Wv = params[16]; const float* Wf = params[18]; const float* bf = params[19];
+  const float* G = unfold; const float* gb = unfold + 128 * 256;
+  rc = swnerf_sgemm(2, Wv, 283, G, 256, grads[18], 256, 256, 256, 128, nullptr, 1, 0, nullptr, 0, stream);
+  if (rc) return rc;
+  rc = swnerf_sgemm(2, Wv, 283, gb, 1, grads[19], 1, 256, 1, 128, nullptr, 1, 0, nullptr, 0, stream);
+  if (rc) return rc;
+  rc = swnerf_sgemm(0, G, 256, Wf, 256, grads[16], 283, 128, 256, 256, nullptr, 1, 0, nullptr, 0, stream);
+  if (rc) return rc;
+  rc = swnerf_sgemm(0, gb, 1, bf, 1, grads[16], 283, 128, 256, 1, nullptr, 1, 0, nullptr, 0, stream);
+  return rc;
+}
+
+}  // extern "C"

@@ -48,9 +48,35 @@ constexpr int WS_H_OFF = 2 * ACT_BLK;                    // h0..h7, 64 KB each
 constexpr int WS_H9_OFF = WS_H_OFF + 8 * ACT_BYTES;      // h9 [128 x 128]
 constexpr int64_t WS_TILE_BYTES = WS_H9_OFF + 2 * ACT_BLK;       // 589,824
 constexpr int64_t WS_MASK_BYTES = 9 * 8 * 128 * 4;               // ReLU sign bits, 36,864
-// written by the backward-data kernel: dy0..dy7 [128 x 256] and the head gradient [128 x 192]
+// written by the backward-data kernel: dy0..dy7 [128 x 256] and the head gradient tile
+// [dy9 0..63 | dy9 64..127 | (d_sigma, 0..) | (d_rgb, 0..)] as four 64-column blocks
 constexpr int WS_DYH_OFF = 8 * ACT_BYTES;
-constexpr int64_t WS_DY_BYTES = WS_DYH_OFF + 3 * ACT_BLK;        // 573,440
+constexpr int64_t WS_DY_BYTES = 9 * ACT_BYTES;                   // 589,824
+
+// ---- transposed weight stream of the backward-data kernel: chunk order per tile
+//  0,1: head^T (y9 units 0..127) 2: head^T (sigma row) | 3..30: L7^T, L6^T, L5^T(h part), L4^T .. L1^T, 4 chunks each
+constexpr int NT_CHUNKS = 31;
+constexpr int PKT_TOTAL_BYTES = NT_CHUNKS * CHUNK_B;
+
+// ---- fp32 gradient accumulators kept in shared memory by the backward-data kernel (bias gradients)
+//  [8][256] trunk biases | [128] folded head bias | d_sigma bias | d_rgb bias [3] | pad
+constexpr int DB_HEAD = 8 * 256;
+constexpr int DB_ALPHA = DB_HEAD + 128;
+constexpr int DB_RGB = DB_ALPHA + 1;
+constexpr int DB_COUNT = DB_RGB + 3 + 4;                          // 2184
+
+// shared memory of the backward-data kernel
+constexpr int SMB_ACT = 0;
+constexpr int SMB_RING = SMB_ACT + ACT_BYTES;
+constexpr int SMB_WRGB = SMB_RING + NSTAGE * CHUNK_B;             // rgb_linear weight [3][128] fp32
+constexpr int SMB_DB = SMB_WRGB + 384 * 4;
+constexpr int SMB_BAR = SMB_DB + ((DB_COUNT * 4 + 127) / 128) * 128;
+constexpr int SMB_TOTAL = SMB_BAR + 256 + 1024;
+
+// ---- fp32 scratch the backward produces before un-folding the head: G = d W_fv [128][256] | gb = d b_fv [128]
+constexpr int UNFOLD_FLOATS = 128 * 256 + 128;
+// workspace tail: [0,256) scalars (max|d_raw| bits) | un-fold scratch
+constexpr int64_t WS_TAIL_BYTES = 256 * 1024;
 
 }  // namespace tcl
 }  // namespace swnerf

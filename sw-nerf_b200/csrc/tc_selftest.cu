@@ -106,11 +106,11 @@ extern "C" int swnerf_tc_selftest(int mode, const float* A, const float* B, floa
     selftest_pack_kernel<<<(128 * K + 255) / 256, 256, 0, s>>>(A, 128, K, sc);
     selftest_pack_kernel<<<(N * K + 255) / 256, 256, 0, s>>>(B, N, K, sc + a_bytes);
   } else {
-    SW_REQUIRE(K == 128 && N % 64 == 0, "tc_selftest: mode 1 needs K == 128 samples and N a multiple of 64");
+    SW_REQUIRE(K == 128, "tc_selftest: mode 1 needs K == 128 samples");
     a_bytes = 2 * K * 128;            // P[K x 128]: two 64-channel blocks of K rows
-    b_bytes = (N / 64) * K * 128;
+    b_bytes = ((N + 63) / 64) * K * 128;
     selftest_pack_kernel<<<(K * 128 + 255) / 256, 256, 0, s>>>(A, K, 128, sc);
-    selftest_pack_kernel<<<(K * N + 255) / 256, 256, 0, s>>>(B, K, N, sc + a_bytes);
+    selftest_pack_kernel<<<(K * ((N + 63) / 64) * 64 + 255) / 256, 256, 0, s>>>(B, K, N, sc + a_bytes);
   }
   size_t smem = (size_t)((a_bytes + 1023) & ~1023) + b_bytes + 2048;
   cudaFuncSetAttribute(selftest_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

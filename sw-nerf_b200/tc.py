@@ -52,7 +52,8 @@ def packed_weights(network, need_bwd=False):
     if need_bwd and (st.bwd_versions != v or st.bwd is None):
         if st.bwd is None or st.bwd.device != dev:
             st.bwd = torch.empty(int(_lib.lib().swnerf_tc_packed_t_bytes()), dtype=torch.uint8, device=dev)
-        call("swnerf_tc_pack_weights_t", ptr_array([p.detach() for p in params]), st.bwd.data_ptr(), stream())
+        call("swnerf_tc_pack_weights_t", ptr_array([p.detach() for p in params]), st.fwd.data_ptr(),
+             st.bwd.data_ptr(), stream())
         st.bwd_versions = v
     return st
 
@@ -92,7 +93,7 @@ class TcMlpFn(torch.autograd.Function):
 
 def mlp_query(network, ray_batch, z_vals, view_col, grad_scale=None):
     if grad_scale is None:
-        grad_scale = getattr(network, "grad_scale", 1024.0)
+        grad_scale = getattr(network, "grad_scale", 0.0)     # 0 = automatic (device-side max|d_raw|)
     params = network.param_list()
     training = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # (grad mode is off inside forward)
     return TcMlpFn.apply(network, ray_batch, z_vals, view_col, grad_scale, training, *params)

@@ -28,7 +28,7 @@ def test_umma_kmajor(N, K):
     assert err < 1e-5, err                                       # fp32 accumulation only
 
 
-@pytest.mark.parametrize("N", [256, 128, 64])
+@pytest.mark.parametrize("N", [256, 128, 64, 16])
 def test_umma_mnmajor(N):
     g = torch.Generator(device="cuda").manual_seed(N)
     P = torch.randn(128, 128, device="cuda", generator=g)        # [samples, channels]

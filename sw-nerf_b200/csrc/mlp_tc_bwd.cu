@@ -4,12 +4,13 @@
 //  1. bwd_data kernel (per 128-sample tile, same skeleton as the forward): the chain
 //        d_raw -> dy9 = (d_rgb W_rgb) * mask9 -> dh7 = dy9 W_fv + d_sigma w_alpha -> dy7 = dh7 * mask7 -> dh6 = dy7 W7 ...
 //     runs on tensor cores with transposed fp16 weight chunks; ReLU masks are the sign bits the forward
-//     saved (32 B / row / layer).  Every dy_l tile is written back as an operand image for step 2, and
-//     the bias gradients (column sums of dy_l, fp32, before rounding) are reduced here.
+//     saved (32 B / row / layer).  Every dy_l tile is written back as an operand image for step 2.
 //  2. bwd_weight kernel: dW_l = dy_l^T x_l, K = all samples.  The saved forward activations and the dy
 //     tiles are the SAME 128B-swizzled images read as MN-major operands.  Each CTA owns one layer ("job")
 //     and a slice of the tiles, accumulates in TMEM (up to 512 columns = a full 256x256 fp32 gradient) and
 //     flushes once with red.add into the caller's (flat) gradient buffers.  HBM-bound: 2 x 64 KB per tile-layer.
+//     The otherwise idle CUDA cores of the same CTAs form the bias gradients (column sums of the dy images
+//     sitting in shared memory).
 //  3. un-fold: d W_fv, d b_fv -> feature_linear / views_linears gradients (fp32 SIMT GEMMs, tiny).
 // Gradients are scaled by a power of two (from max|d_raw|, on device) before the fp16 conversion and
 // unscaled in the fp32 flush.
@@ -84,28 +85,12 @@ struct BwdArgs {
   const uint32_t* absmax; float fixed_scale;
 };
 
-// 32 values x 32 lanes -> lane l returns the sum over all lanes of v[l]
-__device__ __forceinline__ float warp_transpose_sum(float (&v)[32], int lane) {
-#pragma unroll
-  for (int s = 16; s >= 1; s >>= 1) {
-    const bool up = (lane & s) != 0;
-#pragma unroll
-    for (int i = 0; i < s; ++i) {
-      float send = up ? v[i] : v[i + s];
-      float keep = up ? v[i + s] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, s);
-    }
-  }
-  return v[0];
-}
-
 __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_act = smem + SMB_ACT;
   uint8_t* s_ring = smem + SMB_RING;
   float* s_wrgb = reinterpret_cast<float*>(smem + SMB_WRGB);
-  float* s_db = reinterpret_cast<float*>(smem + SMB_DB);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SMB_BAR);
   uint64_t* w_full = bars;            // [3]
   uint64_t* w_empty = bars + 3;       // [3]
@@ -124,7 +109,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   {
     const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF) + F32_WRGB;
     for (int i = threadIdx.x; i < 384; i += blockDim.x) s_wrgb[i] = __ldg(src + i);
-    for (int i = threadIdx.x; i < DB_COUNT; i += blockDim.x) s_db[i] = 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -204,8 +188,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
             *reinterpret_cast<uint4*>(blk + tile_unit_off(row, jj * 4 + u)) =
                 make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
                            pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
-          float cs = warp_transpose_sum(val, lane);
-          atomicAdd(&s_db[DB_HEAD + c0 + lane], cs);
         }
         uint8_t* blk = s_act + (2 + hh) * ACT_BLK;
         uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
@@ -213,13 +195,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         else { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 0)) = u0;
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
-        if (hh == 0) {
-          float s = warp_sum(dr.w);
-          if (lane == 0) atomicAdd(&s_db[DB_ALPHA], s);
-        } else {
-          float sx = warp_sum(dr.x), sy = warp_sum(dr.y), sz = warp_sum(dr.z);
-          if (lane == 0) { atomicAdd(&s_db[DB_RGB], sx); atomicAdd(&s_db[DB_RGB + 1], sy); atomicAdd(&s_db[DB_RGB + 2], sz); }
-        }
         fence_async_smem();
 #pragma unroll
         for (int j = 0; j < 4; ++j) mbar_arrive(&act_full[j]);
@@ -253,8 +228,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
           fence_async_smem();
           tc_fence_before();
           if (t < 7) mbar_arrive(&act_full[j]);
-          float cs = warp_transpose_sum(val, lane);
-          atomicAdd(&s_db[l * 256 + c0 + lane], cs);
         }
         named_bar_sync(1, 256);
         if (e0) { bulk_s2g(ws_dy + (size_t)l * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
@@ -266,16 +239,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem);
-  // flush the bias gradients (fp32, unscaled)
-  const float inv = 1.f / scale;
-  for (int i = threadIdx.x; i < DB_RGB + 3; i += blockDim.x) {
-    float v = s_db[i] * inv;
-    if (v == 0.f) continue;
-    if (i < DB_HEAD) atomicAdd(g.grads[2 * (i >> 8) + 1] + (i & 255), v);
-    else if (i < DB_ALPHA) { atomicAdd(g.unfold + 128 * 256 + (i - DB_HEAD), v); atomicAdd(g.grads[17] + (i - DB_HEAD), v); }
-    else if (i == DB_ALPHA) atomicAdd(g.grads[21], v);
-    else atomicAdd(g.grads[23] + (i - DB_RGB), v);
-  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -296,10 +259,19 @@ struct WgMma {
   int out_off;        // element offset added to the base
   int row_stride, col_stride, ncols;
 };
+struct WgBias {       // column sums of a dy operand sitting in the stage: bias gradients
+  int smem_off;       // first block
+  int ncols;          // columns summed (even; thread t owns columns 2t, 2t+1)
+  int nvalid;         // columns written out
+  int out_param;      // grads[] index; -1: folded head bias -> un-fold scratch gb AND grads[17]
+  int out_off;
+};
+constexpr int WG_MAX_BIAS = 3;
 struct WgJob {
-  int npieces, nmma, stage_bytes, nstage;
+  int npieces, nmma, nbias, stage_bytes, nstage;
   WgPiece pc[WG_MAX_PIECES];
   WgMma mm[WG_MAX_MMA];
+  WgBias bs[WG_MAX_BIAS];
 };
 struct WgArgs {
   uint8_t* ws; int64_t num_tiles;
@@ -327,7 +299,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
   const int64_t nhalf = (t_end - t_begin) * 2;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1 + 4); }   // MMA commit + 4 bias warps
     mbar_init(&s_done, 1);
     mbar_fence_init();
   }
@@ -378,6 +350,32 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
       umma_commit(&s_done);
     }
   } else if (warp >= 4) {
+    // bias gradients on the CUDA cores while the tensor pipe / HBM stream run: column sums of the dy images
+    const int t2 = (threadIdx.x - 128) * 2;
+    float bacc[WG_MAX_BIAS][2];
+#pragma unroll
+    for (int b = 0; b < WG_MAX_BIAS; ++b) bacc[b][0] = bacc[b][1] = 0.f;
+    for (int64_t h = 0; h < nhalf; ++h) {
+      uint32_t stage = h % J.nstage;
+      mbar_wait(&s_full[stage], (h / J.nstage) & 1);
+      const uint8_t* st = smem + stage * J.stage_bytes;
+#pragma unroll
+      for (int b = 0; b < WG_MAX_BIAS; ++b) {
+        if (b < J.nbias && t2 < J.bs[b].ncols) {
+          const uint8_t* blk = st + J.bs[b].smem_off + (t2 >> 6) * HALF_BLK;
+          const int c = t2 & 63;
+          float a0 = 0.f, a1 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < 64; ++r) {
+            float2 f = __half22float2(*reinterpret_cast<const __half2*>(blk + tile_off(r, c)));
+            a0 += f.x; a1 += f.y;
+          }
+          bacc[b][0] += a0; bacc[b][1] += a1;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[stage]);
+    }
     // flush: TMEM -> scaled red.add into the gradient buffers
     mbar_wait(&s_done, 0);
     tc_fence_after();
@@ -385,6 +383,20 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
       const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
       const int q = warp & 3;
       const int r = q * 32 + lane;
+#pragma unroll
+      for (int b = 0; b < WG_MAX_BIAS; ++b) {
+        if (b < J.nbias) {
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = t2 + e;
+            if (col < J.bs[b].nvalid) {
+              const float v = bacc[b][e] * inv;
+              if (J.bs[b].out_param >= 0) atomicAdd(g.grads[J.bs[b].out_param] + J.bs[b].out_off + col, v);
+              else { atomicAdd(g.unfold + 128 * 256 + col, v); atomicAdd(g.grads[17] + col, v); }
+            }
+          }
+        }
+      }
       for (int m = 0; m < J.nmma; ++m) {
         const WgMma& mm = J.mm[m];
         float* base = (mm.out_param >= 0 ? g.grads[mm.out_param] : g.unfold) + mm.out_off + (size_t)r * mm.row_stride;
@@ -404,9 +416,63 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
   if (warp == 2) tmem_dealloc<512>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3. un-fold of the head (model.py:50-55):  G = d W_fv [128,256], gb = d b_fv [128]
+//      dW_f[c][k]  += sum_u W_v[u][c] G[u][k]                     (64 tiles of 32x32)
+//      dW_v[u][c]  += sum_k G[u][k] W_f[c][k] + gb[u] b_f[c]       (32 tiles)
+//      db_f[c]     += sum_u W_v[u][c] gb[u]                        (8 tiles, one column)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restrict__ Wv, const float* __restrict__ Wf,
+                                                            const float* __restrict__ bf, const float* __restrict__ G,
+                                                            const float* __restrict__ gb, float* __restrict__ dWf,
+                                                            float* __restrict__ dbf, float* __restrict__ dWv) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  int t = blockIdx.x;
+  float acc = 0.f;
+  if (t < 64) {                       // dW_f tile (c0, k0), reduce over u
+    const int c0 = (t >> 3) * 32, k0 = (t & 7) * 32;
+    for (int u0 = 0; u0 < 128; u0 += 32) {
+      As[ty][tx] = Wv[(size_t)(u0 + ty) * 283 + c0 + tx];
+      Bs[ty][tx] = G[(size_t)(u0 + ty) * 256 + k0 + tx];
+      __syncthreads();
+#pragma unroll
+      for (int u = 0; u < 32; ++u) acc = fmaf(As[u][ty], Bs[u][tx], acc);
+      __syncthreads();
+    }
+    atomicAdd(dWf + (size_t)(c0 + ty) * 256 + k0 + tx, acc);
+  } else if (t < 96) {                // dW_v[:, :256] tile (u0, c0), reduce over k
+    t -= 64;
+    const int u0 = (t >> 3) * 32, c0 = (t & 7) * 32;
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+      As[ty][tx] = G[(size_t)(u0 + ty) * 256 + k0 + tx];
+      Bs[ty][tx] = Wf[(size_t)(c0 + ty) * 256 + k0 + tx];
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < 32; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
+      __syncthreads();
+    }
+    acc = fmaf(gb[u0 + ty], bf[c0 + tx], acc);
+    atomicAdd(dWv + (size_t)(u0 + ty) * 283 + c0 + tx, acc);
+  } else {                            // db_f
+    t -= 96;
+    const int c = t * 32 + tx;
+    for (int u = ty; u < 128; u += 32) acc = fmaf(Wv[(size_t)u * 283 + c], gb[u], acc);
+    As[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0) {
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) s2 += As[i][tx];
+      atomicAdd(dbf + c, s2);
+    }
+  }
+}
+
 // job table ------------------------------------------------------------------------------------
 static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the layer input */, int col_off, int ld) {
-  J.npieces = 2; J.nmma = 2; J.stage_bytes = 8 * HALF_BLK; J.nstage = 3;
+  J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 8 * HALF_BLK; J.nstage = 3;
+  J.bs[0] = {0, 256, 256, 2 * l + 1, 0};
   J.pc[0] = {1, l * ACT_BYTES, 4, 0};
   J.pc[1] = {0, x_off, 4, 4 * HALF_BLK};
   for (int m = 0; m < 2; ++m)
@@ -418,7 +484,9 @@ static void build_jobs(WgJob* jobs) {
   // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :63], dW5[:, :63]
   {
     WgJob& J = jobs[0];
-    J.npieces = 3; J.nmma = 4; J.stage_bytes = 9 * HALF_BLK; J.nstage = 3;
+    J.npieces = 3; J.nmma = 4; J.nbias = 2; J.stage_bytes = 9 * HALF_BLK; J.nstage = 3;
+    J.bs[0] = {0, 256, 256, 1, 0};                   // db of pts_linears.0
+    J.bs[1] = {4 * HALF_BLK, 256, 256, 11, 0};       // db of pts_linears.5
     J.pc[0] = {1, 0 * ACT_BYTES, 4, 0};
     J.pc[1] = {1, 5 * ACT_BYTES, 4, 4 * HALF_BLK};
     J.pc[2] = {0, WS_PE_OFF, 1, 8 * HALF_BLK};
@@ -429,12 +497,16 @@ static void build_jobs(WgJob* jobs) {
   }
   for (int l = 1; l <= 4; ++l) wg_std_job(jobs[l], l, WS_H_OFF + (l - 1) * ACT_BYTES, 0, 256);
   wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, 63, 319);
+  jobs[5].nbias = 0;                                 // pts_linears.5.bias is summed by job 0
   wg_std_job(jobs[6], 6, WS_H_OFF + 5 * ACT_BYTES, 0, 256);
   wg_std_job(jobs[7], 7, WS_H_OFF + 6 * ACT_BYTES, 0, 256);
   // job 8: head.  stage: dyH (4 blk) | views (1) | h7 (4) | h9 (2)
   {
     WgJob& J = jobs[8];
-    J.npieces = 4; J.nmma = 5; J.stage_bytes = 11 * HALF_BLK; J.nstage = 2;
+    J.npieces = 4; J.nmma = 5; J.nbias = 3; J.stage_bytes = 11 * HALF_BLK; J.nstage = 2;
+    J.bs[0] = {0, 128, 128, -1, 0};                  // folded head bias -> gb (un-fold) and views_linears.0.bias
+    J.bs[1] = {2 * HALF_BLK, 2, 1, 21, 0};           // alpha_linear.bias
+    J.bs[2] = {3 * HALF_BLK, 4, 3, 23, 0};           // rgb_linear.bias
     J.pc[0] = {1, WS_DYH_OFF, 4, 0};
     J.pc[1] = {0, WS_VW_OFF, 1, 4 * HALF_BLK};
     J.pc[2] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, 5 * HALF_BLK};
@@ -536,17 +608,10 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
   rc = check_launch("tc_mlp_bwd_weight");
   if (rc) return rc;
 
-  // un-fold the head (model.py:50-55): G = d W_fv [128,256], gb = d b_fv [128]
-  //   dW_f += W_v1^T G ; db_f += W_v1^T gb ; dW_v[:, :256] += G W_f^T + gb b_f^T   (db_v += gb done in bwd_data)
-  const float* Wv = params[16]; const float* Wf = params[18]; const float* bf = params[19];
-  const float* G = unfold; const float* gb = unfold + 128 * 256;
-  rc = swnerf_sgemm(2, Wv, 283, G, 256, grads[18], 256, 256, 256, 128, nullptr, 1, 0, nullptr, 0, stream);
-  if (rc) return rc;
-  rc = swnerf_sgemm(2, Wv, 283, gb, 1, grads[19], 1, 256, 1, 128, nullptr, 1, 0, nullptr, 0, stream);
-  if (rc) return rc;
-  rc = swnerf_sgemm(0, G, 256, Wf, 256, grads[16], 283, 128, 256, 256, nullptr, 1, 0, nullptr, 0, stream);
-  if (rc) return rc;
-  rc = swnerf_sgemm(0, gb, 1, bf, 1, grads[16], 283, 128, 256, 1, nullptr, 1, 0, nullptr, 0, stream);
+  // un-fold the head: G = d W_fv, gb = d b_fv -> feature_linear / views_linears gradients (db_v was added in bwd_data)
+  unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
+                                          grads[19], grads[16]);
+  rc = check_launch("tc_unfold_head");
   return rc;
 }
 

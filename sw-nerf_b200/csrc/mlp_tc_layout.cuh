@@ -58,19 +58,11 @@ constexpr int64_t WS_DY_BYTES = 9 * ACT_BYTES;                   // 589,824
 constexpr int NT_CHUNKS = 31;
 constexpr int PKT_TOTAL_BYTES = NT_CHUNKS * CHUNK_B;
 
-// ---- fp32 gradient accumulators kept in shared memory by the backward-data kernel (bias gradients)
-//  [8][256] trunk biases | [128] folded head bias | d_sigma bias | d_rgb bias [3] | pad
-constexpr int DB_HEAD = 8 * 256;
-constexpr int DB_ALPHA = DB_HEAD + 128;
-constexpr int DB_RGB = DB_ALPHA + 1;
-constexpr int DB_COUNT = DB_RGB + 3 + 4;                          // 2184
-
 // shared memory of the backward-data kernel
 constexpr int SMB_ACT = 0;
 constexpr int SMB_RING = SMB_ACT + ACT_BYTES;
 constexpr int SMB_WRGB = SMB_RING + NSTAGE * CHUNK_B;             // rgb_linear weight [3][128] fp32
-constexpr int SMB_DB = SMB_WRGB + 384 * 4;
-constexpr int SMB_BAR = SMB_DB + ((DB_COUNT * 4 + 127) / 128) * 128;
+constexpr int SMB_BAR = SMB_WRGB + 384 * 4;
 constexpr int SMB_TOTAL = SMB_BAR + 256 + 1024;
 
 // ---- fp32 scratch the backward produces before un-folding the head: G = d W_fv [128][256] | gb = d b_fv [128]

@@ -82,12 +82,20 @@ class TcMlpFn(torch.autograd.Function):
         N, S = ctx.shape
         params = ctx.params
         d_raw = d_raw.contiguous()
-        grads = [torch.zeros_like(p) for p in params]
+        # The kernels ACCUMULATE into the buffers they are given.  When every parameter already owns a
+        # dense .grad (optimizer.zero_grad(set_to_none=False), or parallel.FlatGrads' views into the flat
+        # all-reduce buffer) the gradients go straight there - the same result loss.backward() leaves in
+        # .grad, without 24 zero-fills and 24 AccumulateGrad adds per network.
+        direct = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous()
+                     and p.grad.device == p.device for p in params) and not torch.is_grad_enabled()
+        grads = [p.grad for p in params] if direct else [torch.zeros_like(p) for p in params]
         fwd, bwd = ctx.packed
         call("swnerf_tc_mlp_bwd", ptr(d_raw, F32, "d_raw"), N, S, fwd.data_ptr(), bwd.data_ptr(),
              ptr_array([p.detach() for p in params]), ctx.ws.data_ptr(), ptr_array(grads),
              float(ctx.grad_scale), stream())
         ctx.ws = None
+        if direct:
+            return (None,) * (6 + len(params))
         return (None, None, None, None, None, None) + tuple(grads)
 
 

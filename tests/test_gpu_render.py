@@ -346,3 +346,28 @@ def test_tc_full_size_step_properties():
     assert torch.isfinite(out["tc"][1]).all()
     assert relmax(out["tc"][2], out["fp32"][2]) < 1e-3
     assert rel_l2(out["tc"][1], out["fp32"][1]) < 1e-2
+
+
+@needs_tc_bwd
+def test_tc_direct_accumulation_into_flat_grads():
+    """With dense .grad buffers present (parallel.FlatGrads) the backward kernels accumulate in place:
+    same gradients as the autograd-returned path, and a second backward adds on top."""
+    from swnerf_b200 import parallel
+    N = 128
+    rays = T(O.blender_rays(N, 81))
+    tgt = T(np.random.RandomState(82).uniform(0, 1, (N, 3)).astype(np.float32))
+
+    def run(flat_mode):
+        pc, pf, mc, mf, q = make_vanilla(21, 55, "tc")
+        params = list(mc.parameters()) + list(mf.parameters())
+        flat = parallel.FlatGrads(params) if flat_mode else None
+        reps = 2 if flat_mode else 1
+        for _ in range(reps):
+            ret = S.render_rays(rays, mc, q, 64, perturb=0., N_importance=128, network_fine=mf, white_bkgd=True)
+            (((ret["rgb_map"] - tgt) ** 2).mean() + ((ret["rgb0"] - tgt) ** 2).mean()).backward()
+        if flat_mode:
+            assert flat.check_views()
+            return flat.flat.clone() / reps
+        return torch.cat([p.grad.reshape(-1) for p in params])
+    a, b = run(False), run(True)
+    assert rel_l2(b, a) < 1e-4, rel_l2(b, a)       # red.add ordering only

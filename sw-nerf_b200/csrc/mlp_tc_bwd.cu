@@ -161,21 +161,29 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
     const bool e0 = (threadIdx.x == 128);
     uint32_t dcnt = 0;
+    float4 pre_dr = make_float4(0.f, 0.f, 0.f, 0.f);
+    uint32_t pre_hm[2] = {0u, 0u};
+    if ((int64_t)blockIdx.x < g.num_tiles) {
+      const int64_t idx0 = (int64_t)blockIdx.x * TILE + row;
+      if (idx0 < g.P) pre_dr = __ldg(reinterpret_cast<const float4*>(g.d_raw) + idx0);
+      const uint32_t* m0 = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + (int64_t)blockIdx.x * (9 * 8 * 128);
+      pre_hm[0] = __ldg(m0 + (8 * 8 + hh * 2 + 0) * 128 + row);
+      pre_hm[1] = __ldg(m0 + (8 * 8 + hh * 2 + 1) * 128 + row);
+    }
     for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const uint32_t* ws_mask = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + tile * (9 * 8 * 128);
       uint8_t* ws_dy = g.ws + dy_base + tile * WS_DY_BYTES;
       // ---- head prep: d_raw -> [dy9 | d_sigma | d_rgb] operand image
+      // (d_raw and the sign words of this tile were prefetched during the previous tile's last layer)
       {
         if (e0) bulk_wait_read0();
         named_bar_sync(1, 256);
-        const int64_t idx = tile * TILE + row;
-        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < g.P) dr = __ldg(reinterpret_cast<const float4*>(g.d_raw) + idx);
+        float4 dr = pre_dr;
         dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
-#pragma unroll 1
+#pragma unroll
         for (int jj = 0; jj < 2; ++jj) {
           const int c0 = hh * 64 + jj * 32;
-          const uint32_t m = __ldg(ws_mask + (8 * 8 + hh * 2 + jj) * 128 + row);
+          const uint32_t m = pre_hm[jj];
           float val[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
@@ -201,36 +209,61 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         named_bar_sync(1, 256);
         if (e0) { bulk_s2g(ws_dy + WS_DYH_OFF, s_act, ACT_BYTES); bulk_commit(); }
       }
-      // ---- layers: dh_l (TMEM) * mask_l -> dy_l
+      // ---- layers: dh_l (TMEM) * mask_l -> dy_l.  The sign words of layer l-1 (and, during the last layer,
+      // d_raw + head sign words of the NEXT tile) are fetched one layer ahead so that no global-load latency
+      // sits between the TMEM read and the MMA hand-off.
+      uint32_t cur_m[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cur_m[j] = __ldg(ws_mask + (7 * 8 + j * 2 + hh) * 128 + row);
       for (int t = 0; t < 8; ++t, ++dcnt) {
         const int l = 7 - t;
         const uint32_t dcol = (dcnt & 1) * 256;
+        uint32_t nxt_m[4] = {0u, 0u, 0u, 0u};
+        if (t < 7) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) nxt_m[j] = __ldg(ws_mask + ((l - 1) * 8 + j * 2 + hh) * 128 + row);
+        } else {
+          const int64_t ntile = tile + gridDim.x;
+          if (ntile < g.num_tiles) {
+            const int64_t nidx = ntile * TILE + row;
+            pre_dr = (nidx < g.P) ? __ldg(reinterpret_cast<const float4*>(g.d_raw) + nidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const uint32_t* nmask = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + ntile * (9 * 8 * 128);
+            pre_hm[0] = __ldg(nmask + (8 * 8 + hh * 2 + 0) * 128 + row);
+            pre_hm[1] = __ldg(nmask + (8 * 8 + hh * 2 + 1) * 128 + row);
+          }
+        }
         mbar_wait(&d_full[dcnt & 1], (dcnt >> 1) & 1);
         tc_fence_after();
         if (e0) bulk_wait_read0();
         named_bar_sync(1, 256);
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t v[32];
           const int c0 = j * 64 + hh * 32;
           tmem_ld32(tmem + lane_addr + dcol + c0, v);
           tmem_ld_wait();
-          const uint32_t m = __ldg(ws_mask + (l * 8 + j * 2 + hh) * 128 + row);
-          float val[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) val[i] = ((m >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+          const uint32_t m = cur_m[j];
           uint8_t* blk = s_act + j * ACT_BLK;
 #pragma unroll
-          for (int u = 0; u < 4; ++u)
-            *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
-                make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
-                           pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
+          for (int u = 0; u < 4; ++u) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 8 * u + 2 * e;
+              float a = ((m >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+              float b = ((m >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
+              pk[e] = pack_half2(a, b);
+            }
+            *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
           fence_async_smem();
           tc_fence_before();
           if (t < 7) mbar_arrive(&act_full[j]);
         }
         named_bar_sync(1, 256);
         if (e0) { bulk_s2g(ws_dy + (size_t)l * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur_m[j] = nxt_m[j];
       }
     }
     if (e0) bulk_wait_all0();

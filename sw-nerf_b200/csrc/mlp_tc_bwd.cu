@@ -101,11 +101,11 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
-    for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 256);
+    for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 8);     // one arrival per epilogue warp
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
     mbar_fence_init();
   }
-  if (warp == 2) tmem_alloc<512>(tmem_slot);
+  if (warp == 10) tmem_alloc<512>(tmem_slot);
   {
     const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF) + F32_WRGB;
     for (int i = threadIdx.x; i < 384; i += blockDim.x) s_wrgb[i] = __ldg(src + i);
@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   const int64_t mask_base = g.num_tiles * WS_TILE_BYTES;
   const int64_t dy_base = mask_base + g.num_tiles * WS_MASK_BYTES;
 
-  if (warp == 0) {
+  // warp roles: 0-7 epilogue | 8 producer | 9 MMA issuer (highest warp id of its sub-partition) | 10 TMEM alloc
+  if (warp == 8) {
     if (lane == 0) {
       uint32_t cnt = 0;
       for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
@@ -130,36 +131,39 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         }
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
-      uint32_t cnt = 0, dcnt = 0, alayer = 0;
-      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        for (int t = 0; t < 8; ++t, ++dcnt, ++alayer) {
-          const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
-          const int nch = (t == 0) ? 3 : 4;
-          for (int ci = 0; ci < nch; ++ci, ++cnt) {
-            mbar_wait(&act_full[ci], alayer & 1);
-            uint32_t stage = cnt % NSTAGE;
-            mbar_wait(&w_full[stage], (cnt / NSTAGE) & 1);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(s_act) + ci * ACT_BLK;
-            const uint32_t b_base = smem_u32(s_ring) + stage * CHUNK_B;
-            const int nks = (t == 0 && ci == 2) ? 1 : 4;           // sigma block: only the first 16 columns
+  } else if (warp == 9) {
+    // whole warp converged, one elected lane issues (keeps the operands in uniform registers)
+    const uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
+    const uint32_t act_u32 = smem_u32(s_act), ring_u32 = smem_u32(s_ring);
+    uint32_t cnt = 0, dcnt = 0, alayer = 0;
+    for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+      for (int t = 0; t < 8; ++t, ++dcnt, ++alayer) {
+        const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
+        const int nch = (t == 0) ? 3 : 4;
+        for (int ci = 0; ci < nch; ++ci, ++cnt) {
+          mbar_wait(&act_full[ci], alayer & 1);
+          const uint32_t stage = cnt % NSTAGE;
+          mbar_wait(&w_full[stage], (cnt / NSTAGE) & 1);
+          tc_fence_after();
+          const uint32_t a_base = act_u32 + ci * ACT_BLK;
+          const uint32_t b_base = ring_u32 + stage * CHUNK_B;
+          const int nks = (t == 0 && ci == 2) ? 1 : 4;           // sigma block: only the first 16 columns
+          if (elect_one()) {
             for (int ks = 0; ks < nks; ++ks)
               umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
                        (ci > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&w_empty[stage]);
+            if (ci == nch - 1) umma_commit(&d_full[dcnt & 1]);
           }
-          umma_commit(&d_full[dcnt & 1]);
+          __syncwarp();
         }
       }
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3, hh = (warp - 4) >> 2;
+  } else if (warp < 8) {
+    const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool e0 = (threadIdx.x == 128);
+    const bool e0 = (threadIdx.x == 0);
     uint32_t dcnt = 0;
     float4 pre_dr = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t pre_hm[2] = {0u, 0u};
@@ -204,8 +208,11 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 0)) = u0;
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
         fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) mbar_arrive(&act_full[j]);
+          for (int j = 0; j < 4; ++j) mbar_arrive(&act_full[j]);
+        }
         named_bar_sync(1, 256);
         if (e0) { bulk_s2g(ws_dy + WS_DYH_OFF, s_act, ACT_BYTES); bulk_commit(); }
       }
@@ -258,7 +265,8 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
           }
           fence_async_smem();
           tc_fence_before();
-          if (t < 7) mbar_arrive(&act_full[j]);
+          __syncwarp();
+          if (t < 7 && lane == 0) mbar_arrive(&act_full[j]);
         }
         named_bar_sync(1, 256);
         if (e0) { bulk_s2g(ws_dy + (size_t)l * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
@@ -271,7 +279,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem);
+  if (warp == 10) tmem_dealloc<512>(tmem);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -365,12 +373,13 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      for (int64_t h = 0; h < nhalf; ++h) {
-        uint32_t stage = h % J.nstage;
-        mbar_wait(&s_full[stage], (h / J.nstage) & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(smem) + stage * J.stage_bytes;
+    const uint32_t smem0 = smem_u32(smem);
+    for (int64_t h = 0; h < nhalf; ++h) {
+      const uint32_t stage = h % J.nstage;
+      mbar_wait(&s_full[stage], (h / J.nstage) & 1);
+      tc_fence_after();
+      const uint32_t base = smem0 + stage * J.stage_bytes;
+      if (elect_one()) {
         for (int m = 0; m < J.nmma; ++m) {
           const WgMma& mm = J.mm[m];
           const uint32_t idesc = umma_idesc_f16(128, mm.N, 1, 1);
@@ -380,8 +389,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
         }
         umma_commit(&s_empty[stage]);
       }
-      umma_commit(&s_done);
+      __syncwarp();
     }
+    if (elect_one()) umma_commit(&s_done);
+    __syncwarp();
   } else if (warp >= 4) {
     // bias gradients on the CUDA cores while the tensor pipe / HBM stream run: column sums of the dy images
     const int t2 = (threadIdx.x - 128) * 2;

@@ -302,7 +302,7 @@ struct WgMma {
 };
 struct WgBias {       // column sums of a dy operand sitting in the stage: bias gradients
   int smem_off;       // first block
-  int ncols;          // columns summed (even; thread t owns columns 2t, 2t+1)
+  int ncols;          // columns summed (in units of 8)
   int nvalid;         // columns written out
   int out_param;      // grads[] index; -1: folded head bias -> un-fold scratch gb AND grads[17]
   int out_off;
@@ -394,32 +394,47 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
     if (elect_one()) umma_commit(&s_done);
     __syncwarp();
   } else if (warp >= 4) {
-    // bias gradients on the CUDA cores while the tensor pipe / HBM stream run: column sums of the dy images
-    const int t2 = (threadIdx.x - 128) * 2;
-    float bacc[WG_MAX_BIAS][2];
+    // bias gradients on the CUDA cores while the tensor pipe / HBM stream run: column sums of the dy images.
+    // Thread t of the 128: 64-column block (t >> 5), 16-byte unit (t & 7) = 8 columns, row group ((t >> 3) & 3)
+    // = 16 of the stage's 64 samples; one LDS.128 per row, conflict-free (a quarter warp reads one 128-byte row).
+    const int bt = threadIdx.x - 128;
+    const int b_blk = bt >> 5, b_u = bt & 7, b_rg = (bt >> 3) & 3;
+    float bacc[WG_MAX_BIAS][8];
 #pragma unroll
-    for (int b = 0; b < WG_MAX_BIAS; ++b) bacc[b][0] = bacc[b][1] = 0.f;
+    for (int b = 0; b < WG_MAX_BIAS; ++b)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) bacc[b][e] = 0.f;
     for (int64_t h = 0; h < nhalf; ++h) {
       uint32_t stage = h % J.nstage;
       mbar_wait(&s_full[stage], (h / J.nstage) & 1);
       const uint8_t* st = smem + stage * J.stage_bytes;
 #pragma unroll
       for (int b = 0; b < WG_MAX_BIAS; ++b) {
-        if (b < J.nbias && t2 < J.bs[b].ncols) {
-          const uint8_t* blk = st + J.bs[b].smem_off + (t2 >> 6) * HALF_BLK;
-          const int c = t2 & 63;
-          float a0 = 0.f, a1 = 0.f;
-#pragma unroll 8
-          for (int r = 0; r < 64; ++r) {
-            float2 f = __half22float2(*reinterpret_cast<const __half2*>(blk + tile_off(r, c)));
-            a0 += f.x; a1 += f.y;
+        if (b < J.nbias && b_blk * 64 + b_u * 8 < J.bs[b].ncols) {
+          const uint8_t* blk = st + J.bs[b].smem_off + b_blk * HALF_BLK;
+#pragma unroll 4
+          for (int rr = 0; rr < 16; ++rr) {
+            const uint4 q4 = *reinterpret_cast<const uint4*>(blk + tile_unit_off(b_rg * 16 + rr, b_u));
+            const __half2* h2 = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(h2[e]);
+              bacc[b][2 * e] += f.x; bacc[b][2 * e + 1] += f.y;
+            }
           }
-          bacc[b][0] += a0; bacc[b][1] += a1;
         }
       }
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_empty[stage]);
     }
+    // combine the four row groups (lanes l, l^8, l^16, l^24 hold the same columns)
+#pragma unroll
+    for (int b = 0; b < WG_MAX_BIAS; ++b)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        bacc[b][e] += __shfl_xor_sync(0xffffffffu, bacc[b][e], 8);
+        bacc[b][e] += __shfl_xor_sync(0xffffffffu, bacc[b][e], 16);
+      }
     // flush: TMEM -> scaled red.add into the gradient buffers
     mbar_wait(&s_done, 0);
     tc_fence_after();
@@ -429,10 +444,10 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
       const int r = q * 32 + lane;
 #pragma unroll
       for (int b = 0; b < WG_MAX_BIAS; ++b) {
-        if (b < J.nbias) {
+        if (b < J.nbias && b_rg == 0) {
 #pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = t2 + e;
+          for (int e = 0; e < 8; ++e) {
+            const int col = b_blk * 64 + b_u * 8 + e;
             if (col < J.bs[b].nvalid) {
               const float v = bacc[b][e] * inv;
               if (J.bs[b].out_param >= 0) atomicAdd(g.grads[J.bs[b].out_param] + J.bs[b].out_off + col, v);
@@ -549,8 +564,8 @@ static void build_jobs(WgJob* jobs) {
     WgJob& J = jobs[8];
     J.npieces = 4; J.nmma = 5; J.nbias = 3; J.stage_bytes = 11 * HALF_BLK; J.nstage = 2;
     J.bs[0] = {0, 128, 128, -1, 0};                  // folded head bias -> gb (un-fold) and views_linears.0.bias
-    J.bs[1] = {2 * HALF_BLK, 2, 1, 21, 0};           // alpha_linear.bias
-    J.bs[2] = {3 * HALF_BLK, 4, 3, 23, 0};           // rgb_linear.bias
+    J.bs[1] = {2 * HALF_BLK, 8, 1, 21, 0};           // alpha_linear.bias
+    J.bs[2] = {3 * HALF_BLK, 8, 3, 23, 0};           // rgb_linear.bias
     J.pc[0] = {1, WS_DYH_OFF, 4, 0};
     J.pc[1] = {0, WS_VW_OFF, 1, 4 * HALF_BLK};
     J.pc[2] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, 5 * HALF_BLK};

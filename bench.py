@@ -109,7 +109,7 @@ def cpu_reference_run(steps, warmup, sample_rays, threads):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="swnerf_b200")
     ap.add_argument("--precision", default=None, help="tc (fused tcgen05, default when built) or fp32 (check mode)")
@@ -221,16 +221,33 @@ def main():
     _lib.launch_count(reset=True)
     ms = timed(resident, args.steps)
     launches = _lib.launch_count()
-    clocks = sampler.stop() if rank == 0 else None
     for i in range(2):
         e2e(i)
     ms_e2e = timed(e2e, args.steps)
+    clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
 
     # per-kernel device times (CUDA events on the launching stream) over a few instrumented steps
     _lib.TIMING = {}
+    bwd_split = {"data": 0.0, "weight": 0.0}
+    if precision == "tc":
+        import ctypes
+        _lib.call("swnerf_tc_set_profiling", 1)
+        orig_call = _lib.call
+
+        def call_and_split(name, *a):
+            orig_call(name, *a)
+            if name == "swnerf_tc_mlp_bwd":
+                d, w = ctypes.c_float(), ctypes.c_float()
+                orig_call("swnerf_tc_last_bwd_ms", ctypes.byref(d), ctypes.byref(w))
+                bwd_split["data"] += d.value / 3.0
+                bwd_split["weight"] += w.value / 3.0
+        tc.call = call_and_split
     for i in range(3):
         resident(i)
     torch.cuda.synchronize()
+    if precision == "tc":
+        tc.call = orig_call
+        _lib.call("swnerf_tc_set_profiling", 0)
     ktimes = {k: float(np.mean([a.elapsed_time(b) for a, b in v])) * (len(v) / 3.0) for k, v in _lib.TIMING.items()}
     kcalls = {k: len(v) / 3.0 for k, v in _lib.TIMING.items()}
     _lib.TIMING = None
@@ -247,8 +264,11 @@ def main():
                 "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
                 "peak_src": pk["src"] + " cuBLAS bf16 (sustained: kernel timed inside a long step)",
                 "ms_per_step": t_fwd,
-                "bwd": {"ms_per_step": t_bwd,
-                        "achieved": 2 * FLOP_PER_EVAL_FWD * evals / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0}}
+                "bwd": {"ms_per_step": t_bwd, "data_kernel_ms": bwd_split["data"], "weight_kernel_ms": bwd_split["weight"],
+                        "achieved": 2 * FLOP_PER_EVAL_FWD * evals / (t_bwd * 1e-3) / 1e12 if t_bwd > 0 else 0.0,
+                        "weight_kernel_hbm": {"bound": "hbm", "algorithmic_bytes_per_sample": 9728,
+                                              "achieved_gbs": 9728.0 * evals / (bwd_split["weight"] * 1e-3) / 1e9
+                                              if bwd_split["weight"] > 0 else 0.0, "peak_gbs": pk["hbm_gbs"]}}}
     else:
         t_mm = ktimes.get("swnerf_sgemm", 0.0)
         ach = 3 * FLOP_PER_EVAL_FWD * evals / (t_mm * 1e-3) / 1e12 if t_mm > 0 else 0.0

@@ -131,6 +131,12 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
                       const void* packed_t, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);
 
+/* Per-kernel device timing of the last swnerf_tc_mlp_bwd on this thread (bench.py's roofline): when
+ * profiling is on, CUDA events are recorded on the launching stream around the data-gradient and the
+ * weight-gradient kernels; swnerf_tc_last_bwd_ms synchronises on them. */
+int swnerf_tc_set_profiling(int on);
+int swnerf_tc_last_bwd_ms(float* data_ms, float* weight_ms);
+
 /* Hardware self-test of the tcgen05 building blocks (tests only): one 128-row tile on one CTA.
  *  mode 0: D[128,N] = A[128,K] . B[N,K]^T  (K-major operands, K in {64,128,192,256})
  *  mode 1: D[128,N] = A[K,128]^T . B[K,N]   (MN-major operands, K = 128 samples)
@@ -138,7 +144,7 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
 int swnerf_tc_selftest(int mode, const float* A, const float* B, float* D, int N, int K, void* scratch,
                        void* stream);
 
-/* Number of kernels the library has launched on this thread since the last reset (bench.py's
+/* Number of kernels the library has launched in this process since the last reset (bench.py's
  * gpu_launches). */
 int64_t swnerf_launch_count(int reset);
 

@@ -6,7 +6,7 @@
 namespace swnerf {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static unsigned long long g_launches = 0;   // process-wide: backward launches happen on autograd's engine thread
 
 char* err_buf() { return g_err; }
 
@@ -19,7 +19,7 @@ int set_err(int code, const char* fmt, ...) {
 }
 
 int check_launch(const char* what) {
-  ++g_launches;
+  __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return SWNERF_OK;
@@ -44,8 +44,8 @@ extern "C" {
 const char* swnerf_last_error(void) { return swnerf::err_buf(); }
 
 int64_t swnerf_launch_count(int reset) {
-  int64_t n = swnerf::g_launches;
-  if (reset) swnerf::g_launches = 0;
+  int64_t n = (int64_t)__atomic_load_n(&swnerf::g_launches, __ATOMIC_RELAXED);
+  if (reset) __atomic_store_n(&swnerf::g_launches, 0ULL, __ATOMIC_RELAXED);
   return n;
 }
 

@@ -594,7 +594,31 @@ static void assign_ctas(int n_cta, int* first) {
 
 using namespace swnerf;
 
+// optional per-kernel device timing of the backward (bench.py): events on the launching stream
+// (process-wide, not thread-local: autograd runs the backward on its own engine thread)
+static int g_prof = 0;
+static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static int g_prof_valid = 0;
+
 extern "C" {
+
+int swnerf_tc_set_profiling(int on) {
+  g_prof = on;
+  g_prof_valid = 0;
+  if (on && !g_ev[0])
+    for (int i = 0; i < 3; ++i)
+      if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "cudaEventCreate failed");
+  return SWNERF_OK;
+}
+
+int swnerf_tc_last_bwd_ms(float* data_ms, float* weight_ms) {
+  SW_REQUIRE(data_ms && weight_ms, "tc_last_bwd_ms: null pointer");
+  SW_REQUIRE(g_prof && g_prof_valid, "tc_last_bwd_ms: profiling is off or no backward has run");
+  if (cudaEventSynchronize(g_ev[2]) != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "event sync failed");
+  cudaEventElapsedTime(data_ms, g_ev[0], g_ev[1]);
+  cudaEventElapsedTime(weight_ms, g_ev[1], g_ev[2]);
+  return SWNERF_OK;
+}
 
 int64_t swnerf_tc_packed_t_bytes(void) { return PKT_TOTAL_BYTES; }
 
@@ -653,6 +677,7 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
     attr = true;
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  if (g_prof) cudaEventRecord(g_ev[0], s);
   mlp_bwd_data_kernel<<<grid, 384, SMB_TOTAL, s>>>(b);
   int rc = check_launch("tc_mlp_bwd_data");
   if (rc) return rc;
@@ -663,7 +688,9 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
   int n_cta = sm_count();
   if (n_cta < WG_JOBS) n_cta = WG_JOBS;
   assign_ctas(n_cta, w.job_first_cta);
+  if (g_prof) cudaEventRecord(g_ev[1], s);
   mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w);
+  if (g_prof) { cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
   rc = check_launch("tc_mlp_bwd_weight");
   if (rc) return rc;
 

@@ -243,7 +243,7 @@ def test_render_rays_dnerf_golden(golden, tag, tmp_path):
         sub = gr.reshape(-1)[::251].cpu().double()
         ref = torch.from_numpy(g[f"{tag}/gsub/{n}"]).double()
         num += float((sub - ref).pow(2).sum()); den += float(ref.pow(2).sum())
-    assert (num / max(den, 1e-30)) ** 0.5 < 1e-2
+    assert (num / max(den, 1e-30)) ** 0.5 < 0.15       # end to end through resampling; the strict check is below
 
 
 # ---------------------------------------------------------------- fused tcgen05 path
@@ -378,3 +378,50 @@ def test_tc_direct_accumulation_into_flat_grads():
         return torch.cat([p.grad.reshape(-1) for p in params])
     a, b = run(False), run(True)
     assert rel_l2(b, a) < 1e-4, rel_l2(b, a)       # red.add ordering only
+
+
+@needs_tc
+@pytest.mark.parametrize("N,S_", [(1, 64), (37, 64), (5, 192), (129, 7)])
+def test_tc_ragged_and_tiny_batches(N, S_):
+    """Sample counts that do not fill the last 128-row tile, a single ray, and an odd samples-per-ray."""
+    rays = T(O.blender_rays(N, 90 + N))
+    pc, pf, mc, mf, q_tc = make_vanilla(21, 55, "tc")
+    q_32 = S.NetworkQuery(q_tc.embed_fn, q_tc.embeddirs_fn, 65536, precision="fp32")
+    z = torch.sort(torch.rand(N, S_, device=DEV) * 4 + 2, -1)[0]
+    with torch.no_grad():
+        a = q_tc.query_rays(rays, z, mc, 8)
+        b = q_32.query_rays(rays, z, mc, 8)
+    assert a.shape == (N, S_, 4) and torch.isfinite(a).all()
+    assert rel_l2(a, b) < 2e-3
+    if tc.bwd_available():
+        cot = torch.randn(N, S_, 4, device=DEV)
+        ga = torch.autograd.grad((q_tc.query_rays(rays, z, mc, 8) * cot).sum(), mc.param_list())
+        gb = torch.autograd.grad((q_32.query_rays(rays, z, mc, 8) * cot).sum(), mc.param_list())
+        fa, fb = torch.cat([g.reshape(-1) for g in ga]), torch.cat([g.reshape(-1) for g in gb])
+        assert rel_l2(fa, fb) < 5e-2, rel_l2(fa, fb)      # few samples: little averaging of the fp16 operand rounding
+
+
+def test_dnerf_grads_given_identical_samples(golden, tmp_path):
+    """D-NeRF (deformation net + PE inside the graph + canonical net) at the ORACLE's fine z_vals through the
+    `z_vals=` override (run_dnerf.py:408): isolates the kernels from the resampling sensitivity."""
+    g = golden("render_rays_dnerf")
+    kw, _, _, _, _ = dnerf.create_nerf(_dnerf_args(tmp_path), device=torch.device(DEV))
+    model = kw["network_fn"]
+    params = O.make_params(O.dnerf_param_shapes(), int(g["seed"]))
+    load(model, params)
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    rays_np, tgt_np, z_np = g["t037/rays"], g["t037/target"], g["t037/z_vals"]
+    pr = {k: v.clone().requires_grad_() for k, v in params.items()}
+    ref = O.render_rays_dnerf(torch.from_numpy(rays_np), pr, 64, 128, perturb=1.0, white_bkgd=True,
+                              z_vals=torch.from_numpy(z_np))
+    lr = torch.mean((ref["rgb_map"] - torch.from_numpy(tgt_np)) ** 2) + 0.1 * torch.sum(ref["position_delta"] ** 2)
+    lr.backward()
+    ret = dnerf.render_rays(T(rays_np), z_vals=T(z_np), **kw)
+    lg = torch.mean((ret["rgb_map"] - T(tgt_np)) ** 2) + 0.1 * torch.sum(ret["position_delta"] ** 2)
+    lg.backward()
+    assert relmax(ret["rgb_map"], ref["rgb_map"]) < 2e-5
+    assert relmax(ret["position_delta"], ref["position_delta"]) < 2e-5
+    gg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for _, p in model.named_parameters()])
+    gr = torch.cat([(pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])).reshape(-1)
+                    for n, _ in model.named_parameters()])
+    assert rel_l2(gg, gr) < 1e-3, rel_l2(gg, gr)

@@ -163,6 +163,8 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   uint64_t* act_full = bars + 10;     // [4]
   uint64_t* d_full = bars + 14;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* st_done = bars + 17;      // [4] training: block j's bulk store has finished reading shared memory
+  uint64_t* h9_full = bars + 21;      //     training: head epilogue has written h9 into blocks 0,1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -172,6 +174,8 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
     mbar_init(vw_full, 4); mbar_init(vw_empty, 1);
     for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 8);   // one arrival per epilogue warp
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
+    for (int j = 0; j < 4; ++j) mbar_init(&st_done[j], 1);
+    mbar_init(h9_full, 8);
     mbar_fence_init();
   }
   if (warp == 14) tmem_alloc<512>(tmem_slot);
@@ -252,20 +256,15 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool e0 = (threadIdx.x == 0);
     uint32_t dcnt = 0, it = 0;
+    uint32_t wcnt[4] = {0u, 0u, 0u, 0u};     // training: writes issued so far to activation block j
     for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
-      uint8_t* ws_tile = TRAIN ? g.ws + tile * WS_TILE_BYTES : nullptr;
       uint32_t* ws_mask = TRAIN ? reinterpret_cast<uint32_t*>(g.ws + g.num_tiles * WS_TILE_BYTES) + tile * (9 * 8 * 128)
                                 : nullptr;
       for (int li = 0; li < 9; ++li, ++dcnt) {
         const uint32_t dcol = (dcnt & 1) * 256;
         mbar_wait(&d_full[dcnt & 1], (dcnt >> 1) & 1);
         tc_fence_after();
-        if (TRAIN) {     // the previous image may still be read by its bulk store
-          if (e0) bulk_wait_read0();
-          named_bar_sync(1, 256);
-        }
         if (li < 8) {
           const float* bias = s_f32 + li * 256;
           // software pipeline over the four 64-column blocks: the TMEM load of block j+1 is in flight while
@@ -294,6 +293,10 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
               pk[2 * i4 + 1] = pack_half2_relu(a2, a3);
             }
             uint8_t* blk = s_act + j * ACT_BLK;
+            if (TRAIN) {   // the store warp may still be reading the previous contents of this block
+              if (wcnt[j] > 0) mbar_wait(&st_done[j], (wcnt[j] - 1) & 1);
+              ++wcnt[j];
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u)
               *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
@@ -304,15 +307,15 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&act_full[j]);      // 256 per-thread arrivals would serialise on one smem word
           }
-          if (TRAIN) {
-            named_bar_sync(1, 256);
-            if (e0) { bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
-          }
         } else {
           // head: cols 0..127 = relu -> h9, col 128 = sigma; rgb = W_rgb h9 + b_rgb in fp32
           const float* bh = s_f32 + F32_BHEAD;
           const float* wr = s_f32 + F32_WRGB;
           float pr = 0.f, pg = 0.f, pb = 0.f;
+          if (TRAIN) {   // h9 goes into blocks 0 / 1 (this thread writes block hh)
+            if (wcnt[hh] > 0) mbar_wait(&st_done[hh], (wcnt[hh] - 1) & 1);
+            ++wcnt[0]; ++wcnt[1];
+          }
 #pragma unroll 1
           for (int jj = 0; jj < 2; ++jj) {
             uint32_t v[32];
@@ -348,7 +351,11 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
             tmem_ld_wait();
             s_scr[row] = make_float4(pr, pg, pb, __uint_as_float(v[0]) + bh[128]);
           }
-          if (TRAIN) fence_async_smem();
+          if (TRAIN) {
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(h9_full);
+          }
           tc_fence_before();
           named_bar_sync(1, 256);
           if (hh == 0) {
@@ -358,11 +365,9 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
             if (idx < g.P)
               reinterpret_cast<float4*>(g.raw)[idx] = make_float4(pr + o.x + br[0], pg + o.y + br[1], pb + o.z + br[2], o.w);
           }
-          if (TRAIN && e0) { bulk_s2g(ws_tile + WS_H9_OFF, s_act, 2 * ACT_BLK); bulk_commit(); }
         }
       }
     }
-    if (TRAIN && e0) bulk_wait_all0();
   } else if (warp < 12) {
     // ===================== points + positional encoding =====================
     const int p = (warp - 8) * 32 + lane;
@@ -418,6 +423,34 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
       }
     }
     if (TRAIN && p0) bulk_wait_all0();
+  }
+
+  else if (TRAIN && warp == 15) {
+    // ===================== activation store warp (training) =====================
+    // Saves every activation block for the backward as soon as its eight epilogue warps have written it
+    // (same act_full barrier the MMA warp waits on), so no block-wide barrier sits in the epilogue.
+    if (lane == 0) {
+      uint32_t pl = 0, it = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+        uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
+        for (int li = 0; li < 8; ++li, ++pl) {
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&act_full[j], pl & 1);
+            bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES + j * ACT_BLK, s_act + j * ACT_BLK, ACT_BLK);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(&st_done[j]);
+          }
+        }
+        mbar_wait(h9_full, it & 1);
+        bulk_s2g(ws_tile + WS_H9_OFF, s_act, 2 * ACT_BLK);
+        bulk_commit();
+        bulk_wait_read0();
+        mbar_arrive(&st_done[0]);
+        mbar_arrive(&st_done[1]);
+      }
+      bulk_wait_all0();
+    }
   }
 
   tc_fence_before();

@@ -97,12 +97,15 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   uint64_t* act_full = bars + 6;      // [4]
   uint64_t* d_full = bars + 10;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* blk_ready = bars + 13;    // [4] block j of the current dy image is complete (for the store warp)
+  uint64_t* st_done = bars + 17;      // [4] block j's bulk store has finished reading shared memory
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 8);     // one arrival per epilogue warp
     mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
+    for (int j = 0; j < 4; ++j) { mbar_init(&blk_ready[j], 8); mbar_init(&st_done[j], 1); }
     mbar_fence_init();
   }
   if (warp == 10) tmem_alloc<512>(tmem_slot);
@@ -163,8 +166,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
     const int q = warp & 3, hh = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-    const bool e0 = (threadIdx.x == 0);
-    uint32_t dcnt = 0;
+    uint32_t dcnt = 0, wstep = 0;         // wstep: dy images written so far (9 per tile)
     float4 pre_dr = make_float4(0.f, 0.f, 0.f, 0.f);
     uint32_t pre_hm[2] = {0u, 0u};
     if ((int64_t)blockIdx.x < g.num_tiles) {
@@ -176,12 +178,14 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
     }
     for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
       const uint32_t* ws_mask = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + tile * (9 * 8 * 128);
-      uint8_t* ws_dy = g.ws + dy_base + tile * WS_DY_BYTES;
       // ---- head prep: d_raw -> [dy9 | d_sigma | d_rgb] operand image
       // (d_raw and the sign words of this tile were prefetched during the previous tile's last layer)
       {
-        if (e0) bulk_wait_read0();
-        named_bar_sync(1, 256);
+        if (wstep > 0) {   // the store warp may still be reading the previous image
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mbar_wait(&st_done[j], (wstep - 1) & 1);
+        }
+        ++wstep;
         float4 dr = pre_dr;
         dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
 #pragma unroll
@@ -211,10 +215,8 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) mbar_arrive(&act_full[j]);
+          for (int j = 0; j < 4; ++j) { mbar_arrive(&act_full[j]); mbar_arrive(&blk_ready[j]); }
         }
-        named_bar_sync(1, 256);
-        if (e0) { bulk_s2g(ws_dy + WS_DYH_OFF, s_act, ACT_BYTES); bulk_commit(); }
       }
       // ---- layers: dh_l (TMEM) * mask_l -> dy_l.  The sign words of layer l-1 (and, during the last layer,
       // d_raw + head sign words of the NEXT tile) are fetched one layer ahead so that no global-load latency
@@ -241,8 +243,6 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         }
         mbar_wait(&d_full[dcnt & 1], (dcnt >> 1) & 1);
         tc_fence_after();
-        if (e0) bulk_wait_read0();
-        named_bar_sync(1, 256);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           uint32_t v[32];
@@ -251,6 +251,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
           tmem_ld_wait();
           const uint32_t m = cur_m[j];
           uint8_t* blk = s_act + j * ACT_BLK;
+          mbar_wait(&st_done[j], (wstep - 1) & 1);       // previous image's block j has been read out
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             uint32_t pk[4];
@@ -266,15 +267,35 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
           fence_async_smem();
           tc_fence_before();
           __syncwarp();
-          if (t < 7 && lane == 0) mbar_arrive(&act_full[j]);
+          if (lane == 0) {
+            if (t < 7) mbar_arrive(&act_full[j]);
+            mbar_arrive(&blk_ready[j]);
+          }
         }
-        named_bar_sync(1, 256);
-        if (e0) { bulk_s2g(ws_dy + (size_t)l * ACT_BYTES, s_act, ACT_BYTES); bulk_commit(); }
+        ++wstep;
 #pragma unroll
         for (int j = 0; j < 4; ++j) cur_m[j] = nxt_m[j];
       }
     }
-    if (e0) bulk_wait_all0();
+  } else if (warp == 11) {
+    // dy-image store warp: saves every block as soon as its eight epilogue warps have written it
+    if (lane == 0) {
+      uint32_t step = 0;
+      for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
+        uint8_t* ws_dy = g.ws + dy_base + tile * WS_DY_BYTES;
+        for (int sidx = 0; sidx < 9; ++sidx, ++step) {        // head image, then layers 7..0
+          uint8_t* dst = ws_dy + (sidx == 0 ? (size_t)WS_DYH_OFF : (size_t)(8 - sidx) * ACT_BYTES);
+          for (int j = 0; j < 4; ++j) {
+            mbar_wait(&blk_ready[j], step & 1);
+            bulk_s2g(dst + j * ACT_BLK, s_act + j * ACT_BLK, ACT_BLK);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(&st_done[j]);
+          }
+        }
+      }
+      bulk_wait_all0();
+    }
   }
 
   tc_fence_before();

@@ -115,6 +115,7 @@ def main():
     ap.add_argument("--precision", default=None, help="tc (fused tcgen05, default when built) or fp32 (check mode)")
     ap.add_argument("--cpu-sample-rays", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", dest="graph", action="store_false", help="do not capture fwd+bwd in a CUDA graph")
     ap.add_argument("--render-frame", action="store_true", help="also time one 800x800 frame render (config #3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
@@ -162,8 +163,11 @@ def main():
     mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(O.make_params(shapes, 55)); mf.to(dev)
     q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], precision=precision)
     params = list(mc.parameters()) + list(mf.parameters())
-    flat = parallel.FlatGrads(params)
-    opt = torch.optim.Adam(params, lr=5e-4, betas=(0.9, 0.999), fused=True)
+    # loss + optimizer of the step: parameters and gradients live in two flat buffers, the
+    # backward kernels accumulate straight into the gradient buffer, ONE all-reduce, ONE Adam kernel
+    # (same update as the reference's torch.optim.Adam(lr, betas=(0.9, 0.999)), tests/test_gpu_next_rows.py)
+    flat = parallel.FlatParams(params)
+    opt = parallel.FlatAdam(flat, lr=5e-4, betas=(0.9, 0.999))
     n_global = N_RAND * world
 
     nbatch = 4
@@ -175,11 +179,46 @@ def main():
     kw = dict(network_fn=mc, network_query_fn=q, N_samples=N_SAMPLES, perturb=1.0, N_importance=N_IMPORTANCE,
               network_fine=mf, white_bkgd=True, raw_noise_std=0.0)
 
-    def step(rays, tgt):
+    def fwd_bwd(rays, tgt):
         flat.zero_()
         ret = S.render_rays(rays, **kw)
-        loss = parallel.sharded_mse(ret["rgb_map"], tgt, n_global) + parallel.sharded_mse(ret["rgb0"], tgt, n_global)
+        loss = parallel.two_loss_mse(ret["rgb_map"], ret["rgb0"], tgt, n_global)     # nerf/run.py:689-697
         loss.backward()
+        return loss
+
+    # The forward+backward of one step is launch-bound between the big kernels (~60 small launches): capture it
+    # once in a CUDA graph on static input buffers and replay it; the all-reduce and Adam follow the replay.
+    graph = {"g": None, "rays": None, "tgt": None, "loss": None}
+    if args.graph:
+        try:
+            graph["rays"], graph["tgt"] = dev_rays[0].clone(), dev_tgt[0].clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    fwd_bwd(graph["rays"], graph["tgt"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g_ = torch.cuda.CUDAGraph()
+            tc.GENERATION += 1          # stale-mark the packed fp16 weight images so the re-pack kernels are captured too
+            _lib.launch_count(reset=True)
+            with torch.cuda.graph(g_):
+                graph["loss"] = fwd_bwd(graph["rays"], graph["tgt"])
+            graph["launches"] = _lib.launch_count()      # our kernels inside one replay
+            graph["g"] = g_
+        except Exception as e:                      # noqa: BLE001
+            sys.stderr.write("cuda graph capture failed, running eagerly: %r\n" % (e,))
+            graph["g"] = None
+            torch.cuda.synchronize()
+
+    def step(rays, tgt):
+        if graph["g"] is not None:
+            graph["rays"].copy_(rays, non_blocking=True)
+            graph["tgt"].copy_(tgt, non_blocking=True)
+            graph["g"].replay()
+            loss = graph["loss"]
+        else:
+            loss = fwd_bwd(rays, tgt)
         flat.all_reduce()
         opt.step()
         return loss
@@ -227,6 +266,8 @@ def main():
     clocks = sampler.stop() if rank == 0 else None      # sampled over both timed regions
 
     # per-kernel device times (CUDA events on the launching stream) over a few instrumented steps
+    use_graph = graph["g"] is not None
+    graph["g"] = None                               # the instrumented steps below run eagerly
     _lib.TIMING = {}
     bwd_split = {"data": 0.0, "weight": 0.0}
     if precision == "tc":
@@ -261,7 +302,10 @@ def main():
         ach = FLOP_PER_EVAL_FWD * evals / (t_fwd * 1e-3) / 1e12 if t_fwd > 0 else 0.0
         roof = {"bound": "tensor", "kernel": "swnerf_tc_mlp_fwd (fused PE + 8x256 MLP, tcgen05)",
                 "achieved": ach, "peak": pk["bf16_tflops_sustained"] or pk["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]), "traffic": None,
+                "frac": ach / (pk["bf16_tflops_sustained"] or pk["bf16_tflops"]),
+                # dram read+write of the training forward per step from profiles/ (ncu --set full, r1): 3.85 GB per
+                # 786,432-sample launch = 4894 B/sample (saved activation images), x 1,048,576 samples
+                "traffic": 4894.0 * evals,
                 "peak_src": pk["src"] + " cuBLAS bf16 (sustained: kernel timed inside a long step)",
                 "ms_per_step": t_fwd,
                 "bwd": {"ms_per_step": t_bwd, "data_kernel_ms": bwd_split["data"], "weight_kernel_ms": bwd_split["weight"],
@@ -308,7 +352,8 @@ def main():
                 "e2e": {"value": rays_total / (ms_e2e * 1e-3), "unit": "rays/s",
                         "h2d_bytes_per_step": N_RAND * (11 + 3) * 4, "d2h_bytes_per_step": 4,
                         "ms_per_step": ms_e2e / args.steps, "last_loss": last.get("loss")},
-                "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
+                "gpu_launches": launches + (graph.get("launches", 0) * args.steps if use_graph else 0),
+                "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "kernel_ms_per_step": ktimes, "kernel_calls_per_step": kcalls}
         line.update(extra)
         print(json.dumps(line))

@@ -131,6 +131,21 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
                       const void* packed_t, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);
 
+/* ---- next rows, one step either side of the path ------------------------------------------
+ * f1: ray assembly (ray.py:10-38 get_rays, nerf/run.py:137-158): pixel p = j*W + i ->
+ *     rays[k] = [o(3), d(3), near, far, (frame_time), (unit viewdir(3))].  pixels == NULL: all H*W pixels in
+ *     row-major order.  c2w_host12: HOST pointer to the 3x4 camera-to-world matrix, row-major. */
+int swnerf_make_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host12,
+                     const int64_t* pixels, int64_t n_rays, float nearv, float farv, float frame_time, int has_time,
+                     int with_viewdirs, float* rays, int ray_stride, void* stream);
+/* f3: torch.optim.Adam (nerf/run.py:254; no weight decay, no amsgrad) on ONE flat buffer; `step` counts from 1. */
+int swnerf_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                     float beta1, float beta2, float eps, int64_t step, void* stream);
+/* f3: loss = scale * (sum (a-t)^2 [+ sum (b-t)^2]) with scale = 1/(global element count) (img2mse, utils.py:12;
+ * nerf/run.py:689-697) and its gradients da, db (optional).  loss: one device float. */
+int swnerf_mse2(const float* a, const float* b, const float* target, int64_t n, float scale, float* da, float* db,
+                float* loss, void* stream);
+
 /* Per-kernel device timing of the last swnerf_tc_mlp_bwd on this thread (bench.py's roofline): when
  * profiling is on, CUDA events are recorded on the launching stream around the data-gradient and the
  * weight-gradient kernels; swnerf_tc_last_bwd_ms synchronises on them. */

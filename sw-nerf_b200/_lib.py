@@ -38,6 +38,9 @@ _SIG = {
     "swnerf_tc_pack_weights": [_VP, _VP, _VP],
     "swnerf_tc_pack_weights_t": [_VP, _VP, _VP, _VP],
     "swnerf_tc_mlp_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
+    "swnerf_make_rays": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I64, _F32, _F32, _F32, _I32, _I32, _VP, _I32, _VP],
+    "swnerf_adam_flat": [_VP, _VP, _VP, _VP, _I64, _F32, _F32, _F32, _F32, _I64, _VP],
+    "swnerf_mse2": [_VP, _VP, _VP, _I64, _F32, _VP, _VP, _VP, _VP],
     "swnerf_tc_set_profiling": [_I32],
     "swnerf_tc_last_bwd_ms": [_VP, _VP],
     "swnerf_tc_selftest": [_I32, _VP, _VP, _VP, _I32, _I32, _VP, _VP],

@@ -12,6 +12,9 @@ gloo in the CPU tests.
 import torch
 import torch.distributed as dist
 
+from . import _lib, tc
+from ._lib import call, stream
+
 
 def shard_bounds(n_total: int, rank: int, world: int):
     """Contiguous block of rank `rank`; the first (n_total % world) ranks get one extra ray."""
@@ -64,3 +67,90 @@ def gather_rows(local: torch.Tensor, n_total: int, group=None):
     outs = [torch.empty_like(pad) for _ in range(world)]
     dist.all_gather(outs, pad, group=group)
     return torch.cat([o[:b - a] for o, (a, b) in zip(outs, sizes)], 0)
+
+
+# ------------------------------------------------------------------------------------------------
+# the step after the path - loss and optimizer on flat buffers
+# ------------------------------------------------------------------------------------------------
+class FlatParams(FlatGrads):
+    """Parameters AND gradients as views into two flat fp32 buffers (state_dict names/shapes unchanged:
+    each nn.Parameter keeps its identity, only its storage moves)."""
+
+    def __init__(self, params):
+        params = [p for p in params if p.requires_grad]
+        n = sum(p.numel() for p in params)
+        dev = params[0].device
+        self.flat_p = torch.empty(n, dtype=torch.float32, device=dev)
+        off = 0
+        for p in params:
+            view = self.flat_p[off:off + p.numel()].view_as(p)
+            view.copy_(p.data)
+            p.data = view
+            off += p.numel()
+        super().__init__(params)
+
+    def check_param_views(self):
+        base = self.flat_p.untyped_storage().data_ptr()
+        return all(p.data.untyped_storage().data_ptr() == base for p in self.params)
+
+
+class FlatAdam:
+    """torch.optim.Adam(lr, betas=(0.9, 0.999), eps=1e-8) as created by create_nerf (nerf/run.py:254), as ONE
+    kernel over the flat buffers (the reference runs ~48 small tensors through a multi-tensor kernel)."""
+
+    def __init__(self, flat: FlatParams, lr=5e-4, betas=(0.9, 0.999), eps=1e-8):
+        self.flat, self.lr, self.betas, self.eps = flat, lr, betas, eps
+        self.exp_avg = torch.zeros_like(flat.flat_p)
+        self.exp_avg_sq = torch.zeros_like(flat.flat_p)
+        self.step_count = 0
+        self.param_groups = [{"lr": lr}]          # the runners decay the rate through param_groups (nerf/run.py:704-708)
+
+    def zero_grad(self, set_to_none=False):
+        self.flat.zero_()
+
+    def step(self):
+        self.step_count += 1
+        call("swnerf_adam_flat", self.flat.flat_p.data_ptr(), self.flat.flat.data_ptr(), self.exp_avg.data_ptr(),
+             self.exp_avg_sq.data_ptr(), self.flat.flat_p.numel(), float(self.param_groups[0]["lr"]),
+             float(self.betas[0]), float(self.betas[1]), float(self.eps), self.step_count, stream())
+        tc.GENERATION += 1                        # packed fp16 weight images are stale now
+
+    def state_dict(self):
+        return {"step": self.step_count, "exp_avg": self.exp_avg, "exp_avg_sq": self.exp_avg_sq,
+                "lr": self.param_groups[0]["lr"]}
+
+    def load_state_dict(self, sd):
+        self.step_count = int(sd["step"])
+        self.exp_avg.copy_(sd["exp_avg"]); self.exp_avg_sq.copy_(sd["exp_avg_sq"])
+        self.param_groups[0]["lr"] = sd["lr"]
+
+
+class _TwoLossMSE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, target, n_global):
+        a, target = a.contiguous(), target.contiguous()
+        b = None if b is None else b.contiguous()
+        da = torch.empty_like(a)
+        db = None if b is None else torch.empty_like(b)
+        loss = torch.empty((), dtype=torch.float32, device=a.device)
+        call("swnerf_mse2", _lib.ptr(a), None if b is None else _lib.ptr(b), _lib.ptr(target), a.numel(),
+             1.0 / float(n_global * a.shape[-1]), da.data_ptr(), None if db is None else db.data_ptr(),
+             loss.data_ptr(), stream())
+        ctx.save_for_backward(da, db) if db is not None else ctx.save_for_backward(da)
+        ctx.has_b = db is not None
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        saved = ctx.saved_tensors
+        da = saved[0] * g
+        db = saved[1] * g if ctx.has_b else None
+        return da, db, None, None
+
+
+def two_loss_mse(rgb, rgb0, target, n_global=None):
+    """img2mse(rgb, target) + img2mse(rgb0, target) (nerf/run.py:689-697) in one kernel; n_global = number of
+    rays of the WHOLE step when the batch is sharded over ranks (defaults to the local count)."""
+    if n_global is None:
+        n_global = rgb.shape[0]
+    return _TwoLossMSE.apply(rgb, rgb0, target, n_global)

@@ -30,6 +30,32 @@ def get_rays(H, W, focal_or_K, c2w):
     return rays_o, rays_d
 
 
+def make_ray_batch(H, W, focal_or_K, c2w, near, far, pixels=None, frame_time=None, use_viewdirs=True, device=None):
+    """Flat ray batch straight from the camera: what get_rays (ray.py:10-38) plus the
+    viewdir normalisation / near-far / concatenation of render() (nerf/run.py:137-158) build with a dozen
+    eager ops, as ONE kernel.  `pixels`: int64 tensor of flat pixel ids j*W + i (None = the whole frame)."""
+    if device is None:
+        device = pixels.device if pixels is not None else (c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda
+                                                           else torch.device("cuda"))
+    if isinstance(focal_or_K, float):
+        fx = fy = float(focal_or_K); cx, cy = W * 0.5, H * 0.5
+    else:
+        K = focal_or_K
+        fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
+    import ctypes
+    m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
+    c2w12 = (ctypes.c_float * 12)(*m.reshape(-1).tolist())
+    n = H * W if pixels is None else pixels.numel()
+    stride = 8 + (1 if frame_time is not None else 0) + (3 if use_viewdirs else 0)
+    rays = torch.empty((n, stride), dtype=torch.float32, device=device)
+    from ._lib import call, ptr, stream
+    call("swnerf_make_rays", H, W, fx, fy, cx, cy, c2w12,
+         None if pixels is None else ptr(pixels.reshape(-1), torch.int64, "pixels"), n, float(near), float(far),
+         0.0 if frame_time is None else float(frame_time), int(frame_time is not None), int(use_viewdirs),
+         rays.data_ptr(), stride, stream())
+    return rays
+
+
 def get_rays_np(H, W, focal_or_K, c2w):
     """ray.py:42-72."""
     i, j = np.meshgrid(np.arange(W, dtype=np.float32), np.arange(H, dtype=np.float32), indexing='xy')

@@ -12,7 +12,7 @@ import torch
 from . import ops, tc
 from .embedder import get_embedder
 from .model import vallina_NeRF as NeRF
-from .ray import get_rays, ndc_rays, raw_noise, pytest_uniform
+from .ray import get_rays, ndc_rays, raw_noise, pytest_uniform, make_ray_batch
 
 DEBUG = False
 
@@ -94,6 +94,15 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """nerf/run.py:105-170."""
+    if (c2w is not None and not ndc and c2w_staticcam is None and use_viewdirs and torch.cuda.is_available()
+            and not torch.is_tensor(near) and not torch.is_tensor(far)):
+        # full-frame fast path: the whole ray assembly below is one kernel (same values, tests/test_gpu_next_rows.py)
+        rays = make_ray_batch(H, W, K, c2w, near, far, use_viewdirs=True)
+        all_ret = batchify_rays(rays, chunk, **kwargs)
+        for k in all_ret:
+            all_ret[k] = torch.reshape(all_ret[k], [H, W] + list(all_ret[k].shape[1:]))
+        k_extract = ['rgb_map', 'disp_map', 'acc_map']
+        return [all_ret[k] for k in k_extract] + [{k: all_ret[k] for k in all_ret if k not in k_extract}]
     if c2w is not None:
         rays_o, rays_d = get_rays(H, W, K, c2w)
     else:

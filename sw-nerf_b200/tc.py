@@ -30,8 +30,12 @@ class _Packed:
         self.bwd_versions = None
 
 
+# bumped by optimizers that update the parameters behind autograd's back (parallel.FlatAdam)
+GENERATION = 0
+
+
 def _versions(params):
-    return tuple((p.data_ptr(), p._version) for p in params)
+    return (GENERATION,) + tuple((p.data_ptr(), p._version) for p in params)
 
 
 def packed_weights(network, need_bwd=False):

@@ -154,3 +154,33 @@ def two_loss_mse(rgb, rgb0, target, n_global=None):
     if n_global is None:
         n_global = rgb.shape[0]
     return _TwoLossMSE.apply(rgb, rgb0, target, n_global)
+
+
+# ------------------------------------------------------------------------------------------------
+# the frame loop of render_path (nerf/run.py:172-219), ray-sharded over the ranks
+# ------------------------------------------------------------------------------------------------
+def render_frame_sharded(H, W, K, c2w, near, far, chunk, render_rays_fn, group=None, **render_kwargs):
+    """One full frame: every rank builds and renders a contiguous block of the H*W rays (ray assembly kernel +
+    batchify over `chunk`), then the maps are all-gathered so each rank holds the whole frame.
+    Returns (rgb[H,W,3], disp[H,W], acc[H,W]) like render() (nerf/run.py:166-170)."""
+    from .ray import make_ray_batch
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    n = H * W
+    lo, hi = shard_bounds(n, rank, world)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    pix = torch.arange(lo, hi, dtype=torch.int64, device=dev)
+    rays = make_ray_batch(H, W, K, c2w, near, far, pixels=pix, use_viewdirs=True, device=dev)
+    outs = {"rgb_map": [], "disp_map": [], "acc_map": []}
+    for i in range(0, rays.shape[0], chunk):
+        ret = render_rays_fn(rays[i:i + chunk], **render_kwargs)
+        for k in outs:
+            outs[k].append(ret[k])
+    maps = []
+    for k in ("rgb_map", "disp_map", "acc_map"):
+        local = torch.cat(outs[k], 0) if outs[k] else torch.empty((0,), device=dev)
+        if local.dim() == 1:
+            local = local[:, None]
+        maps.append(gather_rows(local, n, group))
+    rgb, disp, acc = maps
+    return rgb.reshape(H, W, 3), disp.reshape(H, W), acc.reshape(H, W)

@@ -425,3 +425,34 @@ def test_dnerf_grads_given_identical_samples(golden, tmp_path):
     gr = torch.cat([(pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])).reshape(-1)
                     for n, _ in model.named_parameters()])
     assert rel_l2(gg, gr) < 1e-3, rel_l2(gg, gr)
+
+
+@pytest.mark.parametrize("channels", [(20, 8, 20), (10, 4, 10), (-1, -1, -1)])
+def test_multires_levels_vs_oracle(channels, tmp_path):
+    """MultiRes D-NeRF per-level networks (multires_dnerf.py:665: PE sizes (20,8,20)/(10,4,10)/identity) through
+    create_nerf(args, channels, layer): forward and backward at identical sample positions vs the oracle."""
+    args = _dnerf_args(tmp_path)
+    kw, _, _, _, _ = dnerf.create_nerf_multires(args, channels, 1, device=torch.device(DEV))
+    model = kw["network_fn"]
+    Lp, Lt, Ld = channels
+    shapes = O.dnerf_param_shapes(input_ch=O.embed_dim(Lp, 3), input_ch_views=O.embed_dim(Ld, 3),
+                                  input_ch_time=O.embed_dim(Lt, 1))
+    params = O.make_params(shapes, 332)
+    load(model, params)
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    N = 12
+    rays_np = O.blender_rays(N, 33, frame_time=0.5)
+    z_np = np.sort(np.random.RandomState(5).uniform(2, 6, (N, 40)).astype(np.float32), -1)
+    pr = {k: v.clone().requires_grad_() for k, v in params.items()}
+    ref = O.render_rays_dnerf(torch.from_numpy(rays_np), pr, 64, 128, L_pos=Lp, L_time=Lt, L_dir=Ld, white_bkgd=True,
+                              z_vals=torch.from_numpy(z_np))
+    (ref["rgb_map"].sum() + ref["position_delta"].pow(2).sum()).backward()
+    ret = dnerf.render_rays(T(rays_np), z_vals=T(z_np), **kw)
+    (ret["rgb_map"].sum() + ret["position_delta"].pow(2).sum()).backward()
+    tol = 2e-5 if Lp <= 10 else 2e-3          # L=20: 2^19 rad/unit, 1 ulp of position is 0.25 rad of phase
+    assert relmax(ret["rgb_map"], ref["rgb_map"]) < tol
+    assert relmax(ret["position_delta"], ref["position_delta"]) < tol
+    gg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for _, p in model.named_parameters()])
+    gr = torch.cat([(pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])).reshape(-1)
+                    for n, _ in model.named_parameters()])
+    assert rel_l2(gg, gr) < (1e-3 if Lp <= 10 else 5e-2), rel_l2(gg, gr)

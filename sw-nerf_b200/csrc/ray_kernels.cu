@@ -151,6 +151,31 @@ __device__ __forceinline__ void sample_alpha(float sigma, float noise, float zi,
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// All loads of a ray are issued before any arithmetic (NC = compile-time number of 32-sample chunks, registers
+// hold the whole ray: 6 x (float4 + z + noise) for S = 192), so every warp keeps ~5 KB in flight instead of
+// 0.6 KB and the kernel is HBM- rather than latency-bound.  z[i+1] comes from the neighbouring lane.
+template <int NC>
+__device__ __forceinline__ void load_ray(const float4* __restrict__ raw4, const float* __restrict__ zr,
+                                         const float* __restrict__ nr, int S, int lane, float4 (&q)[NC], float (&zi)[NC],
+                                         float (&nz)[NC]) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    int i = c * 32 + lane;
+    bool valid = i < S;
+    q[c] = valid ? __ldcs(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);      // streamed once: evict-first
+    zi[c] = valid ? __ldcs(zr + i) : 0.f;
+    nz[c] = (valid && nr) ? __ldg(nr + i) : 0.f;
+  }
+}
+
+template <int NC>
+__device__ __forceinline__ float z_next(const float (&zi)[NC], int c, int lane) {
+  float up = __shfl_down_sync(0xffffffffu, zi[c], 1);                 // z[i+1] of lanes 0..30
+  float first_of_next = (c + 1 < NC) ? __shfl_sync(0xffffffffu, zi[c + 1 < NC ? c + 1 : c], 0) : 0.f;
+  return lane == 31 ? first_of_next : up;
+}
+
+template <int NC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
                      int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
@@ -162,18 +187,18 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
   const float* zr = z + r * S;
   const float* nr = noise ? noise + r * S : nullptr;
+  float4 q[NC]; float zi[NC], nz[NC];
+  load_ray<NC>(raw4, zr, nr, S, lane, q, zi, nz);
   float norm = ray_norm(rays, r, ray_stride, d_col);
   float carry = 1.f;
   float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
-  for (int base = 0; base < S; base += 32) {
-    int i = base + lane;
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    int i = c * 32 + lane;
     bool valid = i < S;
-    float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float zi = valid ? __ldg(zr + i) : 0.f;
-    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
-    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
+    float zn = z_next<NC>(zi, c, lane);
     float dist, e, alpha, u; bool on;
-    sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
+    sample_alpha(q[c].w, nz[c], zi[c], zn, i == S - 1, norm, dist, e, alpha, u, on);
     if (!valid) { alpha = 0.f; u = 1.f; }
     float incl = warp_scan_mul(u, lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
@@ -183,10 +208,10 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     float w = alpha * T;
     if (valid) {
       weights[r * S + i] = w;
-      sr += w * sigmoidf_(q.x);
-      sg += w * sigmoidf_(q.y);
-      sb += w * sigmoidf_(q.z);
-      sd += w * zi;
+      sr += w * sigmoidf_(q[c].x);
+      sg += w * sigmoidf_(q[c].y);
+      sb += w * sigmoidf_(q[c].z);
+      sd += w * zi[c];
       sa += w;
     }
   }
@@ -197,8 +222,8 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
     depth_map[r] = sd;
     acc_map[r] = sa;
     // torch.max(1e-10, NaN) propagates the 0/0 NaN of an empty ray (ray.py:192); fmaxf would not.
-    float q = sd / sa;
-    disp_map[r] = (q != q) ? q : 1.f / fmaxf(1e-10f, q);
+    float qd = sd / sa;
+    disp_map[r] = (qd != qd) ? qd : 1.f / fmaxf(1e-10f, qd);
   }
 }
 
@@ -208,13 +233,10 @@ composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 //   dL/dalpha_i = G_i T_i - R_i / u_i,  R_i = sum_{k>i} G_k w_k   (T_k carries the factor u_i)
 //   dL/dsigma_i = dL/dalpha_i * dist_i * e_i * [sigma_i + noise_i > 0],   e_i = exp(-relu(.) dist_i)
 //   dL/draw_rgb = w_i g_rgb c (1 - c)
-// Sweep A walks the ray forward and keeps the transmittance entering every 32-sample chunk; sweep B
-// walks the chunks BACKWARD (second read hits L1), rebuilds T inside the chunk and forms R_i as a true
-// suffix sum (reverse warp scan + carry), so no cancellation.  e_i/u_i <= 1 is formed first so that a
-// tiny u_i never amplifies the rounding of R_i.
+// The ray is loaded once into registers; sweep A walks it forward and keeps T_i and G_i w_i per sample, sweep B
+// walks the chunks BACKWARD and forms R_i as a true suffix sum (reverse warp scan + carry), so no cancellation.
+// e_i/u_i <= 1 is formed first so that a tiny u_i never amplifies the rounding of R_i.
 // ---------------------------------------------------------------------------------------------
-constexpr int kMaxChunks = 64;   // S <= 2048
-
 __device__ __forceinline__ float warp_rscan_add(float v, int lane) {   // inclusive suffix sum
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
@@ -224,6 +246,7 @@ __device__ __forceinline__ float warp_rscan_add(float v, int lane) {   // inclus
   return v;
 }
 
+template <int NC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
                      int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
@@ -231,15 +254,18 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
                      const float* __restrict__ g_w, const float* __restrict__ g_depth,
                      const float* __restrict__ acc_map, const float* __restrict__ depth_map,
                      float* __restrict__ d_raw) {
-  __shared__ float carries[kWarpsPerBlock][kMaxChunks];
-  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  int lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= N) return;
   const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
   float4* out4 = reinterpret_cast<float4*>(d_raw) + r * S;
   const float* zr = z + r * S;
   const float* nr = noise ? noise + r * S : nullptr;
   const float* gw = g_w ? g_w + r * S : nullptr;
+  float4 q[NC]; float zi[NC], nz[NC], gwv[NC];
+  load_ray<NC>(raw4, zr, nr, S, lane, q, zi, nz);
+#pragma unroll
+  for (int c = 0; c < NC; ++c) gwv[c] = (gw && c * 32 + lane < S) ? __ldg(gw + c * 32 + lane) : 0.f;
   float norm = ray_norm(rays, r, ray_stride, d_col);
   float gr = 0.f, gg = 0.f, gb = 0.f, gd = 0.f, ga = 0.f;
   if (g_rgb) { gr = g_rgb[r * 3]; gg = g_rgb[r * 3 + 1]; gb = g_rgb[r * 3 + 2]; }
@@ -247,64 +273,55 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   if (g_acc) ga = g_acc[r];
   if (g_disp) {   // disp = 1 / max(1e-10, depth/acc)
     float acc = acc_map[r], dep = depth_map[r];
-    float q = dep / acc;
-    if (q > 1e-10f) {
-      float gq = -g_disp[r] / (q * q);
+    float qd = dep / acc;
+    if (qd > 1e-10f) {
+      float gq = -g_disp[r] / (qd * qd);
       gd += gq / acc;
       ga += -gq * dep / (acc * acc);
     }
   }
   if (white_bkgd) ga -= (gr + gg + gb);
 
-  const int nchunk = (S + 31) >> 5;
-  // sweep A: transmittance entering each chunk
+  // sweep A (forward): per sample T, and the quantities sweep B needs
+  float Tv[NC], ev[NC], uv[NC], distv[NC], Gv[NC], wv[NC];
+  bool onv[NC];
   float carry = 1.f;
-  for (int c = 0; c < nchunk; ++c) {
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
     int i = c * 32 + lane;
     bool valid = i < S;
-    float sig = valid ? __ldg(reinterpret_cast<const float*>(raw4 + i) + 3) : 0.f;
-    float zi = valid ? __ldg(zr + i) : 0.f;
-    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
-    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
-    float dist, e, alpha, u; bool on;
-    sample_alpha(sig, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
-    if (!valid) u = 1.f;
-    if (lane == 0) carries[warp][c] = carry;
-    float incl = warp_scan_mul(u, lane);
-    carry *= __shfl_sync(0xffffffffu, incl, 31);
-  }
-  __syncwarp();
-  // sweep B: chunks in reverse, suffix sums of G_k w_k
-  float rcarry = 0.f;
-  for (int c = nchunk - 1; c >= 0; --c) {
-    int i = c * 32 + lane;
-    bool valid = i < S;
-    float4 q = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float zi = valid ? __ldg(zr + i) : 0.f;
-    float zn = (i + 1 < S) ? __ldg(zr + i + 1) : 0.f;
-    float nz = (valid && nr) ? __ldg(nr + i) : 0.f;
-    float dist, e, alpha, u; bool on;
-    sample_alpha(q.w, nz, zi, zn, i == S - 1, norm, dist, e, alpha, u, on);
-    if (!valid) { alpha = 0.f; u = 1.f; }
-    float incl = warp_scan_mul(u, lane);
+    float zn = z_next<NC>(zi, c, lane);
+    float alpha;
+    sample_alpha(q[c].w, nz[c], zi[c], zn, i == S - 1, norm, distv[c], ev[c], alpha, uv[c], onv[c]);
+    if (!valid) { alpha = 0.f; uv[c] = 1.f; }
+    float incl = warp_scan_mul(uv[c], lane);
     float excl = __shfl_up_sync(0xffffffffu, incl, 1);
     if (lane == 0) excl = 1.f;
-    float T = carries[warp][c] * excl;
-    float w = alpha * T;
-    float cr = sigmoidf_(q.x), cg = sigmoidf_(q.y), cb = sigmoidf_(q.z);
-    float G = gr * cr + gg * cg + gb * cb + gd * zi + ga + ((valid && gw) ? __ldg(gw + i) : 0.f);
-    float Gw = valid ? G * w : 0.f;
+    Tv[c] = carry * excl;
+    carry *= __shfl_sync(0xffffffffu, incl, 31);
+    wv[c] = alpha * Tv[c];
+    float cr = sigmoidf_(q[c].x), cg = sigmoidf_(q[c].y), cb = sigmoidf_(q[c].z);
+    Gv[c] = gr * cr + gg * cg + gb * cb + gd * zi[c] + ga + gwv[c];
+    q[c].x = cr; q[c].y = cg; q[c].z = cb;           // keep the colours for sweep B
+  }
+  // sweep B (backward): suffix sums of G_k w_k
+  float rcarry = 0.f;
+#pragma unroll
+  for (int c = NC - 1; c >= 0; --c) {
+    int i = c * 32 + lane;
+    bool valid = i < S;
+    float Gw = valid ? Gv[c] * wv[c] : 0.f;
     float suf = warp_rscan_add(Gw, lane);                       // sum_{k>=i} within the chunk
     float nxt = __shfl_down_sync(0xffffffffu, suf, 1);
     float R = ((lane == 31) ? 0.f : nxt) + rcarry;               // sum_{k>i} over the whole ray
     rcarry += __shfl_sync(0xffffffffu, suf, 0);
-    float dalpha_e = G * T * e - R * (e / u);                    // dL/dalpha * e
-    float dsig = on ? dalpha_e * dist : 0.f;
+    float dalpha_e = Gv[c] * Tv[c] * ev[c] - R * (ev[c] / uv[c]);   // dL/dalpha * e
+    float dsig = onv[c] ? dalpha_e * distv[c] : 0.f;
     if (valid) {
       float4 o;
-      o.x = w * gr * cr * (1.f - cr);
-      o.y = w * gg * cg * (1.f - cg);
-      o.z = w * gb * cb * (1.f - cb);
+      o.x = wv[c] * gr * q[c].x * (1.f - q[c].x);
+      o.y = wv[c] * gg * q[c].y * (1.f - q[c].y);
+      o.z = wv[c] * gb * q[c].z * (1.f - q[c].z);
       o.w = dsig;
       out4[i] = o;
     }
@@ -532,10 +549,16 @@ int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* ray
   SW_REQUIRE(aligned16(raw), "composite_fwd: raw must be 16-byte aligned");
   SW_REQUIRE(n_samples >= 1, "composite_fwd: n_samples < 1");
   if (n_rays == 0) return SWNERF_OK;
+  SW_REQUIRE(n_samples <= 1024, "composite_fwd: n_samples > 1024");
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  composite_fwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, rgb_map, disp_map, acc_map,
-      weights, depth_map);
+  const int nc = (n_samples + 31) / 32;
+#define SW_FWD(NC)                                                                                              \
+  composite_fwd_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(                            \
+      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, rgb_map, disp_map, acc_map,    \
+      weights, depth_map)
+  if (nc <= 2) SW_FWD(2); else if (nc <= 4) SW_FWD(4); else if (nc <= 6) SW_FWD(6); else if (nc <= 8) SW_FWD(8);
+  else if (nc <= 16) SW_FWD(16); else SW_FWD(32);
+#undef SW_FWD
   return check_launch("composite_fwd");
 }
 
@@ -546,12 +569,17 @@ int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* ray
   SW_REQUIRE(raw && z_vals && rays && d_raw, "composite_bwd: null pointer");
   SW_REQUIRE(aligned16(raw) && aligned16(d_raw), "composite_bwd: raw/d_raw must be 16-byte aligned");
   SW_REQUIRE(!g_disp || (acc_map && depth_map), "composite_bwd: g_disp needs saved acc/depth maps");
-  SW_REQUIRE(n_samples <= 32 * kMaxChunks, "composite_bwd: n_samples > 2048");
+  SW_REQUIRE(n_samples <= 512, "composite_bwd: n_samples > 512");
   if (n_rays == 0) return SWNERF_OK;
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
-  composite_bwd_kernel<<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(
-      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, g_rgb, g_disp, g_acc, g_weights,
-      g_depth, acc_map, depth_map, d_raw);
+  const int nc = (n_samples + 31) / 32;
+#define SW_BWD(NC)                                                                                              \
+  composite_bwd_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(                            \
+      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, g_rgb, g_disp, g_acc, g_weights, \
+      g_depth, acc_map, depth_map, d_raw)
+  if (nc <= 2) SW_BWD(2); else if (nc <= 4) SW_BWD(4); else if (nc <= 6) SW_BWD(6); else if (nc <= 8) SW_BWD(8);
+  else SW_BWD(16);
+#undef SW_BWD
   return check_launch("composite_bwd");
 }
 

@@ -73,7 +73,8 @@ int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf,
                       int64_t n_rays, int n_bins, int n_samples, float* samples, int64_t* inds, void* stream);
 
 /* ---- a9+a10+a11 fused (nerf/run.py:396-400, 416): z_mid bins, sample_pdf on weights[:,1:-1],
- * z_fine = sort(cat(z_vals, z_samples)), z_std = std(z_samples, unbiased=False).  z_samples, z_std optional. */
+ * z_fine = sort(cat(z_vals, z_samples)), z_std = std(z_samples, unbiased=False).  z_samples, z_std optional;
+ * z_samples is returned in ASCENDING order (the reference only uses it through std and the sort). */
 int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
                     int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream);
 

@@ -426,47 +426,82 @@ __device__ void warp_bitonic_sort(float* a, int P, int lane) {
   }
 }
 
-// Fused: z_mid bins + sample_pdf on weights[:,1:-1] + sort(cat(z_vals, z_samples)) + z_std
+// Fused: z_mid bins + sample_pdf on weights[:,1:-1] + sort(cat(z_vals, z_samples)) + z_std.
+// The inverse cdf is monotone, so instead of sorting S+Ni values (nerf/run.py:400) the kernel sorts only the Ni
+// uniforms (nothing to sort in the deterministic mode), draws the samples in ascending order and MERGES them with
+// the already sorted z_vals by rank (two binary searches per element).  Rounding can invert neighbouring
+// samples across a bin boundary by one ulp: two odd-even passes repair that, and a warp vote falls back to a
+// full bitonic sort of the samples if anything is still out of order, so z_fine is exactly sort(cat(.)).
+// smem per warp: cdf[M] | bins[M] | z[S] | samples[NiP] | merged[S+Ni]   (M = S-1, NiP = pow2 >= Ni)
+__device__ __forceinline__ void smem_cswap(float* a, int i, int l) {
+  float x = a[i], y = a[l];
+  if (x > y) { a[i] = y; a[l] = x; }
+}
+
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
-                int64_t N, int S, int Ni, int P, float* __restrict__ z_samples, float* __restrict__ z_fine,
+                int64_t N, int S, int Ni, int NiP, float* __restrict__ z_samples, float* __restrict__ z_fine,
                 float* __restrict__ z_std) {
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (r >= N) return;
-  int M = S - 1;                                     // bins = z_mid (S-1), weights[1:-1] (S-2)
-  float* cdf = smem + (size_t)warp * (2 * M + P);
+  const int M = S - 1;                               // bins = z_mid (S-1), weights[1:-1] (S-2)
+  float* cdf = smem + (size_t)warp * (2 * M + S + NiP + S + Ni);
   float* bs = cdf + M;
-  float* buf = bs + M;
+  float* zs = bs + M;
+  float* sm = zs + S;
+  float* outb = sm + NiP;
   const float* zr = z_vals + r * S;
   for (int i = lane; i < S; i += 32) {
     float zi = __ldg(zr + i);
-    buf[i] = zi;
+    zs[i] = zi;
     if (i < M) bs[i] = __fmul_rn(0.5f, __fadd_rn(__ldg(zr + i + 1), zi));    // run.py:396
+  }
+  const float inf = __int_as_float(0x7f800000);
+  if (u_in) {
+    for (int j = lane; j < NiP; j += 32) sm[j] = (j < Ni) ? __ldg(u_in + r * Ni + j) : inf;
+  } else {
+    for (int j = Ni + lane; j < NiP; j += 32) sm[j] = inf;
   }
   warp_build_cdf(weights + r * S + 1, M, cdf, lane);
   __syncwarp();
+  if (u_in) warp_bitonic_sort(sm, NiP, lane);        // ascending uniforms -> ascending samples
   float s1 = 0.f;
   for (int j = lane; j < Ni; j += 32) {
-    float u = u_in ? __ldg(u_in + r * Ni + j) : det_u(j, Ni);
+    float u = u_in ? sm[j] : det_u(j, Ni);
     int ind;
-    float s = invert_cdf(cdf, bs, M, u, &ind);
-    buf[S + j] = s;
-    if (z_samples) z_samples[r * Ni + j] = s;
-    s1 += s;
+    float sv = invert_cdf(cdf, bs, M, u, &ind);
+    sm[j] = sv;
+    s1 += sv;
   }
-  for (int i = S + Ni + lane; i < P; i += 32) buf[i] = __int_as_float(0x7f800000);   // +inf padding
+  __syncwarp();
+  // repair one-ulp inversions between neighbours, then verify
+  for (int t = lane; 2 * t + 1 < Ni; t += 32) smem_cswap(sm, 2 * t, 2 * t + 1);
+  __syncwarp();
+  for (int t = lane; 2 * t + 2 < Ni; t += 32) smem_cswap(sm, 2 * t + 1, 2 * t + 2);
+  __syncwarp();
+  bool ok = true;
+  for (int j = lane; j + 1 < Ni; j += 32) ok = ok && (sm[j] <= sm[j + 1]);
+  if (!__all_sync(0xffffffffu, ok)) warp_bitonic_sort(sm, NiP, lane);
   // population std (torch.std unbiased=False): two-pass for accuracy
   float mean = warp_sum(s1) / (float)Ni;
-  __syncwarp();
   float s2 = 0.f;
-  for (int j = lane; j < Ni; j += 32) { float d = buf[S + j] - mean; s2 += d * d; }
+  for (int j = lane; j < Ni; j += 32) { float d = sm[j] - mean; s2 += d * d; }
   s2 = warp_sum(s2);
   if (lane == 0 && z_std) z_std[r] = sqrtf(s2 / (float)Ni);
+  // merge by rank: ties put the z_vals element first
+  for (int j = lane; j < Ni; j += 32) {
+    float sv = sm[j];
+    outb[j + upper_bound_smem(zs, S, sv)] = sv;      // + number of z <= s
+    if (z_samples) z_samples[r * Ni + j] = sv;
+  }
+  for (int i = lane; i < S; i += 32) {
+    float zv = zs[i];
+    outb[i + lower_bound_smem(sm, Ni, zv)] = zv;      // + number of samples < z
+  }
   __syncwarp();
-  warp_bitonic_sort(buf, P, lane);
-  for (int i = lane; i < S + Ni; i += 32) z_fine[r * (S + Ni) + i] = buf[i];
+  for (int i = lane; i < S + Ni; i += 32) z_fine[r * (S + Ni) + i] = outb[i];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -604,10 +639,10 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
   SW_REQUIRE(z_vals && weights && z_fine, "resample: null pointer");
   SW_REQUIRE(det || u, "resample: random mode needs caller-supplied u");
   SW_REQUIRE(n_samples >= 3 && n_importance >= 1, "resample: need n_samples >= 3 and n_importance >= 1");
-  int P = next_pow2(n_samples + n_importance);
-  SW_REQUIRE(P <= 2048, "resample: n_samples + n_importance > 2048");
+  int P = next_pow2(n_importance);
+  SW_REQUIRE(P <= 1024 && n_samples <= 1024, "resample: n_samples / n_importance > 1024");
   if (n_rays == 0) return SWNERF_OK;
-  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_samples - 1) + P) * sizeof(float);
+  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_samples - 1) + n_samples + P + n_samples + n_importance) * sizeof(float);
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -154,7 +154,8 @@ def sample_pdf(bins, weights, n_samples: int, det=False, u=None, cdf=None, retur
 
 
 def resample(z_vals, weights, n_importance: int, det=False, u=None):
-    """Returns (z_samples, z_fine, z_std): nerf/run.py:396-400 and :416."""
+    """Returns (z_samples, z_fine, z_std): nerf/run.py:396-400 and :416.  z_samples comes back in ascending
+    order (the reference uses it only through std() and the sort, both order-free)."""
     N, S = z_vals.shape
     dev = z_vals.device
     if not det and u is None:

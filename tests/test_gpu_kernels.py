@@ -182,7 +182,7 @@ def test_resample(N, S_, Ni, det):
     zs_ref = O.sample_pdf(z_mid, wt[:, 1:-1], Ni, det=det, u=None if det else torch.from_numpy(u))
     # the cdf is rebuilt on the GPU (warp scan instead of a sequential cumsum): a 1-ulp cdf difference can
     # move a sample across a near-empty bin ("bit-exact given identical CDFs"), so allow <= 0.1% outliers
-    bad = ((zs.cpu() - zs_ref).abs() > 3e-4).float().mean().item()
+    bad = ((zs.cpu() - torch.sort(zs_ref, -1)[0]).abs() > 3e-4).float().mean().item()   # returned ascending
     assert bad < 1e-3, bad
     # exact properties: z_fine is sorted and is exactly the multiset {z_vals} U {z_samples}
     zf_c, zs_c = zf.cpu(), zs.cpu()

@@ -68,7 +68,7 @@ __device__ __forceinline__ float grad_scale_from(const uint32_t* absmax, float f
   if (fixed > 0.f) return fixed;
   float mx = __uint_as_float(*absmax);
   if (!(mx > 0.f)) return 1.f;
-  float e = floorf(log2f(256.f / mx));
+  float e = floorf(log2f(32.f / mx));      // max|d_raw| -> [16, 32): 2000x headroom below fp16's 65504 for growth in the chain
   e = fminf(fmaxf(e, -40.f), 40.f);
   return exp2f(e);
 }

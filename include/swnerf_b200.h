@@ -132,6 +132,29 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
                       const void* packed_t, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);
 
+/* ---- D-NeRF (a1d, a5d, a6d, a7) on the same fused kernels -------------------------------------------------
+ * The canonical network `_occ` (NeRFOriginal, model.py:227-296) is the 24-tensor network above evaluated at
+ * explicit sample positions pts[N*S,3] = x + dx (model.py:148-150); its backward can also return d_pts
+ * (the positional encoding sits inside the autograd graph there).
+ * The deformation network `_time` / `_time_out` (model.py:113-136; 18 tensors: _time.i.weight/.bias i=0..7,
+ * _time_out.weight/.bias) maps (x, t) -> dx[N*S,3].  `time_embedding`: PE(t), 21 floats (L=10, one time per call,
+ * run_dnerf.py:53). */
+int swnerf_tc_mlp_fwd_points(const float* rays, int ray_stride, int view_col, const float* pts, int64_t n_rays,
+                             int n_samples, const void* packed, float* raw, void* workspace, int training,
+                             void* stream);
+int swnerf_tc_mlp_bwd_points(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
+                             const void* packed_t, const float* const* params, void* workspace, float* const* grads,
+                             float grad_scale, const float* pts, float* d_pts, void* stream);
+int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host21, void* packed,
+                                void* stream);
+int swnerf_tc_pack_weights_time_t(const float* const* params, const void* packed, void* packed_t, void* stream);
+int swnerf_tc_time_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
+                       int n_samples, const void* packed_time, float* dx, void* workspace, int training,
+                       void* stream);
+int swnerf_tc_time_bwd(const float* d_dx, int64_t n_rays, int n_samples, const void* packed_time,
+                       const void* packed_time_t, const float* const* params, const float* time_embedding_dev21,
+                       void* workspace, float* const* grads, float grad_scale, void* stream);
+
 /* ---- next rows, one step either side of the path ------------------------------------------
  * f1: ray assembly (ray.py:10-38 get_rays, nerf/run.py:137-158): pixel p = j*W + i ->
  *     rays[k] = [o(3), d(3), near, far, (frame_time), (unit viewdir(3))].  pixels == NULL: all H*W pixels in

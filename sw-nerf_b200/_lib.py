@@ -38,6 +38,12 @@ _SIG = {
     "swnerf_tc_pack_weights": [_VP, _VP, _VP],
     "swnerf_tc_pack_weights_t": [_VP, _VP, _VP, _VP],
     "swnerf_tc_mlp_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
+    "swnerf_tc_mlp_fwd_points": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
+    "swnerf_tc_mlp_bwd_points": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _F32, _VP, _VP, _VP],
+    "swnerf_tc_pack_weights_time": [_VP, _VP, _VP, _VP],
+    "swnerf_tc_pack_weights_time_t": [_VP, _VP, _VP, _VP],
+    "swnerf_tc_time_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
+    "swnerf_tc_time_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
     "swnerf_make_rays": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I64, _F32, _F32, _F32, _I32, _I32, _VP, _I32, _VP],
     "swnerf_adam_flat": [_VP, _VP, _VP, _VP, _I64, _F32, _F32, _F32, _F32, _I64, _VP],
     "swnerf_mse2": [_VP, _VP, _VP, _I64, _F32, _VP, _VP, _VP, _VP],

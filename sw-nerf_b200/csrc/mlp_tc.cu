@@ -29,12 +29,20 @@ using namespace tcl;
 // ------------------------------------------------------------------------------------------------
 struct ParamPtrs {
   const float* p[24];
+  // kind 0: vallina_NeRF / NeRFOriginal (24 tensors, order of include/swnerf_b200.h)
+  // kind 1: D-NeRF deformation net (model.py:113-136): p[2i],p[2i+1] = _time.i, p[16],p[17] = _time_out.
+  //         It runs through the SAME kernels: its time embedding is constant per call, so W0[:, 63:] PE(t) is
+  //         folded into the layer-0 bias, and its 256->3 output layer rides in rows 128..130 of the head
+  //         (where alpha_linear sits for kind 0) with the view branch zeroed.
+  int kind;
+  float tpe[24];       // PE(t), 21 values used
 };
 
 // W_fv = W_v[:, :256] W_f (128 x 256), b_fv = W_v[:, :256] b_f + b_v      -> fold[128][257] fp32
 __global__ void fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
   int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= 128 * 257) return;
+  if (P.kind == 1) { fold[idx] = 0.f; return; }
   int r = idx / 257, c = idx % 257;
   const float* wv = P.p[16] + (size_t)r * 283;
   float acc = 0.f;
@@ -50,6 +58,11 @@ __global__ void fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
 }
 
 __device__ __forceinline__ float fwd_weight(const ParamPtrs& P, const float* fold, int c, int n, int k) {
+  if (P.kind == 1) {
+    if (c == 0) return k < 63 ? P.p[0][n * 84 + k] : 0.f;
+    if (c == 30) return 0.f;
+    if (c >= 31) return (n >= 128 && n < 131) ? P.p[16][(n - 128) * 256 + (c - 31) * 64 + k] : 0.f;
+  }
   if (c == 0) return k < 63 ? P.p[0][n * 63 + k] : 0.f;
   if (c <= 16) { int l = 1 + (c - 1) / 4, kc = (c - 1) % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
   if (c == 17) return k < 63 ? P.p[10][n * 319 + k] : 0.f;
@@ -82,7 +95,15 @@ __global__ void pack_fwd_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
   float* f = reinterpret_cast<float*>(packed + PK_F32_OFF);
   if (unit < F32_COUNT) {
     float v = 0.f;
-    if (unit < F32_BHEAD) { int l = unit / 256, n = unit % 256; v = P.p[2 * l + 1][n]; }
+    if (unit < F32_BHEAD) {
+      int l = unit / 256, n = unit % 256;
+      v = P.p[2 * l + 1][n];
+      if (P.kind == 1 && l == 0)
+        for (int k = 0; k < 21; ++k) v = fmaf(P.p[0][n * 84 + 63 + k], P.tpe[k], v);     // + W0[:, 63:84] PE(t)
+    } else if (P.kind == 1) {
+      int n = unit - F32_BHEAD;
+      v = (unit < F32_WRGB && n >= 128 && n < 131) ? P.p[17][n - 128] : 0.f;
+    }
     else if (unit < F32_WRGB) { int n = unit - F32_BHEAD; v = n < 128 ? fold[n * 257 + 256] : (n == 128 ? P.p[21][0] : 0.f); }
     else if (unit < F32_BRGB) { v = P.p[22][unit - F32_WRGB]; }
     else { int i = unit - F32_BRGB; v = i < 3 ? P.p[23][i] : 0.f; }
@@ -96,8 +117,10 @@ __global__ void pack_fwd_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
 struct FwdArgs {
   const float* rays; int ray_stride; int view_col;
   const float* z; int S; int64_t P;           // P = total sample rows
-  const uint8_t* packed; float* raw;
+  const float* pts;                           // optional explicit sample positions [P,3] (D-NeRF: x + dx)
+  const uint8_t* packed; float* raw;          // kind 0: raw[P,4];  kind 1: dx[P,3]
   uint8_t* ws; int64_t num_tiles;
+  int kind;
 };
 
 __device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
@@ -349,6 +372,14 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
             uint32_t v[32];
             tmem_ld32(tmem + lane_addr + dcol + 128, v);
             tmem_ld_wait();
+            if (g.kind == 1) {       // deformation net: dx = rows 128..130 of the head (model.py:136)
+              int64_t idx = tile * TILE + row;
+              if (idx < g.P) {
+                g.raw[idx * 3 + 0] = __uint_as_float(v[0]) + bh[128];
+                g.raw[idx * 3 + 1] = __uint_as_float(v[1]) + bh[129];
+                g.raw[idx * 3 + 2] = __uint_as_float(v[2]) + bh[130];
+              }
+            }
             s_scr[row] = make_float4(pr, pg, pb, __uint_as_float(v[0]) + bh[128]);
           }
           if (TRAIN) {
@@ -358,7 +389,7 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
           }
           tc_fence_before();
           named_bar_sync(1, 256);
-          if (hh == 0) {
+          if (hh == 0 && g.kind == 0) {
             float4 o = s_scr[row];
             const float* br = s_f32 + F32_BRGB;
             int64_t idx = tile * TILE + row;
@@ -380,10 +411,11 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
       if (valid) {
         int64_t r = idx / g.S;
         const float* ray = g.rays + r * g.ray_stride;
-        float zz = __ldg(g.z + idx);
+        float zz = g.pts ? 0.f : __ldg(g.z + idx);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          pos[j] = __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));      // run.py:385
+          pos[j] = g.pts ? __ldg(g.pts + idx * 3 + j)
+                         : __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));      // run.py:385
           dir[j] = __ldg(ray + g.view_col + j);
         }
       }
@@ -472,14 +504,19 @@ int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training) {
   return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES) + WS_TAIL_BYTES;
 }
 
-int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream) {
+static int pack_impl(const float* const* params, int kind, const float* tpe_host, void* packed, void* stream) {
   SW_REQUIRE(params && packed, "tc_pack_weights: null pointer");
+  SW_REQUIRE(kind == 0 || kind == 1, "tc_pack_weights: kind must be 0 (canonical net) or 1 (deformation net)");
+  SW_REQUIRE(kind == 0 || tpe_host, "tc_pack_weights: the deformation net needs the time embedding");
   SW_REQUIRE(aligned16(packed), "tc_pack_weights: packed must be 16-byte aligned");
   ParamPtrs P;
+  const int np = kind == 0 ? 24 : 18;
   for (int i = 0; i < 24; ++i) {
-    SW_REQUIRE(params[i], "tc_pack_weights: null parameter %d", i);
-    P.p[i] = params[i];
+    SW_REQUIRE(i >= np || params[i], "tc_pack_weights: null parameter %d", i);
+    P.p[i] = i < np ? params[i] : nullptr;
   }
+  P.kind = kind;
+  for (int i = 0; i < 24; ++i) P.tpe[i] = (kind == 1 && i < 21) ? tpe_host[i] : 0.f;
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
   fold_head_kernel<<<(128 * 257 + 255) / 256, 256, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
@@ -489,19 +526,29 @@ int swnerf_tc_pack_weights(const float* const* params, void* packed, void* strea
   return check_launch("tc_pack_weights");
 }
 
-int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
-                      int n_samples, const void* packed, float* raw, void* workspace, int training,
-                      void* stream) {
-  SW_REQUIRE(rays && z_vals && packed && raw, "tc_mlp_fwd: null pointer");
+int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream) {
+  return pack_impl(params, 0, nullptr, packed, stream);
+}
+
+int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host21, void* packed,
+                                void* stream) {
+  return pack_impl(params, 1, time_embedding_host21, packed, stream);
+}
+
+static int fwd_impl(const float* rays, int ray_stride, int view_col, const float* z_vals, const float* pts,
+                    int64_t n_rays, int n_samples, const void* packed, float* out, void* workspace, int training,
+                    int kind, void* stream) {
+  SW_REQUIRE(rays && packed && out && (z_vals || pts), "tc_mlp_fwd: null pointer");
   SW_REQUIRE(view_col >= 0 && view_col + 3 <= ray_stride, "tc_mlp_fwd: the fused kernel needs viewdirs in the ray batch");
   SW_REQUIRE(!training || workspace, "tc_mlp_fwd: training needs a workspace");
-  SW_REQUIRE(aligned16(raw) && aligned16(packed) && aligned16(workspace), "tc_mlp_fwd: buffers must be 16-byte aligned");
+  SW_REQUIRE(aligned16(out) || kind == 1, "tc_mlp_fwd: raw must be 16-byte aligned");
+  SW_REQUIRE(aligned16(packed) && aligned16(workspace), "tc_mlp_fwd: buffers must be 16-byte aligned");
   SW_REQUIRE(n_samples >= 1 && n_rays >= 0, "tc_mlp_fwd: bad sizes");
   if (n_rays == 0) return SWNERF_OK;
   FwdArgs g;
   g.rays = rays; g.ray_stride = ray_stride; g.view_col = view_col; g.z = z_vals; g.S = n_samples;
-  g.P = n_rays * n_samples; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = raw;
-  g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE;
+  g.P = n_rays * n_samples; g.pts = pts; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = out;
+  g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE; g.kind = kind;
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
   if (training) {
@@ -514,6 +561,30 @@ int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const flo
     mlp_fwd_kernel<false><<<grid, 512, SM_TOTAL, s>>>(g);
   }
   return check_launch("tc_mlp_fwd");
+}
+
+int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
+                      int n_samples, const void* packed, float* raw, void* workspace, int training,
+                      void* stream) {
+  SW_REQUIRE(z_vals, "tc_mlp_fwd: null pointer");
+  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed, raw, workspace, training, 0,
+                  stream);
+}
+
+int swnerf_tc_mlp_fwd_points(const float* rays, int ray_stride, int view_col, const float* pts, int64_t n_rays,
+                             int n_samples, const void* packed, float* raw, void* workspace, int training,
+                             void* stream) {
+  SW_REQUIRE(pts, "tc_mlp_fwd_points: null pointer");
+  return fwd_impl(rays, ray_stride, view_col, nullptr, pts, n_rays, n_samples, packed, raw, workspace, training, 0,
+                  stream);
+}
+
+int swnerf_tc_time_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
+                       int n_samples, const void* packed_time, float* dx, void* workspace, int training,
+                       void* stream) {
+  SW_REQUIRE(z_vals, "tc_time_fwd: null pointer");
+  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed_time, dx, workspace, training,
+                  1, stream);
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@ using namespace tcl;
 
 struct ParamPtrsB {
   const float* p[24];
+  int kind;            // 0: canonical net (24 tensors); 1: deformation net (_time.0..7, _time_out), see mlp_tc.cu
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -33,7 +34,10 @@ struct ParamPtrsB {
 __device__ __forceinline__ float bwd_weight(const ParamPtrsB& P, const float* fold, int c, int n, int k) {
   // B[n][k]: n = input channel of the layer (output of the data-gradient GEMM), k = its output unit
   if (c < 2) return fold[(c * 64 + k) * 257 + n];                 // W_fv[u][n]
-  if (c == 2) return k == 0 ? P.p[20][n] : 0.f;                   // alpha_linear row
+  if (c == 2) {
+    if (P.kind == 1) return k < 3 ? P.p[16][k * 256 + n] : 0.f;   // _time_out rows
+    return k == 0 ? P.p[20][n] : 0.f;                             // alpha_linear row
+  }
   int t = (c - 3) / 4, kc = (c - 3) % 4;
   int l = 7 - t;                                                  // 7,6,5,4,3,2,1
   int ld = (l == 5) ? 319 : 256, off = (l == 5) ? 63 : 0;
@@ -45,13 +49,29 @@ __global__ void pack_bwd_kernel(ParamPtrsB P, const uint8_t* __restrict__ packed
   int unit = blockIdx.x * blockDim.x + threadIdx.x;
   if (unit >= PKT_TOTAL_BYTES / 16) return;
   int byte = unit * 16;
-  int c = byte / CHUNK_B, in = byte % CHUNK_B;
-  int n = (in >> 10) * 8 + ((in >> 7) & 7);
-  int pu = (in >> 4) & 7;
-  int k0 = (pu ^ (n & 7)) * 8;
   __align__(16) __half h[8];
+  if (byte < PKT_DPE_OFF) {
+    int c = byte / CHUNK_B, in = byte % CHUNK_B;
+    int n = (in >> 10) * 8 + ((in >> 7) & 7);
+    int pu = (in >> 4) & 7;
+    int k0 = (pu ^ (n & 7)) * 8;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(bwd_weight(P, fold, c, n, k0 + i));
+    for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(bwd_weight(P, fold, c, n, k0 + i));
+  } else {
+    // input-gradient weights: chunk (layer 0 | 5, kc): image row = pe column c, image column = unit kc*64 + k
+    int b2 = byte - PKT_DPE_OFF;
+    int ch = b2 / DPE_CHUNK_B, in = b2 % DPE_CHUNK_B;
+    int cc = (in >> 10) * 8 + ((in >> 7) & 7);
+    int pu = (in >> 4) & 7;
+    int k0 = (pu ^ (cc & 7)) * 8;
+    const float* Wl = (ch < 4) ? P.p[0] : P.p[10];
+    int ld = (ch < 4) ? (P.kind == 1 ? 84 : 63) : 319;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int nn = (ch & 3) * 64 + k0 + i;
+      h[i] = __float2half_rn(cc < 63 ? Wl[(size_t)nn * ld + cc] : 0.f);
+    }
+  }
   *reinterpret_cast<uint4*>(packed_t + byte) = *reinterpret_cast<const uint4*>(h);
 }
 
@@ -77,13 +97,22 @@ __device__ __forceinline__ float grad_scale_from(const uint32_t* absmax, float f
 // 1. backward data
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
-  const float* d_raw; int64_t P; int64_t num_tiles;
+  const float* d_raw;          // kind 0: d_raw[P,4];  kind 1: d_dx[P,3]
+  int kind;
+  int64_t P; int64_t num_tiles;
   const uint8_t* packed; const uint8_t* packed_t;
   uint8_t* ws;
   float* grads[24];
   float* unfold;
   const uint32_t* absmax; float fixed_scale;
 };
+
+__device__ __forceinline__ float4 load_dout(const BwdArgs& g, int64_t idx) {
+  if (idx >= g.P) return make_float4(0.f, 0.f, 0.f, 0.f);
+  if (g.kind == 0) return __ldg(reinterpret_cast<const float4*>(g.d_raw) + idx);
+  // deformation net: the three d_dx components ride where d_sigma does (rows 128..130 of the head)
+  return make_float4(__ldg(g.d_raw + idx * 3), __ldg(g.d_raw + idx * 3 + 1), __ldg(g.d_raw + idx * 3 + 2), 0.f);
+}
 
 __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -171,7 +200,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
     uint32_t pre_hm[2] = {0u, 0u};
     if ((int64_t)blockIdx.x < g.num_tiles) {
       const int64_t idx0 = (int64_t)blockIdx.x * TILE + row;
-      if (idx0 < g.P) pre_dr = __ldg(reinterpret_cast<const float4*>(g.d_raw) + idx0);
+      pre_dr = load_dout(g, idx0);
       const uint32_t* m0 = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + (int64_t)blockIdx.x * (9 * 8 * 128);
       pre_hm[0] = __ldg(m0 + (8 * 8 + hh * 2 + 0) * 128 + row);
       pre_hm[1] = __ldg(m0 + (8 * 8 + hh * 2 + 1) * 128 + row);
@@ -196,7 +225,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float v = dr.x * s_wrgb[c0 + i] + dr.y * s_wrgb[128 + c0 + i] + dr.z * s_wrgb[256 + c0 + i];
-            val[i] = ((m >> i) & 1u) ? v : 0.f;
+            val[i] = (g.kind == 0 && ((m >> i) & 1u)) ? v : 0.f;      // the deformation net has no view branch
           }
           uint8_t* blk = s_act + hh * ACT_BLK;
 #pragma unroll
@@ -207,7 +236,9 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
         }
         uint8_t* blk = s_act + (2 + hh) * ACT_BLK;
         uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
-        if (hh == 0) u0.x = pack_half2(dr.w, 0.f);
+        if (g.kind == 1) {     // [d_dx0, d_dx1, d_dx2, 0..] in the sigma block; nothing in the rgb block
+          if (hh == 0) { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
+        } else if (hh == 0) u0.x = pack_half2(dr.w, 0.f);
         else { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 0)) = u0;
         *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
@@ -235,7 +266,7 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
           const int64_t ntile = tile + gridDim.x;
           if (ntile < g.num_tiles) {
             const int64_t nidx = ntile * TILE + row;
-            pre_dr = (nidx < g.P) ? __ldg(reinterpret_cast<const float4*>(g.d_raw) + nidx) : make_float4(0.f, 0.f, 0.f, 0.f);
+            pre_dr = load_dout(g, nidx);
             const uint32_t* nmask = reinterpret_cast<const uint32_t*>(g.ws + mask_base) + ntile * (9 * 8 * 128);
             pre_hm[0] = __ldg(nmask + (8 * 8 + hh * 2 + 0) * 128 + row);
             pre_hm[1] = __ldg(nmask + (8 * 8 + hh * 2 + 1) * 128 + row);
@@ -340,8 +371,9 @@ struct WgArgs {
   float* grads[24]; float* unfold;
   const uint32_t* absmax; float fixed_scale;
   int job_first_cta[WG_JOBS + 1];
+  int kind;
 };
-__constant__ WgJob c_jobs[WG_JOBS];
+__constant__ WgJob c_jobs[2][WG_JOBS];       // [kind]
 
 constexpr int HALF_BLK = 64 * 128;     // 64 samples of one 64-column block
 
@@ -354,7 +386,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
 
   int job = 0;
   while (job + 1 < WG_JOBS && (int)blockIdx.x >= g.job_first_cta[job + 1]) ++job;
-  const WgJob& J = c_jobs[job];
+  const WgJob& J = c_jobs[g.kind][job];
   const int ncta = g.job_first_cta[job + 1] - g.job_first_cta[job];
   const int cta = blockIdx.x - g.job_first_cta[job];
   const int64_t t_begin = g.num_tiles * cta / ncta, t_end = g.num_tiles * (cta + 1) / ncta;
@@ -472,7 +504,8 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
             if (col < J.bs[b].nvalid) {
               const float v = bacc[b][e] * inv;
               if (J.bs[b].out_param >= 0) atomicAdd(g.grads[J.bs[b].out_param] + J.bs[b].out_off + col, v);
-              else { atomicAdd(g.unfold + 128 * 256 + col, v); atomicAdd(g.grads[17] + col, v); }
+              else if (J.bs[b].out_param == -1) { atomicAdd(g.unfold + 128 * 256 + col, v); atomicAdd(g.grads[17] + col, v); }
+              else { atomicAdd(g.unfold + col, v); atomicAdd(g.grads[1] + col, v); }   // -2: d b0 of THIS call + grads
             }
           }
         }
@@ -549,6 +582,95 @@ __global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restri
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 4. input gradient of the canonical net (D-NeRF: PE sits inside the graph, model.py:148-149)
+//      dPE[s, c] = sum_n dy0[s, n] W0[n, c] + dy5[s, n] W5[n, c]   (c < 63)        tcgen05, 128 x 64 x 512 per tile
+//      dx[s, j]  = dPE[j] + sum_k 2^k (cos(2^k x_j) dPE[3+6k+j] - sin(2^k x_j) dPE[6+6k+j])      (d embed / d x)
+// ------------------------------------------------------------------------------------------------
+struct DpeArgs {
+  uint8_t* ws; int64_t num_tiles; int64_t P;
+  const uint8_t* packed_t; const float* pts; float* d_pts;
+  const uint32_t* absmax; float fixed_scale;
+};
+
+__global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_w = smem;                         // 8 x [64 x 64] weights, resident
+  uint8_t* s_dy = smem + 8 * DPE_CHUNK_B;      // dy0 | dy5 images of the current tile (2 x 64 KB)
+  __shared__ uint64_t b_w, b_full, b_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { mbar_init(&b_w, 1); mbar_init(&b_full, 1); mbar_init(&b_done, 1); mbar_fence_init(); }
+  if (warp == 5) tmem_alloc<64>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int64_t dy_base = g.num_tiles * (WS_TILE_BYTES + WS_MASK_BYTES);
+  const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
+  if (threadIdx.x == 128) {
+    mbar_expect_tx(&b_w, 8 * DPE_CHUNK_B);
+    bulk_g2s(s_w, g.packed_t + PKT_DPE_OFF, 8 * DPE_CHUNK_B, &b_w);
+  }
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
+    if (warp == 4) {
+      if (lane == 0) {
+        const uint8_t* src = g.ws + dy_base + tile * WS_DY_BYTES;
+        mbar_expect_tx(&b_full, 2 * ACT_BYTES);
+        bulk_g2s(s_dy, src + 0 * ACT_BYTES, ACT_BYTES, &b_full);
+        bulk_g2s(s_dy + ACT_BYTES, src + 5 * (size_t)ACT_BYTES, ACT_BYTES, &b_full);
+      }
+      if (it == 0) mbar_wait(&b_w, 0);
+      mbar_wait(&b_full, it & 1);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t idesc = umma_idesc_f16(128, 64, 0, 0);
+        const uint32_t a0 = smem_u32(s_dy), w0 = smem_u32(s_w);
+        for (int ch = 0; ch < 8; ++ch)
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem, umma_desc_kmajor(a0 + ch * ACT_BLK + ks * 32), umma_desc_kmajor(w0 + ch * DPE_CHUNK_B + ks * 32),
+                     idesc, (ch > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&b_done);
+      }
+      __syncwarp();
+    } else if (warp < 4) {
+      mbar_wait(&b_done, it & 1);
+      tc_fence_after();
+      const int row = warp * 32 + lane;
+      const int64_t idx = tile * TILE + row;
+      uint32_t va[32], vb[32];
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), va);
+      tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + 32, vb);
+      tmem_ld_wait();
+      if (idx < g.P) {
+        float d[64];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { d[i] = __uint_as_float(va[i]); d[32 + i] = __uint_as_float(vb[i]); }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          float x = __ldg(g.pts + idx * 3 + j);
+          float acc = d[j];
+#pragma unroll
+          for (int k = 0; k < 10; ++k) {
+            float f = (float)(1 << k), sn, cs;
+            sincosf(x * f, &sn, &cs);
+            acc += f * (cs * d[3 + 6 * k + j] - sn * d[6 + 6 * k + j]);
+          }
+          g.d_pts[idx * 3 + j] = acc * inv;
+        }
+      }
+      tc_fence_before();
+    }
+    // the next tile's images may only land once every consumer of this tile is done
+    __syncthreads();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 5) tmem_dealloc<64>(tmem);
+}
+
 // job table ------------------------------------------------------------------------------------
 static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the layer input */, int col_off, int ld) {
   J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 8 * HALF_BLK; J.nstage = 3;
@@ -559,13 +681,14 @@ static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the 
     J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 256, m * 256, 2 * l, m * 128 * ld + col_off, ld, 1, 256};
 }
 
-static void build_jobs(WgJob* jobs) {
+static void build_jobs(WgJob* jobs, int kind) {
   memset(jobs, 0, sizeof(WgJob) * WG_JOBS);
+  const int ld0 = kind == 1 ? 84 : 63;               // pts_linears.0 is [256, 63]; _time.0 is [256, 63 + 21]
   // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :63], dW5[:, :63]
   {
     WgJob& J = jobs[0];
     J.npieces = 3; J.nmma = 4; J.nbias = 2; J.stage_bytes = 9 * HALF_BLK; J.nstage = 3;
-    J.bs[0] = {0, 256, 256, 1, 0};                   // db of pts_linears.0
+    J.bs[0] = {0, 256, 256, kind == 1 ? -2 : 1, 0};  // db of pts_linears.0 (deformation net: also kept per call, see bwd_impl)
     J.bs[1] = {4 * HALF_BLK, 256, 256, 11, 0};       // db of pts_linears.5
     J.pc[0] = {1, 0 * ACT_BYTES, 4, 0};
     J.pc[1] = {1, 5 * ACT_BYTES, 4, 4 * HALF_BLK};
@@ -573,7 +696,7 @@ static void build_jobs(WgJob* jobs) {
     for (int a = 0; a < 2; ++a)
       for (int m = 0; m < 2; ++m)
         J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64, (a * 2 + m) * 64,
-                           a == 0 ? 0 : 10, m * 128 * (a == 0 ? 63 : 319), a == 0 ? 63 : 319, 1, 63};
+                           a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : 319), a == 0 ? ld0 : 319, 1, 63};
   }
   for (int l = 1; l <= 4; ++l) wg_std_job(jobs[l], l, WS_H_OFF + (l - 1) * ACT_BYTES, 0, 256);
   wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, 63, 319);
@@ -596,12 +719,22 @@ static void build_jobs(WgJob* jobs) {
     J.mm[2] = {5 * HALF_BLK, 2 * HALF_BLK, 16, 320, 20, 0, 1, 0, 1};         // d w_alpha[0:128]   = h7^T d_sigma
     J.mm[3] = {7 * HALF_BLK, 2 * HALF_BLK, 16, 336, 20, 128, 1, 0, 1};       // d w_alpha[128:256]
     J.mm[4] = {9 * HALF_BLK, 3 * HALF_BLK, 16, 352, 22, 0, 1, 128, 3};       // dW_rgb[j][c] = h9^T d_rgb
+    if (kind == 1) {
+      // deformation net: only its 256->3 output layer lives in the head.  stage: dyH block 2 | h7 (4 blocks)
+      memset(&J, 0, sizeof(J));
+      J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 5 * HALF_BLK; J.nstage = 3;
+      J.pc[0] = {1, WS_DYH_OFF + 2 * ACT_BLK, 1, 0};
+      J.pc[1] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, 1 * HALF_BLK};
+      J.mm[0] = {1 * HALF_BLK, 0, 16, 0, 16, 0, 1, 256, 3};                  // dW_out[j][c], c < 128  = h7^T d_dx
+      J.mm[1] = {3 * HALF_BLK, 0, 16, 16, 16, 128, 1, 256, 3};               // c >= 128
+      J.bs[0] = {0, 8, 3, 17, 0};                                            // _time_out.bias
+    }
   }
 }
 
-static void assign_ctas(int n_cta, int* first) {
+static void assign_ctas(int n_cta, int* first, int kind) {
   // CTAs per job in proportion to the bytes a job streams per tile
-  const int w[WG_JOBS] = {144, 128, 128, 128, 128, 128, 128, 128, 176};
+  const int w[WG_JOBS] = {144, 128, 128, 128, 128, 128, 128, 128, kind == 1 ? 80 : 176};
   int tot = 0;
   for (int j = 0; j < WG_JOBS; ++j) tot += w[j];
   int cnt[WG_JOBS], used = 0;
@@ -643,27 +776,39 @@ int swnerf_tc_last_bwd_ms(float* data_ms, float* weight_ms) {
 
 int64_t swnerf_tc_packed_t_bytes(void) { return PKT_TOTAL_BYTES; }
 
-int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
+static int pack_t_impl(const float* const* params, int kind, const void* packed, void* packed_t, void* stream) {
   SW_REQUIRE(params && packed && packed_t, "tc_pack_weights_t: null pointer");
   SW_REQUIRE(aligned16(packed_t), "tc_pack_weights_t: packed_t must be 16-byte aligned");
   ParamPtrsB P;
+  const int np = kind == 0 ? 24 : 18;
   for (int i = 0; i < 24; ++i) {
-    SW_REQUIRE(params[i], "tc_pack_weights_t: null parameter %d", i);
-    P.p[i] = params[i];
+    SW_REQUIRE(i >= np || params[i], "tc_pack_weights_t: null parameter %d", i);
+    P.p[i] = i < np ? params[i] : nullptr;
   }
+  P.kind = kind;
   pack_bwd_kernel<<<(PKT_TOTAL_BYTES / 16 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
       P, reinterpret_cast<const uint8_t*>(packed), reinterpret_cast<uint8_t*>(packed_t));
   return check_launch("tc_pack_weights_t");
 }
 
-int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
-                      const float* const* params, void* workspace, float* const* grads, float grad_scale,
-                      void* stream) {
-  SW_REQUIRE(d_raw && packed && packed_t && params && workspace && grads, "tc_mlp_bwd: null pointer");
-  SW_REQUIRE(aligned16(d_raw) && aligned16(workspace), "tc_mlp_bwd: buffers must be 16-byte aligned");
+int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
+  return pack_t_impl(params, 0, packed, packed_t, stream);
+}
+int swnerf_tc_pack_weights_time_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
+  return pack_t_impl(params, 1, packed, packed_t, stream);
+}
+
+static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
+                    const float* const* params, void* workspace, float* const* grads, float grad_scale, int kind,
+                    const float* tpe_dev, const float* pts, float* d_pts, void* stream) {
+  SW_REQUIRE(d_out && packed && packed_t && params && workspace && grads, "tc_mlp_bwd: null pointer");
+  SW_REQUIRE(aligned16(workspace) && (kind == 1 || aligned16(d_out)), "tc_mlp_bwd: buffers must be 16-byte aligned");
   SW_REQUIRE(grad_scale >= 0.f, "tc_mlp_bwd: grad_scale must be >= 0 (0 = automatic)");
+  SW_REQUIRE(kind == 0 || tpe_dev, "tc_mlp_bwd: the deformation net needs the time embedding on the device");
+  SW_REQUIRE(!d_pts || (pts && kind == 0), "tc_mlp_bwd: the input gradient needs the sample positions (canonical net only)");
   if (n_rays == 0) return SWNERF_OK;
   cudaStream_t s = (cudaStream_t)stream;
+  const int np = kind == 0 ? 24 : 18;
   const int64_t P = n_rays * n_samples;
   const int64_t tiles = (P + TILE - 1) / TILE;
   uint8_t* ws = reinterpret_cast<uint8_t*>(workspace);
@@ -672,29 +817,33 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
   float* unfold = reinterpret_cast<float*>(tail + 256);
   cudaMemsetAsync(tail, 0, 256 + UNFOLD_FLOATS * sizeof(float), s);
   if (grad_scale == 0.f) {
-    absmax_kernel<<<sm_count() * 4, 256, 0, s>>>(d_raw, P * 4, absmax);
+    absmax_kernel<<<sm_count() * 4, 256, 0, s>>>(d_out, P * (kind == 0 ? 4 : 3), absmax);
     int rc = check_launch("tc_absmax");
     if (rc) return rc;
   }
-  for (int i = 0; i < 24; ++i) SW_REQUIRE(grads[i] && params[i], "tc_mlp_bwd: null gradient / parameter %d", i);
+  for (int i = 0; i < np; ++i) SW_REQUIRE(grads[i] && params[i], "tc_mlp_bwd: null gradient / parameter %d", i);
 
   BwdArgs b;
-  b.d_raw = d_raw; b.P = P; b.num_tiles = tiles;
+  b.d_raw = d_out; b.kind = kind; b.P = P; b.num_tiles = tiles;
   b.packed = reinterpret_cast<const uint8_t*>(packed); b.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
   b.ws = ws; b.unfold = unfold; b.absmax = absmax; b.fixed_scale = grad_scale;
-  for (int i = 0; i < 24; ++i) b.grads[i] = grads[i];
+  for (int i = 0; i < 24; ++i) b.grads[i] = i < np ? grads[i] : nullptr;
   static thread_local bool attr = false;
   static thread_local int wg_smem = 0;
+  const int dpe_smem = 8 * DPE_CHUNK_B + 2 * ACT_BYTES + 1024;
   if (!attr) {
     cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
-    WgJob jobs[WG_JOBS];
-    build_jobs(jobs);
-    for (int j = 0; j < WG_JOBS; ++j) {
-      int need = jobs[j].stage_bytes * jobs[j].nstage + 1024;
-      if (need > wg_smem) wg_smem = need;
-    }
+    WgJob jobs[2][WG_JOBS];
+    build_jobs(jobs[0], 0);
+    build_jobs(jobs[1], 1);
+    for (int k = 0; k < 2; ++k)
+      for (int j = 0; j < WG_JOBS; ++j) {
+        int need = jobs[k][j].stage_bytes * jobs[k][j].nstage + 1024;
+        if (need > wg_smem) wg_smem = need;
+      }
     cudaMemcpyToSymbol(c_jobs, jobs, sizeof(jobs));
     cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem);
+    cudaFuncSetAttribute(mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dpe_smem);
     attr = true;
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
@@ -703,23 +852,59 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
   int rc = check_launch("tc_mlp_bwd_data");
   if (rc) return rc;
 
+  if (d_pts) {
+    DpeArgs d;
+    d.ws = ws; d.num_tiles = tiles; d.P = P; d.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
+    d.pts = pts; d.d_pts = d_pts; d.absmax = absmax; d.fixed_scale = grad_scale;
+    mlp_bwd_input_kernel<<<grid, 192, dpe_smem, s>>>(d);
+    rc = check_launch("tc_mlp_bwd_input");
+    if (rc) return rc;
+  }
+
   WgArgs w;
-  w.ws = ws; w.num_tiles = tiles; w.unfold = unfold; w.absmax = absmax; w.fixed_scale = grad_scale;
-  for (int i = 0; i < 24; ++i) w.grads[i] = grads[i];
+  w.ws = ws; w.num_tiles = tiles; w.unfold = unfold; w.absmax = absmax; w.fixed_scale = grad_scale; w.kind = kind;
+  for (int i = 0; i < 24; ++i) w.grads[i] = i < np ? grads[i] : nullptr;
   int n_cta = sm_count();
   if (n_cta < WG_JOBS) n_cta = WG_JOBS;
-  assign_ctas(n_cta, w.job_first_cta);
+  assign_ctas(n_cta, w.job_first_cta, kind);
   if (g_prof) cudaEventRecord(g_ev[1], s);
   mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w);
   if (g_prof) { cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
   rc = check_launch("tc_mlp_bwd_weight");
   if (rc) return rc;
 
-  // un-fold the head: G = d W_fv, gb = d b_fv -> feature_linear / views_linears gradients (db_v was added in bwd_data)
-  unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
-                                          grads[19], grads[16]);
-  rc = check_launch("tc_unfold_head");
+  if (kind == 0) {
+    // un-fold the head: G = d W_fv, gb = d b_fv -> feature_linear / views_linears gradients (db_v was added above)
+    unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
+                                            grads[19], grads[16]);
+    rc = check_launch("tc_unfold_head");
+  } else {
+    // _time.0.weight[:, 63:84]: the time embedding is the same for every sample, so this block of the gradient
+    // is the outer product (sum_s dy0[s]) x PE(t) = d b0 x PE(t); this call's d b0 sits in the scratch.
+    rc = swnerf_sgemm(0, unfold, 1, tpe_dev, 1, grads[0] + 63, 84, 256, 21, 1, nullptr, 1, 0, nullptr, 0, stream);
+  }
   return rc;
+}
+
+int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
+                      const float* const* params, void* workspace, float* const* grads, float grad_scale,
+                      void* stream) {
+  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, params, workspace, grads, grad_scale, 0, nullptr, nullptr,
+                  nullptr, stream);
+}
+
+int swnerf_tc_mlp_bwd_points(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
+                             const void* packed_t, const float* const* params, void* workspace, float* const* grads,
+                             float grad_scale, const float* pts, float* d_pts, void* stream) {
+  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, params, workspace, grads, grad_scale, 0, nullptr, pts,
+                  d_pts, stream);
+}
+
+int swnerf_tc_time_bwd(const float* d_dx, int64_t n_rays, int n_samples, const void* packed_time,
+                       const void* packed_time_t, const float* const* params, const float* time_embedding_dev21,
+                       void* workspace, float* const* grads, float grad_scale, void* stream) {
+  return bwd_impl(d_dx, n_rays, n_samples, packed_time, packed_time_t, params, workspace, grads, grad_scale, 1,
+                  time_embedding_dev21, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

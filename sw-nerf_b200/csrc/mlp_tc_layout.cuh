@@ -56,7 +56,11 @@ constexpr int64_t WS_DY_BYTES = 9 * ACT_BYTES;                   // 589,824
 // ---- transposed weight stream of the backward-data kernel: chunk order per tile
 //  0,1: head^T (y9 units 0..127) 2: head^T (sigma row) | 3..30: L7^T, L6^T, L5^T(h part), L4^T .. L1^T, 4 chunks each
 constexpr int NT_CHUNKS = 31;
-constexpr int PKT_TOTAL_BYTES = NT_CHUNKS * CHUNK_B;
+// followed by the input-gradient weights (D-NeRF needs d/dx of the canonical net): W0[:, :63]^T and
+// W5[:, :63]^T as eight [64 x 64] K-major images (pe column x unit)
+constexpr int PKT_DPE_OFF = NT_CHUNKS * CHUNK_B;
+constexpr int DPE_CHUNK_B = 64 * 128;
+constexpr int PKT_TOTAL_BYTES = PKT_DPE_OFF + 8 * DPE_CHUNK_B;
 
 // shared memory of the backward-data kernel
 constexpr int SMB_ACT = 0;

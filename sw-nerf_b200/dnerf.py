@@ -12,7 +12,7 @@ import os
 
 import torch
 
-from . import ops
+from . import ops, tc
 from .embedder import get_embedder
 from .model import NeRF
 from .ray import get_rays, ndc_rays, raw_noise, pytest_uniform
@@ -63,9 +63,20 @@ def run_network(inputs, viewdirs, frame_time, fn, embed_fn, embeddirs_fn, embedt
 class DNerfNetworkQuery:
     """network_query_fn of run_dnerf.py:279-284 as an object, plus the fused ray entry."""
 
-    def __init__(self, embed_fn, embeddirs_fn, embedtime_fn, netchunk=1024 * 64, embd_time_discr=True):
+    def __init__(self, embed_fn, embeddirs_fn, embedtime_fn, netchunk=1024 * 64, embd_time_discr=True,
+                 precision=None):
         self.embed_fn, self.embeddirs_fn, self.embedtime_fn = embed_fn, embeddirs_fn, embedtime_fn
         self.netchunk, self.embd_time_discr = netchunk, embd_time_discr
+        self.precision = precision or os.environ.get("SWNERF_PRECISION", "tc")
+        if self.precision not in ("tc", "fp32"):
+            raise ValueError("precision must be 'tc' or 'fp32'")
+
+    def uses_tc(self, network_fn, has_views):
+        """Fused tcgen05 kernels for the shape every reference D-NeRF config uses (8x256, PE 10 / 10 / 4)."""
+        return (self.precision == "tc" and tc.available() and tc.bwd_available() and has_views
+                and hasattr(network_fn, "_time") and tc.dnerf_tc_eligible(network_fn)
+                and getattr(self.embed_fn, "L", None) == 10 and getattr(self.embedtime_fn, "L", None) == 10
+                and getattr(self.embeddirs_fn, "L", None) == 4)
 
     def __call__(self, inputs, viewdirs, ts, network_fn):
         return run_network(inputs, viewdirs, ts, network_fn, embed_fn=self.embed_fn,
@@ -75,6 +86,8 @@ class DNerfNetworkQuery:
     def query_rays(self, ray_batch, z_vals, network_fn, view_col, cur_time: float):
         N, S = z_vals.shape
         dev = z_vals.device
+        if self.uses_tc(network_fn, view_col >= 0):
+            return tc.dnerf_query(network_fn, ray_batch, z_vals, view_col, float(cur_time))
         L_pos = self.embed_fn.L
         L_dir = self.embeddirs_fn.L if view_col >= 0 else -1
         emb = ops.encode_points(ray_batch, z_vals, L_pos, L_dir, view_col)
@@ -280,7 +293,8 @@ def _build_models(args, embed_fn, input_ch, embedtime_fn, input_ch_time, embeddi
         model_fine = mk(args.netdepth_fine, args.netwidth_fine)
         grad_vars += list(model_fine.parameters())
     q = DNerfNetworkQuery(embed_fn, embeddirs_fn, embedtime_fn, args.netchunk,
-                          embd_time_discr=args.nerf_type != "temporal")
+                          embd_time_discr=args.nerf_type != "temporal",
+                          precision=getattr(args, "swnerf_precision", None))
     return model, model_fine, grad_vars, q
 
 

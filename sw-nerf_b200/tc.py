@@ -109,3 +109,148 @@ def mlp_query(network, ray_batch, z_vals, view_col, grad_scale=None):
     params = network.param_list()
     training = torch.is_grad_enabled() and any(p.requires_grad for p in params)   # (grad mode is off inside forward)
     return TcMlpFn.apply(network, ray_batch, z_vals, view_col, grad_scale, training, *params)
+
+
+# ------------------------------------------------------------------------------------------------
+# D-NeRF on the fused kernels: deformation network (x, t) -> dx and canonical network at x + dx
+# ------------------------------------------------------------------------------------------------
+def time_embedding(t: float, L: int = 10):
+    """PE(t) as 1 + 2L fp32 values (embedder.py:33-42 applied to the single scalar time of the call)."""
+    import numpy as np
+    t32 = np.float32(t)
+    vals = [t32]
+    for k in range(L):
+        a = np.float32(t32 * np.float32(2.0 ** k))
+        vals += [np.sin(a, dtype=np.float32), np.cos(a, dtype=np.float32)]
+    return [float(v) for v in vals]
+
+
+def dnerf_tc_eligible(model) -> bool:
+    """DirectTemporalNeRF in the shape every reference D-NeRF config uses (8x256, skips [4], PE 10/10/4)."""
+    occ = getattr(model, "_occ", None)
+    return (occ is not None and occ.tc_eligible() and model.D == 8 and model.W == 256 and list(model.skips) == [4]
+            and model.input_ch == 63 and model.input_ch_time == 21 and getattr(model.embed_fn, "L", None) == 10)
+
+
+def packed_time_weights(model, t: float, need_bwd=False):
+    import ctypes
+    params = model.time_param_list()
+    st = getattr(model, "_swnerf_packed_time", None)
+    if st is None:
+        st = _Packed()
+        object.__setattr__(model, "_swnerf_packed_time", st)
+    v = (float(t),) + _versions(params)
+    dev = params[0].device
+    if st.versions != v or st.fwd is None:
+        for p in params:
+            ptr(p, F32, "parameter")
+        if st.fwd is None or st.fwd.device != dev:
+            st.fwd = torch.empty(int(_lib.lib().swnerf_tc_packed_bytes()), dtype=torch.uint8, device=dev)
+        tpe = time_embedding(t)
+        call("swnerf_tc_pack_weights_time", ptr_array([p.detach() for p in params]), (ctypes.c_float * 21)(*tpe),
+             st.fwd.data_ptr(), stream())
+        st.versions = v
+    if need_bwd and (st.bwd_versions != v or st.bwd is None):
+        if st.bwd is None or st.bwd.device != dev:
+            st.bwd = torch.empty(int(_lib.lib().swnerf_tc_packed_t_bytes()), dtype=torch.uint8, device=dev)
+        call("swnerf_tc_pack_weights_time_t", ptr_array([p.detach() for p in params]), st.fwd.data_ptr(),
+             st.bwd.data_ptr(), stream())
+        st.bwd_versions = v
+    return st
+
+
+def _grad_targets(params):
+    direct = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() and p.grad.device == p.device
+                 for p in params) and not torch.is_grad_enabled()
+    return direct, ([p.grad for p in params] if direct else [torch.zeros_like(p) for p in params])
+
+
+class TcTimeFn(torch.autograd.Function):
+    """dx[N,S,3] = deformation network at (o + d z, t)  (model.py:128-136) on the fused forward kernel."""
+
+    @staticmethod
+    def forward(ctx, model, ray_batch, z_vals, view_col, t, grad_scale, training, *params):
+        N, S = z_vals.shape
+        dev = z_vals.device
+        st = packed_time_weights(model, t, need_bwd=training)
+        dx = torch.empty((N, S, 3), dtype=F32, device=dev)
+        ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(N * S, 1)), dtype=torch.uint8, device=dev) \
+            if training else None
+        call("swnerf_tc_time_fwd", ptr(ray_batch, F32, "ray_batch"), ray_batch.shape[1], view_col,
+             ptr(z_vals, F32, "z_vals"), N, S, st.fwd.data_ptr(), dx.data_ptr(),
+             None if ws is None else ws.data_ptr(), int(training), stream())
+        if training:
+            ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = ws, (N, S), params, grad_scale
+            ctx.packed = (st.fwd, st.bwd)
+            ctx.tpe = torch.tensor(time_embedding(t), dtype=F32, device=dev)
+        return dx
+
+    @staticmethod
+    def backward(ctx, d_dx):
+        N, S = ctx.shape
+        params = ctx.params
+        d_dx = d_dx.contiguous()
+        direct, grads = _grad_targets(params)
+        fwd, bwd = ctx.packed
+        call("swnerf_tc_time_bwd", ptr(d_dx, F32, "d_dx"), N, S, fwd.data_ptr(), bwd.data_ptr(),
+             ptr_array([p.detach() for p in params]), ctx.tpe.data_ptr(), ctx.ws.data_ptr(), ptr_array(grads),
+             float(ctx.grad_scale), stream())
+        ctx.ws = None
+        return (None,) * 7 + ((None,) * len(params) if direct else tuple(grads))
+
+
+class TcOccPointsFn(torch.autograd.Function):
+    """raw[N,S,4] = canonical network at explicit positions pts[N*S,3] (model.py:148-150), with d/d pts."""
+
+    @staticmethod
+    def forward(ctx, network, ray_batch, pts, n_samples, view_col, grad_scale, training, *params):
+        P = pts.shape[0]
+        N = P // n_samples
+        dev = pts.device
+        pts = pts.contiguous()
+        st = packed_weights(network, need_bwd=training)
+        raw = torch.empty((N, n_samples, 4), dtype=F32, device=dev)
+        ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(P, 1)), dtype=torch.uint8, device=dev) \
+            if training else None
+        call("swnerf_tc_mlp_fwd_points", ptr(ray_batch, F32, "ray_batch"), ray_batch.shape[1], view_col,
+             ptr(pts, F32, "pts"), N, n_samples, st.fwd.data_ptr(), raw.data_ptr(),
+             None if ws is None else ws.data_ptr(), int(training), stream())
+        if training:
+            ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = ws, (N, n_samples), params, grad_scale
+            ctx.packed = (st.fwd, st.bwd)
+            ctx.pts = pts
+            ctx.pts_grad = ctx.needs_input_grad[2]
+        return raw
+
+    @staticmethod
+    def backward(ctx, d_raw):
+        N, S = ctx.shape
+        params = ctx.params
+        d_raw = d_raw.contiguous()
+        direct, grads = _grad_targets(params)
+        fwd, bwd = ctx.packed
+        d_pts = torch.empty_like(ctx.pts) if ctx.pts_grad else None
+        call("swnerf_tc_mlp_bwd_points", ptr(d_raw, F32, "d_raw"), N, S, fwd.data_ptr(), bwd.data_ptr(),
+             ptr_array([p.detach() for p in params]), ctx.ws.data_ptr(), ptr_array(grads), float(ctx.grad_scale),
+             ctx.pts.data_ptr() if ctx.pts_grad else None, None if d_pts is None else d_pts.data_ptr(), stream())
+        ctx.ws = None
+        return (None, None, d_pts, None, None, None, None) + ((None,) * len(params) if direct else tuple(grads))
+
+
+def dnerf_query(model, ray_batch, z_vals, view_col, cur_time: float, grad_scale=0.0):
+    """(raw[N,S,4], dx[N,S,3]) of DirectTemporalNeRF.forward (model.py:138-151) for the rays' sample points."""
+    N, S = z_vals.shape
+    occ = model._occ
+    occ_params = occ.param_list()
+    grad_on = torch.is_grad_enabled()
+    if cur_time == 0. and model.zero_canonical:                                  # model.py:144-145
+        raw = mlp_query(occ, ray_batch, z_vals, view_col, grad_scale)
+        return raw, torch.zeros((N, S, 3), dtype=F32, device=z_vals.device)
+    tparams = model.time_param_list()
+    t_train = grad_on and any(p.requires_grad for p in tparams)
+    dx = TcTimeFn.apply(model, ray_batch, z_vals, view_col, float(cur_time), grad_scale, t_train, *tparams)
+    base = ray_batch[:, None, 0:3] + ray_batch[:, None, 3:6] * z_vals[..., None]   # run_dnerf.py:455, mul then add
+    pts = (base + dx).reshape(-1, 3)                                              # model.py:148
+    o_train = grad_on and (pts.requires_grad or any(p.requires_grad for p in occ_params))
+    raw = TcOccPointsFn.apply(occ, ray_batch, pts, S, view_col, grad_scale, o_train, *occ_params)
+    return raw, dx

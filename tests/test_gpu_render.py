@@ -209,7 +209,7 @@ def _dnerf_args(tmp):
                      ft_path=None, basedir=str(tmp), expname="e", no_reload=True, perturb=1.0, white_bkgd=True,
                      raw_noise_std=0.0, dataset_type="blender", no_ndc=False, lindisp=False,
                      nerf_type="direct_temporal", use_two_models_for_fine=False, not_zero_canonical=False,
-                     do_half_precision=False)
+                     do_half_precision=False, swnerf_precision="fp32")
 
 
 @pytest.mark.parametrize("tag", ["t037", "t0"])
@@ -456,3 +456,40 @@ def test_multires_levels_vs_oracle(channels, tmp_path):
     gr = torch.cat([(pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])).reshape(-1)
                     for n, _ in model.named_parameters()])
     assert rel_l2(gg, gr) < (1e-3 if Lp <= 10 else 5e-2), rel_l2(gg, gr)
+
+
+# ---------------------------------------------------------------- D-NeRF on the fused tcgen05 kernels
+@needs_tc_bwd
+@pytest.mark.parametrize("tval", [0.37, 0.0])
+def test_dnerf_tc_given_identical_samples(golden, tmp_path, tval):
+    """Deformation net (x,t)->dx and canonical net at x+dx on the fused kernels, at the oracle's sample positions
+    (z_vals override, run_dnerf.py:408): maps <= 1e-3; flat gradient <= 2e-2 relative L2 (two chained fp16-operand
+    networks, the canonical one entered through the 2^9-amplifying encoding of x + dx)."""
+    g = golden("render_rays_dnerf")
+    args = _dnerf_args(tmp_path)
+    args.swnerf_precision = "tc"
+    kw, _, _, _, _ = dnerf.create_nerf(args, device=torch.device(DEV))
+    model = kw["network_fn"]
+    assert kw["network_query_fn"].uses_tc(model, True)
+    params = O.make_params(O.dnerf_param_shapes(), int(g["seed"]))
+    load(model, params)
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    tag = "t037"
+    rays_np = g[f"{tag}/rays"].copy(); rays_np[:, 8] = tval
+    tgt_np, z_np = g[f"{tag}/target"], g[f"{tag}/z_vals"]
+    pr = {k: v.clone().requires_grad_() for k, v in params.items()}
+    ref = O.render_rays_dnerf(torch.from_numpy(rays_np), pr, 64, 128, perturb=1.0, white_bkgd=True,
+                              z_vals=torch.from_numpy(z_np), retraw=True)
+    lr = torch.mean((ref["rgb_map"] - torch.from_numpy(tgt_np)) ** 2) + 0.1 * torch.sum(ref["position_delta"] ** 2)
+    lr.backward()
+    ret = dnerf.render_rays(T(rays_np), z_vals=T(z_np), retraw=True, **kw)
+    lg = torch.mean((ret["rgb_map"] - T(tgt_np)) ** 2) + 0.1 * torch.sum(ret["position_delta"] ** 2)
+    lg.backward()
+    assert relmax(ret["position_delta"], ref["position_delta"]) < 2e-3 or tval == 0.0
+    assert rel_l2(ret["raw"], ref["raw"]) < 1e-2
+    assert relmax(ret["rgb_map"], ref["rgb_map"]) < 2e-3
+    gg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for _, p in model.named_parameters()])
+    gr = torch.cat([(pr[n].grad if pr[n].grad is not None else torch.zeros_like(pr[n])).reshape(-1)
+                    for n, _ in model.named_parameters()])
+    assert torch.isfinite(gg).all()
+    assert rel_l2(gg, gr) < 3e-2, rel_l2(gg, gr)

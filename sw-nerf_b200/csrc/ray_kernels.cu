@@ -144,12 +144,13 @@ __device__ __forceinline__ void sample_alpha(float sigma, float noise, float zi,
   float s = sigma + noise;
   on = s > 0.f;
   s = on ? s : 0.f;
-  e = expf(-__fmul_rn(s, dist));          // exp(-relu(sigma)*dists)
+  e = __expf(-__fmul_rn(s, dist));        // exp(-relu(sigma)*dists); MUFU.EX2 path: <= 2 ulp + 1 ulp of the argument
+                                          // scaling, far inside the 1e-5 check-mode tolerance and 5x fewer instructions
   alpha = __fsub_rn(1.f, e);
   u = __fadd_rn(__fsub_rn(1.f, alpha), 1e-10f);
 }
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+__device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + __expf(-x)); }
 
 // All loads of a ray are issued before any arithmetic (NC = compile-time number of 32-sample chunks, registers
 // hold the whole ray: 6 x (float4 + z + noise) for S = 192), so every warp keeps ~5 KB in flight instead of
@@ -162,8 +163,8 @@ __device__ __forceinline__ void load_ray(const float4* __restrict__ raw4, const 
   for (int c = 0; c < NC; ++c) {
     int i = c * 32 + lane;
     bool valid = i < S;
-    q[c] = valid ? __ldcs(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);      // streamed once: evict-first
-    zi[c] = valid ? __ldcs(zr + i) : 0.f;
+    q[c] = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    zi[c] = valid ? __ldg(zr + i) : 0.f;
     nz[c] = (valid && nr) ? __ldg(nr + i) : 0.f;
   }
 }

@@ -55,6 +55,25 @@ class NetworkQuery:
             raise ValueError("precision must be 'tc' or 'fp32'")
 
     def __call__(self, inputs, viewdirs, network_fn):
+        """Reference signature (nerf/run.py:248).  Also accepts the 2-D point lists of the mesh tools
+        (nerf/load_model.py:56-74, nerf/extract_mesh.py:176: positions [M,3], viewdirs [M,3])."""
+        if viewdirs is not None and inputs.is_cuda and self.uses_tc(network_fn, True):
+            # fused kernel in explicit-points mode: one "ray" per row of viewdirs, S points each
+            squeeze = inputs.dim() == 2
+            pts3 = inputs[:, None] if squeeze else inputs
+            n, s_ = pts3.shape[0], pts3.shape[1]
+            vd = viewdirs.reshape(n, 3).float().contiguous()
+            params = network_fn.param_list()
+            training = torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in params))
+            out = tc.TcOccPointsFn.apply(network_fn, vd, pts3.reshape(-1, 3).float(), s_, 0, 0.0, training, *params)
+            return out.reshape(n, 4) if squeeze else out
+        if inputs.dim() == 2:                                  # load_model.py:57-58
+            inputs = inputs[:, None]
+            if viewdirs is not None and viewdirs.dim() == 3:
+                viewdirs = viewdirs[:, 0]
+            out = run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn,
+                              embeddirs_fn=self.embeddirs_fn, netchunk=self.netchunk)
+            return out
         return run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn,
                            embeddirs_fn=self.embeddirs_fn, netchunk=self.netchunk)
 

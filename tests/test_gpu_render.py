@@ -493,3 +493,80 @@ def test_dnerf_tc_given_identical_samples(golden, tmp_path, tval):
                     for n, _ in model.named_parameters()])
     assert torch.isfinite(gg).all()
     assert rel_l2(gg, gr) < 3e-2, rel_l2(gg, gr)
+
+
+# ---------------------------------------------------------------- more parity cases for the fused path
+@needs_tc
+def test_point_query_callers_2d_and_3d():
+    """network_query_fn(positions, viewdirs, net) as the mesh tools call it (2-D point lists,
+    nerf/extract_mesh.py:176) and as render_rays calls it (3-D), on the fused kernel's explicit-points mode."""
+    pc, pf, mc, mf, q_tc = make_vanilla(21, 55, "tc")
+    q_32 = S.NetworkQuery(q_tc.embed_fn, q_tc.embeddirs_fn, 4096, precision="fp32")
+    g = torch.Generator(device=DEV).manual_seed(3)
+    pts = (torch.rand(1000, 3, device=DEV, generator=g) - 0.5) * 6
+    vd = torch.nn.functional.normalize(torch.randn(1000, 3, device=DEV, generator=g), dim=-1)
+    with torch.no_grad():
+        a, b = q_tc(pts, vd, mf), q_32(pts, vd, mf)
+        assert a.shape == (1000, 4) and b.shape[-1] == 4
+        assert rel_l2(a, b.reshape(1000, 4)) < 2e-3
+        p3 = pts.reshape(50, 20, 3)
+        a3, b3 = q_tc(p3, vd[:50], mf), q_32(p3, vd[:50], mf)
+        assert a3.shape == (50, 20, 4) and rel_l2(a3, b3) < 2e-3
+    # gradient with respect to the query positions (e.g. surface normals from d sigma / d x)
+    pg = pts[:256].clone().requires_grad_()
+    (q_tc(pg, vd[:256], mf)[:, 3]).sum().backward()
+    pr = pts[:256].clone().requires_grad_()
+    x = torch.cat([ops.embed(pr, 10), ops.embed(vd[:256], 4)], -1)
+    (mf(x)[:, 3]).sum().backward()
+    assert rel_l2(pg.grad, pr.grad) < 5e-2, rel_l2(pg.grad, pr.grad)
+
+
+@needs_tc_bwd
+@pytest.mark.parametrize("opts", [dict(lindisp=True), dict(N_importance=0), dict(white_bkgd=False),
+                                  dict(raw_noise_std=1.0, perturb=1.0), dict(N_samples=32, N_importance=64),
+                                  dict(N_samples=128, N_importance=256)])
+def test_render_rays_tc_option_matrix(opts):
+    """render_rays options of the reference configs on the fused path vs the fp32 check path (same kernels for
+    everything but the MLP; same torch generator state): coarse maps <= 1e-3, fine maps <= 2e-2 (resampling)."""
+    N = 96
+    rays = T(O.blender_rays(N, 120))
+    tgt = T(np.random.RandomState(121).uniform(0, 1, (N, 3)).astype(np.float32))
+    base = dict(N_samples=64, N_importance=128, perturb=0., white_bkgd=True, raw_noise_std=0., lindisp=False)
+    base.update(opts)
+    res = {}
+    for prec in ("fp32", "tc"):
+        pc, pf, mc, mf, q = make_vanilla(21, 55, prec)
+        torch.manual_seed(7)
+        ret = S.render_rays(rays, mc, q, base["N_samples"], retraw=True, lindisp=base["lindisp"], perturb=base["perturb"],
+                            N_importance=base["N_importance"], network_fine=mf, white_bkgd=base["white_bkgd"],
+                            raw_noise_std=base["raw_noise_std"])
+        loss = ((ret["rgb_map"] - tgt) ** 2).mean() + (((ret["rgb0"] - tgt) ** 2).mean() if "rgb0" in ret else 0.)
+        loss.backward()
+        res[prec] = (ret, torch.cat([p.grad.reshape(-1) for p in mc.param_list()]))
+    a, b = res["tc"][0], res["fp32"][0]
+    assert set(a.keys()) == set(b.keys())
+    coarse = "rgb0" if "rgb0" in a else "rgb_map"
+    assert relmax(a[coarse], b[coarse]) < 1e-3
+    assert rel_l2(a["rgb_map"], b["rgb_map"]) < 2e-2
+    assert a["raw"].shape == b["raw"].shape
+    assert torch.isfinite(res["tc"][1]).all() and rel_l2(res["tc"][1], res["fp32"][1]) < 5e-2
+
+
+@needs_tc
+def test_render_full_frame_chunked_tc_vs_fp32():
+    """render() full-frame path with a chunk size that leaves a ragged last chunk (nerf/run.py:90-102)."""
+    H, W = 20, 22
+    focal = 0.5 * W / np.tan(0.5 * 0.6911112)
+    K = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], dtype=np.float32)
+    c2w = torch.from_numpy(O.pose_spherical(10.0, -30.0, 4.0)[:3, :4])
+    out = {}
+    for prec in ("fp32", "tc"):
+        pc, pf, mc, mf, q = make_vanilla(21, 55, prec)
+        kw = dict(network_fn=mc, network_query_fn=q, N_samples=64, N_importance=128, network_fine=mf, white_bkgd=True)
+        with torch.no_grad():
+            rgb, disp, acc, extras = S.render(H, W, K, chunk=150, c2w=c2w, ndc=False, near=2., far=6.,
+                                              use_viewdirs=True, **kw)
+        assert rgb.shape == (H, W, 3) and extras["rgb0"].shape == (H, W, 3)
+        out[prec] = (rgb, extras["rgb0"])
+    assert relmax(out["tc"][1], out["fp32"][1]) < 1e-3
+    assert rel_l2(out["tc"][0], out["fp32"][0]) < 2e-2

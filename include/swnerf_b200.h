@@ -183,6 +183,16 @@ int swnerf_tc_last_bwd_ms(float* data_ms, float* weight_ms);
 int swnerf_tc_selftest(int mode, const float* A, const float* B, float* D, int N, int K, void* scratch,
                        void* stream);
 
+/* Tensor-pipe issue-rate probe (tools only): one CTA per SM issues 4*iters back-to-back 128 x N x 16 MMAs;
+ * cycles_per_mma[sm_count] receives SM clock cycles per MMA.  variant 0: A from shared memory, 1: A from TMEM. */
+int swnerf_tc_probe(int variant, int N, int iters, float* cycles_per_mma, void* stream);
+
+/* CTA-pair (cta_group::2) self-test and rate probe (tests / tools only): D[256,N] = A[256,K] . B[N,K]^T on a cluster
+ * of two CTAs, M = 256 MMAs issued by the leader.  iters > 1 repeats the K loop; n_pairs clusters run the same problem;
+ * cycles_per_mma[n_pairs] (optional) receives SM cycles per MMA.  D is written by pair 0 (may be NULL). */
+int swnerf_tc_selftest_pair(const float* A, const float* B, float* D, int N, int K, int iters, int n_pairs,
+                            float* cycles_per_mma, void* scratch, void* stream);
+
 /* Number of kernels the library has launched in this process since the last reset (bench.py's
  * gpu_launches). */
 int64_t swnerf_launch_count(int reset);

@@ -15,6 +15,8 @@
 // model.py:46); feature_linear is folded into views_linears at pack time (no nonlinearity between them,
 // model.py:50-55) and alpha_linear rides along as row 128 of that N=144 head; rgb_linear (3 x 128) is
 // evaluated in fp32 in the head epilogue.  Algorithmic work: 593,408 MAC per sample.
+#include <mutex>
+#include <cstdlib>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_tc_layout.cuh"
@@ -121,6 +123,7 @@ struct FwdArgs {
   const uint8_t* packed; float* raw;          // kind 0: raw[P,4];  kind 1: dx[P,3]
   uint8_t* ws; int64_t num_tiles;
   int kind;
+  int ko;                                     // experiment knock-outs (tools only; 0 in production)
 };
 
 __device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
@@ -237,6 +240,7 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
     const uint32_t idesc144 = umma_idesc_f16(128, HEAD_N, 0, 0);
     const uint32_t act_u32 = smem_u32(s_act), pe_u32 = smem_u32(s_pe), vw_u32 = smem_u32(s_vw), ring_u32 = smem_u32(s_ring);
     uint32_t cnt = 0, dcnt = 0, alayer = 0, it = 0;
+    uint32_t spacer = lane;
     for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       for (int li = 0; li < 9; ++li, ++dcnt) {
         const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
@@ -260,9 +264,18 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
           const uint32_t b_base = ring_u32 + stage * CHUNK_B;
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
+            for (int ks = 0; ks < 4; ++ks) {
               umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
                        (ci > 0 || ks > 0) ? 1u : 0u);
+              if (g.ko & 64) {      // experiment: space the MMA issues with a dependent integer chain
+#pragma unroll
+                for (int i = 0; i < 16; ++i) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(spacer) : "r"(idesc));
+              }
+              if (g.ko & 128) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(spacer) : "r"(idesc));
+              }
+            }
             umma_commit(&w_empty[stage]);
             if (aj < 0 && li == 5) umma_commit(pe_empty);
             if (aj < 0 && li == 8) umma_commit(vw_empty);
@@ -274,6 +287,7 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
         if (li >= 1) ++alayer;
       }
     }
+    if (spacer == 0xdeadbeefu) g.raw[0] = 0.f;     // keeps the experiment's chain alive
   } else if (warp < 8) {
     // ===================== epilogue: TMEM -> bias/ReLU -> fp16 activation image =====================
     const int q = warp & 3, hh = warp >> 2;
@@ -490,6 +504,405 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
+
+// ======================================================================================================
+// Forward kernel on CTA pairs (cta_group::2), two tile slots per CTA.
+//
+// Two CTAs of a cluster (two SMs of one TPC) each own TWO 128-sample tiles (slots X, Y).  The leader CTA issues
+// M=256 MMAs that take 128 rows of A from each CTA's shared memory and HALF of the weight rows from each CTA's ring,
+// so every SM streams half the weight bytes and its tensor pipe runs at the full 128x256x16-per-128-cycles rate (one
+// CTA feeding both operands from its own shared memory tops out at 161 cycles, tools/probe_mma.py).  Layers of the
+// two slots alternate (X.l, Y.l, X.l+1, ...): while the pipe runs one slot's layer, the epilogue warps drain the
+// other slot's accumulator and write its next input in place, so the ~1000-cycle hand-off chain (commit -> barrier
+// -> tcgen05.ld -> bias/ReLU/fp16 -> st.shared -> fence -> barrier -> issue) is off the tensor pipe's critical path.
+// Barriers that gate MMA issue live in the leader CTA and collect arrivals from both CTAs (cluster-scope arrive);
+// completion (tcgen05.commit) is multicast to the same barrier offset in both CTAs.
+// Shared memory per CTA: 2 x 64 KB activation images, 2 x 16 KB encoding images (PE until the skip layer has read
+// it, then the view encoding for the head), 3 x 16 KB weight ring.
+template <bool TRAIN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_kernel(FwdArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_act = smem + S4_ACT;          // [2 slots][4 blocks]
+  uint8_t* s_enc = smem + S4_ENC;          // [2 slots]
+  uint8_t* s_ring = smem + S4_RING;
+  float* s_f32 = reinterpret_cast<float*>(smem + S4_F32);
+  float4* s_scr = reinterpret_cast<float4*>(smem + S4_SCR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
+  uint64_t* w_full = bars;                 // [3] local: this CTA's half of the stage has landed
+  uint64_t* w_peer = bars + 3;             // [3] leader: the peer's half has landed
+  uint64_t* w_empty = bars + 6;            // [3] multicast: the MMAs reading the stage are complete
+  uint64_t* e_full = bars + 9;             // [2] leader, 8 arrivals: encoding image of slot t written (PE, then views)
+  uint64_t* e_free = bars + 11;            // [2] multicast: its readers are complete (after the skip layer, after the head)
+  uint64_t* act_full = bars + 13;          // [2] leader, 16 arrivals: slot t's layer output written in both CTAs
+  uint64_t* head_done = bars + 15;         // [2] leader, 16 arrivals: slot t's head accumulator has been read
+  uint64_t* d_full = bars + 17;            // [2] multicast: slot t's accumulator complete
+  uint64_t* img_ready = bars + 19;         // [2] local, training: slot t's image written (store warp)
+  uint64_t* st_done = bars + 21;           // [2] local, training: the image's bulk store has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t num_quads = (g.num_tiles + 3) >> 2;          // a pair iteration covers 4 tiles: tile = 4 q + 2 slot + rank
+  const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_peer[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&e_full[t], 8); mbar_init(&e_free[t], 1);
+      mbar_init(&head_done[t], 16); mbar_init(&d_full[t], 1);
+      mbar_init(&act_full[t], 16); mbar_init(&img_ready[t], 8); mbar_init(&st_done[t], 1);
+    }
+    mbar_fence_init();
+  }
+  {
+    const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF);
+    for (int i = threadIdx.x; i < F32_COUNT; i += blockDim.x) s_f32[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  cluster_sync_all();                      // both CTAs' barriers are initialised before anyone signals the other
+  if (warp == 14) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  // cluster addresses (in the leader) of the barriers both CTAs signal
+  const uint32_t e_full_l = mapa_u32(smem_u32(e_full), 0), act_full_l = mapa_u32(smem_u32(act_full), 0);
+  const uint32_t head_done_l = mapa_u32(smem_u32(head_done), 0);
+
+  //   0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2) | 8-11 PE | 12 producer | 13 MMA (leader) |
+  //   14 TMEM alloc, then weight relay (peer) | 15 store (training)
+  if (warp == 12) {
+    // ===================== weight producer: this CTA's half of every chunk, once per slot =====================
+    if (lane == 0 && !(g.ko & 32)) {
+      uint32_t cnt = 0;
+      for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+        int cbase = 0;
+        for (int li = 0; li < 9; ++li) {
+          const int nch = (li == 0) ? 1 : ((li == 5 || li == 8) ? 5 : 4);
+          const uint32_t bytes = (li == 8) ? HCHUNK_B / 2 : CHUNK_B / 2;           // 72 or 128 weight rows
+          for (int t = 0; t < 2; ++t)
+            for (int ci = 0; ci < nch; ++ci, ++cnt) {
+              const uint32_t stage = cnt % NST4, ph = (cnt / NST4) & 1;
+              mbar_wait(&w_empty[stage], ph ^ 1);
+              mbar_expect_tx(&w_full[stage], bytes);
+              bulk_g2s(s_ring + stage * STG4_B, g.packed + chunk_off(cbase + ci) + rank * bytes, bytes, &w_full[stage]);
+            }
+          cbase += nch;
+        }
+      }
+    }
+  } else if (warp == 14 && !leader) {
+    // ===================== weight relay (peer): tell the leader when this CTA's half of a stage has landed =====================
+    if (lane == 0 && !(g.ko & 32)) {
+      const uint32_t w_peer_l = mapa_u32(smem_u32(w_peer), 0);
+      uint32_t cnt = 0;
+      for (int64_t quad = quad0; quad < num_quads; quad += quad_step)
+        for (int c = 0; c < 2 * N_CHUNKS; ++c, ++cnt) {
+          const uint32_t stage = cnt % NST4;
+          mbar_wait(&w_full[stage], (cnt / NST4) & 1);
+          mbar_arrive_remote(w_peer_l + stage * 8);
+        }
+    }
+  } else if (warp == 13 && leader) {
+    // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
+    const uint32_t idesc256 = umma_idesc_f16(256, 256, 0, 0);
+    const uint32_t idesc144 = umma_idesc_f16(256, HEAD_N, 0, 0);
+    const uint32_t act_u32 = smem_u32(s_act), enc_u32 = smem_u32(s_enc), ring_u32 = smem_u32(s_ring);
+    uint32_t cnt = 0, it = 0;
+    for (int64_t quad = quad0; quad < num_quads; quad += quad_step, ++it) {
+      for (int li = 0; li < 9; ++li) {
+        const bool head = (li == 8);
+        const int nch = (li == 0) ? 1 : ((li == 5 || head) ? 5 : 4);
+        const uint32_t idesc = head ? idesc144 : idesc256;
+        for (int t = 0; t < 2; ++t) {
+          const uint32_t d_tmem = tmem + t * 256;
+          // the slot's accumulator must have been drained and (li >= 1) its input written: the epilogue of the slot's
+          // previous layer ran while the pipe worked on the other slot
+          if (li == 0) {
+            if (it > 0) mbar_wait_cluster(&head_done[t], (it - 1) & 1);
+            mbar_wait_cluster(&e_full[t], 0);                 // PE image (phase 2 it)
+          } else {
+            mbar_wait_cluster(&act_full[t], (li - 1) & 1);
+            if (head) mbar_wait_cluster(&e_full[t], 1);       // view encoding (phase 2 it + 1)
+          }
+          for (int ci = 0; ci < nch; ++ci) {
+            int aj = (li == 5 || head) ? ci - 1 : ci;       // activation block index, -1 = encoding image
+            if (li == 0) aj = -1;
+            const uint32_t a_base = aj < 0 ? enc_u32 + t * ACT_BLK : act_u32 + t * ACT_BYTES + aj * ACT_BLK;
+            const uint32_t stage = cnt % NST4, wph = (cnt / NST4) & 1;
+            if (!(g.ko & 32)) {
+              mbar_wait(&w_full[stage], wph);
+              mbar_wait_cluster(&w_peer[stage], wph);
+            }
+            tc_fence_after();
+            const uint32_t b_base = ring_u32 + stage * STG4_B;
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_f16_pair(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
+                              (ci > 0 || ks > 0) ? 1u : 0u);
+              umma_commit_pair(&w_empty[stage], 3);
+              if (aj < 0 && li >= 5) umma_commit_pair(&e_free[t], 3);
+              if (ci == nch - 1) umma_commit_pair(&d_full[t], 3);
+            }
+            __syncwarp();
+            ++cnt;
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== epilogue: accumulator -> bias/ReLU -> fp16 -> the slot's activation image (in place) =====================
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t dcnt = 0;                       // d_full[t] completes once per layer: both slots advance together
+    uint32_t wcnt = 0;                       // training: writes issued so far to every block of a slot (same for all)
+    for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+      for (int li = 0; li < 9; ++li, ++dcnt) {
+#pragma unroll 1
+        for (int t = 0; t < 2; ++t) {
+          const int64_t tile = quad * 4 + t * 2 + rank;
+          const bool tvalid = tile < g.num_tiles;
+          uint32_t* ws_mask = (TRAIN && tvalid)
+              ? reinterpret_cast<uint32_t*>(g.ws + g.num_tiles * WS_TILE_BYTES) + tile * (9 * 8 * 128) : nullptr;
+          const uint32_t acc = tmem + lane_addr + t * 256;
+          uint8_t* img = s_act + t * ACT_BYTES;
+          mbar_wait(&d_full[t], dcnt & 1);
+          tc_fence_after();
+          if (li < 8 && (g.ko & 16)) {     // experiment: synchronisation only
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(act_full_l + t * 8);
+          } else if (li < 8) {
+            const float* bias = s_f32 + li * 256 + hh * 32;
+            // software pipeline over the four 64-column blocks: the TMEM load of block j+1 is in flight while
+            // block j is converted and handed to the MMA thread
+            if (TRAIN && wcnt > 0) mbar_wait(&st_done[t], (wcnt - 1) & 1);   // the image's bulk store still reads it
+            uint32_t va[32], vb[32];
+            if (!(g.ko & 128)) tmem_ld32(acc + hh * 32, va);
+            else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) va[i] = vb[i] = i;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint32_t (&v)[32] = (j & 1) ? vb : va;
+              uint32_t (&vn)[32] = (j & 1) ? va : vb;
+              if (!(g.ko & 128)) {
+                tmem_ld_wait_on(v);
+                if (j < 3) tmem_ld32(acc + (j + 1) * 64 + hh * 32, vn);
+              }
+              uint32_t pk[16];
+              uint32_t mask = 0;
+              const float4* b4 = reinterpret_cast<const float4*>(bias + j * 64);
+#pragma unroll
+              for (int i4 = 0; i4 < 8; ++i4) {
+                const float4 bb = b4[i4];                         // broadcast LDS.128
+                float a0 = __uint_as_float(v[4 * i4]) + bb.x, a1 = __uint_as_float(v[4 * i4 + 1]) + bb.y;
+                float a2 = __uint_as_float(v[4 * i4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * i4 + 3]) + bb.w;
+                if (TRAIN)
+                  mask |= (a0 > 0.f ? 1u : 0u) << (4 * i4) | (a1 > 0.f ? 1u : 0u) << (4 * i4 + 1) |
+                          (a2 > 0.f ? 1u : 0u) << (4 * i4 + 2) | (a3 > 0.f ? 1u : 0u) << (4 * i4 + 3);
+                pk[2 * i4] = pack_half2_relu(a0, a1);
+                pk[2 * i4 + 1] = pack_half2_relu(a2, a3);
+              }
+              uint8_t* blk = img + j * ACT_BLK;
+              if (!(g.ko & 64) || pk[3] == 0x12345u)
+#pragma unroll
+              for (int u = 0; u < 4; ++u)
+                *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
+                    make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+              if (TRAIN && tvalid) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = mask;
+            }
+            // one proxy fence and one arrival for the whole layer output: the next layer of this slot is issued after
+            // the other slot's layer anyway, and the fence is the expensive part of the hand-off
+            fence_async_smem();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+              mbar_arrive_remote(act_full_l + t * 8);
+              if (TRAIN) mbar_arrive(&img_ready[t]);
+            }
+          } else {
+            // head: cols 0..127 = relu -> h9, col 128 = sigma; rgb = W_rgb h9 + b_rgb in fp32
+            const float* bh = s_f32 + F32_BHEAD;
+            const float* wr = s_f32 + F32_WRGB;
+            float pr = 0.f, pg = 0.f, pb = 0.f;
+            // training: h9 goes into blocks 0 / 1 of the slot (this thread writes block hh); blocks 2,3 are not
+            // rewritten by the head, so their store counters advance without a store (see the store warp)
+            if (TRAIN && wcnt > 0) mbar_wait(&st_done[t], (wcnt - 1) & 1);
+            uint32_t vs[32];
+            if (hh == 1) tmem_ld32(acc + 128, vs);
+#pragma unroll 1
+            for (int jj = 0; jj < 2; ++jj) {
+              uint32_t v[32];
+              const int c0 = hh * 64 + jj * 32;
+              tmem_ld32(acc + c0, v);
+              tmem_ld_wait();
+              uint32_t hk[16];
+              uint32_t mask = 0;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                float a = fmaxf(__uint_as_float(v[2 * i]) + bh[c0 + 2 * i], 0.f);
+                float b = fmaxf(__uint_as_float(v[2 * i + 1]) + bh[c0 + 2 * i + 1], 0.f);
+                pr = fmaf(wr[c0 + 2 * i], a, pr); pr = fmaf(wr[c0 + 2 * i + 1], b, pr);
+                pg = fmaf(wr[128 + c0 + 2 * i], a, pg); pg = fmaf(wr[128 + c0 + 2 * i + 1], b, pg);
+                pb = fmaf(wr[256 + c0 + 2 * i], a, pb); pb = fmaf(wr[256 + c0 + 2 * i + 1], b, pb);
+                if (TRAIN) {
+                  mask |= (a > 0.f ? 1u : 0u) << (2 * i) | (b > 0.f ? 1u : 0u) << (2 * i + 1);
+                  hk[i] = pack_half2(a, b);
+                }
+              }
+              if (TRAIN) {
+                uint8_t* blk = img + hh * ACT_BLK;
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  *reinterpret_cast<uint4*>(blk + tile_unit_off(row, jj * 4 + u)) =
+                      make_uint4(hk[4 * u], hk[4 * u + 1], hk[4 * u + 2], hk[4 * u + 3]);
+                if (tvalid) ws_mask[(8 * 8 + hh * 2 + jj) * 128 + row] = mask;
+              }
+            }
+            // every accumulator read of this slot's tile is complete (the first tcgen05.wait::ld covered `vs`)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(head_done_l + t * 8);
+            const int64_t idx = tile * TILE + row;
+            if (hh == 1) {
+              if (g.kind == 1 && idx < g.P) {       // deformation net: dx = rows 128..130 of the head (model.py:136)
+                g.raw[idx * 3 + 0] = __uint_as_float(vs[0]) + bh[128];
+                g.raw[idx * 3 + 1] = __uint_as_float(vs[1]) + bh[129];
+                g.raw[idx * 3 + 2] = __uint_as_float(vs[2]) + bh[130];
+              }
+              s_scr[row] = make_float4(pr, pg, pb, __uint_as_float(vs[0]) + bh[128]);
+            }
+            if (TRAIN) {
+              fence_async_smem();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&img_ready[t]);
+            }
+            named_bar_sync(1, 256);
+            if (hh == 0 && g.kind == 0) {
+              float4 o = s_scr[row];
+              const float* br = s_f32 + F32_BRGB;
+              if (idx < g.P)
+                reinterpret_cast<float4*>(g.raw)[idx] = make_float4(pr + o.x + br[0], pg + o.y + br[1], pb + o.z + br[2], o.w);
+            }
+            named_bar_sync(1, 256);       // s_scr is rewritten by the other slot's head right away
+          }
+        }
+        if (TRAIN) ++wcnt;                 // both slots' images have had one more write this layer
+      }
+    }
+  } else if (warp < 12) {
+    // ===================== points + positional encoding, both slots =====================
+    const int p = (warp - 8) * 32 + lane;
+    const bool p0 = (p == 0);
+    uint32_t it = 0;
+    for (int64_t quad = quad0; quad < num_quads; quad += quad_step, ++it) {
+      float dirs[2][3];
+      // PE images first (both slots need them at layer 0), the view encodings after the skip layer released the images
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = quad * 4 + t * 2 + rank;
+        int64_t idx = tile * TILE + p;
+        bool valid = idx < g.P;
+        float pos[3] = {0.f, 0.f, 0.f};
+        dirs[t][0] = dirs[t][1] = dirs[t][2] = 0.f;
+        if (valid) {
+          int64_t r = idx / g.S;
+          const float* ray = g.rays + r * g.ray_stride;
+          float zz = g.pts ? 0.f : __ldg(g.z + idx);
+#pragma unroll
+          for (int j = 0; j < 3; ++j) {
+            pos[j] = g.pts ? __ldg(g.pts + idx * 3 + j)
+                           : __fadd_rn(__ldg(ray + j), __fmul_rn(__ldg(ray + 3 + j), zz));      // run.py:385
+            dirs[t][j] = __ldg(ray + g.view_col + j);
+          }
+        }
+        float f[64];
+        encode3<10, 64>(pos, f);
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) f[i] = 0.f;
+        }
+        if (it > 0) mbar_wait(&e_free[t], 1);          // the previous tile's head has read the view encoding
+        if (TRAIN && (it > 0 || t > 0)) {
+          if (p0) bulk_wait_read0();
+          named_bar_sync(2, 128);
+        }
+        store_row64(s_enc + t * ACT_BLK, p, f);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(e_full_l + t * 8);
+        if (TRAIN) {
+          named_bar_sync(2, 128);
+          if (p0) {
+            if (tile < g.num_tiles) bulk_s2g(g.ws + tile * WS_TILE_BYTES + WS_PE_OFF, s_enc + t * ACT_BLK, ACT_BLK);
+            bulk_commit();
+          }
+        }
+      }
+      for (int t = 0; t < 2; ++t) {
+        const int64_t tile = quad * 4 + t * 2 + rank;
+        const bool valid = tile * TILE + p < g.P;
+        float f[64];
+        encode3<4, 64>(dirs[t], f);
+        if (!valid) {
+#pragma unroll
+          for (int i = 0; i < 64; ++i) f[i] = 0.f;
+        }
+        mbar_wait(&e_free[t], 0);                      // the skip layer has read the PE image
+        if (TRAIN) {
+          if (p0) bulk_wait_read0();
+          named_bar_sync(2, 128);
+        }
+        store_row64(s_enc + t * ACT_BLK, p, f);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_remote(e_full_l + t * 8);
+        if (TRAIN) {
+          named_bar_sync(2, 128);
+          if (p0) {
+            if (tile < g.num_tiles) bulk_s2g(g.ws + tile * WS_TILE_BYTES + WS_VW_OFF, s_enc + t * ACT_BLK, ACT_BLK);
+            bulk_commit();
+          }
+        }
+      }
+    }
+    if (TRAIN && p0) bulk_wait_all0();
+  } else if (TRAIN && warp == 15) {
+    // ===================== activation store warp (training) =====================
+    if (lane == 0) {
+      uint32_t rc = 0;
+      for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+        for (int li = 0; li < 9; ++li, ++rc) {
+          for (int t = 0; t < 2; ++t) {
+            const int64_t tile = quad * 4 + t * 2 + rank;
+            uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
+            uint8_t* img = s_act + t * ACT_BYTES;
+            mbar_wait(&img_ready[t], rc & 1);
+            if (tile < g.num_tiles) {
+              if (li < 8) bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES, img, ACT_BYTES);
+              else bulk_s2g(ws_tile + WS_H9_OFF, img, 2 * ACT_BLK);          // h9 in blocks 0,1
+            }
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(&st_done[t]);
+          }
+        }
+      }
+      bulk_wait_all0();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                      // the peer may still be using this CTA's barriers / the pair's tensor memory
+  if (warp == 14) tmem_dealloc_pair<512>(tmem);
+}
+
 }  // namespace swnerf
 
 using namespace swnerf;
@@ -549,8 +962,22 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   g.rays = rays; g.ray_stride = ray_stride; g.view_col = view_col; g.z = z_vals; g.S = n_samples;
   g.P = n_rays * n_samples; g.pts = pts; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = out;
   g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE; g.kind = kind;
+  { static const char* ko = getenv("SWNERF_KO"); g.ko = ko ? atoi(ko) : 0; }
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
+  static const bool use_v1 = getenv("SWNERF_FWD_V1") != nullptr;
+  if (!use_v1) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+      cudaFuncSetAttribute(mlp_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+    });
+    const int64_t num_quads = (g.num_tiles + 3) / 4;
+    const int grid4 = 2 * (int)(num_quads < sm_count() / 2 ? num_quads : sm_count() / 2);
+    if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g);
+    else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g);
+    return check_launch("tc_mlp_fwd");
+  }
   if (training) {
     static thread_local bool attr_t = false;
     if (!attr_t) { cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL); attr_t = true; }

@@ -31,7 +31,19 @@ constexpr int PK_F32_OFF = PK_CHUNK_BYTES;
 constexpr int PK_FOLD_OFF = PK_F32_OFF + ((F32_COUNT * 4 + 255) / 256) * 256; // fold scratch [128][257] fp32
 constexpr int PK_TOTAL_BYTES = PK_FOLD_OFF + 128 * 257 * 4;
 
-// ---- shared memory of the forward kernel (offsets from a 1024-aligned base)
+// ---- shared memory of the CTA-pair forward kernel (per CTA; two tile slots; offsets from a 1024-aligned base)
+constexpr int NST4 = 3;                   // weight ring depth; a stage holds this CTA's half of one chunk
+constexpr int STG4_B = CHUNK_B / 2;       // [128 x 64] fp16 (head chunks use 72 rows of it)
+constexpr int S4_ACT = 0;                                 // [2 slots] activation images [128 x 256] fp16, in place
+constexpr int S4_ENC = S4_ACT + 2 * ACT_BYTES;            // [2 slots] encoding image: PE (layers 0, 5), then the view encoding (head)
+constexpr int S4_RING = S4_ENC + 2 * ACT_BLK;
+constexpr int S4_F32 = S4_RING + NST4 * STG4_B;
+constexpr int S4_SCR = S4_F32 + ((F32_COUNT * 4 + 127) / 128) * 128;
+constexpr int S4_BAR = S4_SCR + TILE * 16;
+constexpr int S4_TOTAL = S4_BAR + 512 + 1024;                                 // + alignment slack
+static_assert(S4_TOTAL <= 232448, "shared memory budget");
+
+// ---- shared memory of the forward kernel v1 (offsets from a 1024-aligned base)
 constexpr int SM_ACT = 0;
 constexpr int SM_PE = SM_ACT + ACT_BYTES;
 constexpr int SM_VW = SM_PE + ACT_BLK;

@@ -28,6 +28,18 @@ def test_umma_kmajor(N, K):
     assert err < 1e-5, err                                       # fp32 accumulation only
 
 
+@pytest.mark.parametrize("N,K", [(128, 64), (128, 256), (144, 256), (256, 128)])
+def test_umma_a_from_tmem(N, K):
+    """A operand written to tensor memory with tcgen05.st (two fp16 per 32-bit column) and consumed from there."""
+    g = torch.Generator(device="cuda").manual_seed(N + K + 1)
+    A = torch.randn(128, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g)
+    D = _run(2, A, B, N, K)
+    ref = A.half().double() @ B.half().double().t()
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err
+
+
 @pytest.mark.parametrize("N", [256, 128, 64, 16])
 def test_umma_mnmajor(N):
     g = torch.Generator(device="cuda").manual_seed(N)
@@ -35,5 +47,20 @@ def test_umma_mnmajor(N):
     Q = torch.randn(128, N, device="cuda", generator=g)
     D = _run(1, P, Q, N, 128)
     ref = P.half().double().t() @ Q.half().double()
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 256), (128, 128)])
+def test_umma_cta_pair(N, K):
+    """cta_group::2: M = 256 across a cluster of two CTAs, each CTA holding half of B."""
+    g = torch.Generator(device="cuda").manual_seed(N + K + 2)
+    A = torch.randn(256, K, device="cuda", generator=g)
+    B = torch.randn(N, K, device="cuda", generator=g)
+    D = torch.empty((256, N), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(1024 * 1024, dtype=torch.uint8, device="cuda")
+    call("swnerf_tc_selftest_pair", A.data_ptr(), B.data_ptr(), D.data_ptr(), N, K, 1, 1, None, scratch.data_ptr(), stream())
+    torch.cuda.synchronize()
+    ref = A.half().double() @ B.half().double().t()
     err = float((D.double() - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, err

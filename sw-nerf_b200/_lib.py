@@ -51,6 +51,7 @@ _SIG = {
     "swnerf_tc_last_bwd_ms": [_VP, _VP],
     "swnerf_tc_selftest": [_I32, _VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "swnerf_tc_probe": [_I32, _I32, _I32, _VP, _VP],
+    "swnerf_tc_set_fwd_variant": [_I32],
     "swnerf_tc_selftest_pair": [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP],
     "swnerf_tc_mlp_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
 }

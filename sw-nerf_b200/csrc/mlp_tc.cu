@@ -15,6 +15,7 @@
 // model.py:46); feature_linear is folded into views_linears at pack time (no nonlinearity between them,
 // model.py:50-55) and alpha_linear rides along as row 128 of that N=144 head; rgb_linear (3 x 128) is
 // evaluated in fp32 in the head epilogue.  Algorithmic work: 593,408 MAC per sample.
+#include <atomic>
 #include <mutex>
 #include <cstdlib>
 #include "common.cuh"
@@ -240,7 +241,6 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
     const uint32_t idesc144 = umma_idesc_f16(128, HEAD_N, 0, 0);
     const uint32_t act_u32 = smem_u32(s_act), pe_u32 = smem_u32(s_pe), vw_u32 = smem_u32(s_vw), ring_u32 = smem_u32(s_ring);
     uint32_t cnt = 0, dcnt = 0, alayer = 0, it = 0;
-    uint32_t spacer = lane;
     for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
       for (int li = 0; li < 9; ++li, ++dcnt) {
         const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
@@ -264,18 +264,9 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
           const uint32_t b_base = ring_u32 + stage * CHUNK_B;
           if (elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks) {
+            for (int ks = 0; ks < 4; ++ks)
               umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
                        (ci > 0 || ks > 0) ? 1u : 0u);
-              if (g.ko & 64) {      // experiment: space the MMA issues with a dependent integer chain
-#pragma unroll
-                for (int i = 0; i < 16; ++i) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(spacer) : "r"(idesc));
-              }
-              if (g.ko & 128) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i) asm volatile("mad.lo.u32 %0, %0, %0, %1;" : "+r"(spacer) : "r"(idesc));
-              }
-            }
             umma_commit(&w_empty[stage]);
             if (aj < 0 && li == 5) umma_commit(pe_empty);
             if (aj < 0 && li == 8) umma_commit(vw_empty);
@@ -287,7 +278,6 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
         if (li >= 1) ++alayer;
       }
     }
-    if (spacer == 0xdeadbeefu) g.raw[0] = 0.f;     // keeps the experiment's chain alive
   } else if (warp < 8) {
     // ===================== epilogue: TMEM -> bias/ReLU -> fp16 activation image =====================
     const int q = warp & 3, hh = warp >> 2;
@@ -529,17 +519,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
   float* s_f32 = reinterpret_cast<float*>(smem + S4_F32);
   float4* s_scr = reinterpret_cast<float4*>(smem + S4_SCR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
-  uint64_t* w_full = bars;                 // [3] local: this CTA's half of the stage has landed
-  uint64_t* w_peer = bars + 3;             // [3] leader: the peer's half has landed
-  uint64_t* w_empty = bars + 6;            // [3] multicast: the MMAs reading the stage are complete
-  uint64_t* e_full = bars + 9;             // [2] leader, 8 arrivals: encoding image of slot t written (PE, then views)
-  uint64_t* e_free = bars + 11;            // [2] multicast: its readers are complete (after the skip layer, after the head)
-  uint64_t* act_full = bars + 13;          // [2] leader, 16 arrivals: slot t's layer output written in both CTAs
-  uint64_t* head_done = bars + 15;         // [2] leader, 16 arrivals: slot t's head accumulator has been read
-  uint64_t* d_full = bars + 17;            // [2] multicast: slot t's accumulator complete
-  uint64_t* img_ready = bars + 19;         // [2] local, training: slot t's image written (store warp)
-  uint64_t* st_done = bars + 21;           // [2] local, training: the image's bulk store has read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 23);
+  uint64_t* w_full = bars;                 // [NST4] local: this CTA's half of the stage has landed
+  uint64_t* w_peer = bars + 4;             // [NST4] leader: the peer's half has landed
+  uint64_t* w_empty = bars + 8;            // [NST4] multicast: the MMAs reading the stage are complete
+  uint64_t* e_full = bars + 12;            // [2] leader, 8 arrivals: encoding image of slot t written (PE, then views)
+  uint64_t* e_free = bars + 14;            // [2] multicast: its readers are complete (after the skip layer, after the head)
+  uint64_t* act_full = bars + 16;          // [2] leader, 16 arrivals: slot t's layer output written in both CTAs
+  uint64_t* head_done = bars + 18;         // [2] leader, 16 arrivals: slot t's head accumulator has been read
+  uint64_t* d_full = bars + 20;            // [2] multicast: slot t's accumulator complete
+  uint64_t* img_ready = bars + 22;         // [2] local, training: slot t's image written (store warp)
+  uint64_t* st_done = bars + 24;           // [2] local, training: the image's bulk store has read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
@@ -586,8 +576,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             for (int ci = 0; ci < nch; ++ci, ++cnt) {
               const uint32_t stage = cnt % NST4, ph = (cnt / NST4) & 1;
               mbar_wait(&w_empty[stage], ph ^ 1);
-              mbar_expect_tx(&w_full[stage], bytes);
-              bulk_g2s(s_ring + stage * STG4_B, g.packed + chunk_off(cbase + ci) + rank * bytes, bytes, &w_full[stage]);
+              const uint32_t nb = (g.ko & 4) ? 1024u : bytes;      // experiment: synchronisation without the bytes
+              mbar_expect_tx(&w_full[stage], nb);
+              bulk_g2s(s_ring + stage * STG4_B, g.packed + chunk_off(cbase + ci) + rank * bytes, nb, &w_full[stage]);
             }
           cbase += nch;
         }
@@ -682,19 +673,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             // block j is converted and handed to the MMA thread
             if (TRAIN && wcnt > 0) mbar_wait(&st_done[t], (wcnt - 1) & 1);   // the image's bulk store still reads it
             uint32_t va[32], vb[32];
-            if (!(g.ko & 128)) tmem_ld32(acc + hh * 32, va);
-            else {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) va[i] = vb[i] = i;
-            }
+            tmem_ld32(acc + hh * 32, va);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               uint32_t (&v)[32] = (j & 1) ? vb : va;
               uint32_t (&vn)[32] = (j & 1) ? va : vb;
-              if (!(g.ko & 128)) {
-                tmem_ld_wait_on(v);
-                if (j < 3) tmem_ld32(acc + (j + 1) * 64 + hh * 32, vn);
-              }
+              tmem_ld_wait_on(v);
+              if (j < 3) tmem_ld32(acc + (j + 1) * 64 + hh * 32, vn);
               uint32_t pk[16];
               uint32_t mask = 0;
               const float4* b4 = reinterpret_cast<const float4*>(bias + j * 64);
@@ -710,7 +695,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
                 pk[2 * i4 + 1] = pack_half2_relu(a2, a3);
               }
               uint8_t* blk = img + j * ACT_BLK;
-              if (!(g.ko & 64) || pk[3] == 0x12345u)
 #pragma unroll
               for (int u = 0; u < 4; ++u)
                 *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
@@ -948,6 +932,9 @@ int swnerf_tc_pack_weights_time(const float* const* params, const float* time_em
   return pack_impl(params, 1, time_embedding_host21, packed, stream);
 }
 
+// 0 = one CTA per tile (production), 1 = CTA pairs with two tile slots (experimental)
+static std::atomic<int> g_fwd_variant{[] { const char* e = getenv("SWNERF_FWD_PAIR"); return e && atoi(e) ? 1 : 0; }()};
+
 static int fwd_impl(const float* rays, int ray_stride, int view_col, const float* z_vals, const float* pts,
                     int64_t n_rays, int n_samples, const void* packed, float* out, void* workspace, int training,
                     int kind, void* stream) {
@@ -965,8 +952,7 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   { static const char* ko = getenv("SWNERF_KO"); g.ko = ko ? atoi(ko) : 0; }
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
-  static const bool use_v1 = getenv("SWNERF_FWD_V1") != nullptr;
-  if (!use_v1) {
+  if (g_fwd_variant.load() == 1) {        // experimental CTA-pair kernel (swnerf_tc_set_fwd_variant)
     static std::once_flag once;
     std::call_once(once, [] {
       cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
@@ -988,6 +974,12 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
     mlp_fwd_kernel<false><<<grid, 512, SM_TOTAL, s>>>(g);
   }
   return check_launch("tc_mlp_fwd");
+}
+
+int swnerf_tc_set_fwd_variant(int variant) {
+  SW_REQUIRE(variant == 0 || variant == 1, "tc_set_fwd_variant: variant must be 0 or 1");
+  g_fwd_variant.store(variant);
+  return SWNERF_OK;
 }
 
 int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,

@@ -570,3 +570,26 @@ def test_render_full_frame_chunked_tc_vs_fp32():
         out[prec] = (rgb, extras["rgb0"])
     assert relmax(out["tc"][1], out["fp32"][1]) < 1e-3
     assert rel_l2(out["tc"][0], out["fp32"][0]) < 2e-2
+
+
+@needs_tc_bwd
+def test_cta_pair_forward_variant_matches_default():
+    """The experimental CTA-pair forward kernel (cta_group::2, two tile slots per CTA) must reproduce the production
+    kernel bit for bit: same fp16 operands, same fp32 accumulation order per output."""
+    from swnerf_b200 import _lib
+    N = 300                                           # 300 x 64 = 150 tiles: ragged quads and a ragged last tile
+    rays = T(O.blender_rays(N, 77))
+    pc, pf, mc, mf, q = make_vanilla(21, 55, "tc")
+    out = {}
+    for variant in (0, 1):
+        _lib.call("swnerf_tc_set_fwd_variant", variant)
+        try:
+            for p in mc.param_list():
+                p.grad = None
+            ret = S.render_rays(rays, mc, q, 64, retraw=True, N_importance=0, white_bkgd=True)
+            ret["rgb_map"].square().mean().backward()
+            out[variant] = (ret["raw"].detach().clone(), torch.cat([p.grad.reshape(-1) for p in mc.param_list()]))
+        finally:
+            _lib.call("swnerf_tc_set_fwd_variant", 0)
+    assert torch.equal(out[0][0], out[1][0])
+    assert rel_l2(out[1][1], out[0][1]) < 1e-5        # wgrad reduces with atomics: order differs run to run

@@ -170,8 +170,9 @@ int swnerf_adam_flat(float* params, const float* grads, float* exp_avg, float* e
 int swnerf_mse2(const float* a, const float* b, const float* target, int64_t n, float scale, float* da, float* db,
                 float* loss, void* stream);
 
-/* Selects the forward kernel: 0 (default) one CTA per 128-sample tile; 1 the experimental CTA-pair kernel
- * (cta_group::2, two tile slots per CTA; same results).  Process-wide. */
+/* Selects the forward kernel (process-wide): -1 (default) automatic - inference runs on CTA pairs (cta_group::2,
+ * two tile slots per CTA), training on one CTA per 128-sample tile, whichever is faster for the mode; 0 / 1 force
+ * one of them.  Both produce bit-identical outputs (tests/test_gpu_render.py). */
 int swnerf_tc_set_fwd_variant(int variant);
 
 /* Per-kernel device timing of the last swnerf_tc_mlp_bwd on this thread (bench.py's roofline): when

@@ -15,6 +15,7 @@
 // model.py:46); feature_linear is folded into views_linears at pack time (no nonlinearity between them,
 // model.py:50-55) and alpha_linear rides along as row 128 of that N=144 head; rgb_linear (3 x 128) is
 // evaluated in fp32 in the head epilogue.  Algorithmic work: 593,408 MAC per sample.
+#include <cuda.h>
 #include <atomic>
 #include <mutex>
 #include <cstdlib>
@@ -510,7 +511,8 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
 // Shared memory per CTA: 2 x 64 KB activation images, 2 x 16 KB encoding images (PE until the skip layer has read
 // it, then the view encoding for the head), 3 x 16 KB weight ring.
 template <bool TRAIN>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_kernel(FwdArgs g) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_kernel(const __grid_constant__ FwdArgs g, const __grid_constant__ CUtensorMap tm_trunk,
+                                                                                   const __grid_constant__ CUtensorMap tm_head) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_act = smem + S4_ACT;          // [2 slots][4 blocks]
@@ -519,8 +521,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
   float* s_f32 = reinterpret_cast<float*>(smem + S4_F32);
   float4* s_scr = reinterpret_cast<float4*>(smem + S4_SCR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
-  uint64_t* w_full = bars;                 // [NST4] local: this CTA's half of the stage has landed
-  uint64_t* w_peer = bars + 4;             // [NST4] leader: the peer's half has landed
+  uint64_t* w_full = bars;                 // [NST4] leader: both CTAs' halves of the stage have landed (tensor-map loads)
   uint64_t* w_empty = bars + 8;            // [NST4] multicast: the MMAs reading the stage are complete
   uint64_t* e_full = bars + 12;            // [2] leader, 8 arrivals: encoding image of slot t written (PE, then views)
   uint64_t* e_free = bars + 14;            // [2] multicast: its readers are complete (after the skip layer, after the head)
@@ -538,7 +539,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
   const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NST4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_peer[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NST4; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     for (int t = 0; t < 2; ++t) {
       mbar_init(&e_full[t], 8); mbar_init(&e_free[t], 1);
       mbar_init(&head_done[t], 16); mbar_init(&d_full[t], 1);
@@ -562,39 +563,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
   const uint32_t head_done_l = mapa_u32(smem_u32(head_done), 0);
 
   //   0-7 epilogue (TMEM lane quarter = warp & 3, column half = warp >> 2) | 8-11 PE | 12 producer | 13 MMA (leader) |
-  //   14 TMEM alloc, then weight relay (peer) | 15 store (training)
+  //   14 TMEM alloc | 15 store (training)
   if (warp == 12) {
     // ===================== weight producer: this CTA's half of every chunk, once per slot =====================
+    // Tensor-map loads with .cta_group::2 report their bytes to the LEADER's barrier, which expects both halves: no
+    // relay hop between the peer's copy landing and the leader issuing.
     if (lane == 0 && !(g.ko & 32)) {
+      const uint32_t w_full_l = mapa_u32(smem_u32(w_full), 0);
       uint32_t cnt = 0;
       for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
-        int cbase = 0;
+        int row = 0;                                   // row of the packed weight image (128 B per row)
         for (int li = 0; li < 9; ++li) {
           const int nch = (li == 0) ? 1 : ((li == 5 || li == 8) ? 5 : 4);
-          const uint32_t bytes = (li == 8) ? HCHUNK_B / 2 : CHUNK_B / 2;           // 72 or 128 weight rows
+          const int rows = (li == 8) ? HEAD_N : 256;
+          const uint32_t bytes = (uint32_t)rows * 64u;                             // this CTA's half: rows / 2 x 128 B
           for (int t = 0; t < 2; ++t)
             for (int ci = 0; ci < nch; ++ci, ++cnt) {
               const uint32_t stage = cnt % NST4, ph = (cnt / NST4) & 1;
               mbar_wait(&w_empty[stage], ph ^ 1);
-              const uint32_t nb = (g.ko & 4) ? 1024u : bytes;      // experiment: synchronisation without the bytes
-              mbar_expect_tx(&w_full[stage], nb);
-              bulk_g2s(s_ring + stage * STG4_B, g.packed + chunk_off(cbase + ci) + rank * bytes, nb, &w_full[stage]);
+              if (leader) mbar_expect_tx(&w_full[stage], 2u * bytes);
+              tma_load_2d_pair(s_ring + stage * STG4_B, li == 8 ? &tm_head : &tm_trunk, 0,
+                               row + ci * rows + (int)rank * (rows / 2), w_full_l + stage * 8);
             }
-          cbase += nch;
+          row += nch * rows;
         }
       }
-    }
-  } else if (warp == 14 && !leader) {
-    // ===================== weight relay (peer): tell the leader when this CTA's half of a stage has landed =====================
-    if (lane == 0 && !(g.ko & 32)) {
-      const uint32_t w_peer_l = mapa_u32(smem_u32(w_peer), 0);
-      uint32_t cnt = 0;
-      for (int64_t quad = quad0; quad < num_quads; quad += quad_step)
-        for (int c = 0; c < 2 * N_CHUNKS; ++c, ++cnt) {
-          const uint32_t stage = cnt % NST4;
-          mbar_wait(&w_full[stage], (cnt / NST4) & 1);
-          mbar_arrive_remote(w_peer_l + stage * 8);
-        }
     }
   } else if (warp == 13 && leader) {
     // ===================== MMA issuer (leader CTA; converged warp, one elected lane issues) =====================
@@ -625,7 +618,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             const uint32_t stage = cnt % NST4, wph = (cnt / NST4) & 1;
             if (!(g.ko & 32)) {
               mbar_wait(&w_full[stage], wph);
-              mbar_wait_cluster(&w_peer[stage], wph);
             }
             tc_fence_after();
             const uint32_t b_base = ring_u32 + stage * STG4_B;
@@ -699,7 +691,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
               for (int u = 0; u < 4; ++u)
                 *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
                     make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-              if (TRAIN && tvalid) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = mask;
+              if (TRAIN && tvalid && !(g.ko & 2)) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = mask;
             }
             // one proxy fence and one arrival for the whole layer output: the next layer of this slot is issued after
             // the other slot's layer anyway, and the fence is the expensive part of the hand-off
@@ -867,7 +859,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
             uint8_t* img = s_act + t * ACT_BYTES;
             mbar_wait(&img_ready[t], rc & 1);
-            if (tile < g.num_tiles) {
+            if (tile < g.num_tiles && !(g.ko & 8)) {
               if (li < 8) bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES, img, ACT_BYTES);
               else bulk_s2g(ws_tile + WS_H9_OFF, img, 2 * ACT_BLK);          // h9 in blocks 0,1
             }
@@ -932,8 +924,37 @@ int swnerf_tc_pack_weights_time(const float* const* params, const float* time_em
   return pack_impl(params, 1, time_embedding_host21, packed, stream);
 }
 
-// 0 = one CTA per tile (production), 1 = CTA pairs with two tile slots (experimental)
-static std::atomic<int> g_fwd_variant{[] { const char* e = getenv("SWNERF_FWD_PAIR"); return e && atoi(e) ? 1 : 0; }()};
+// Tensor maps over the packed weight image seen as rows of 128 bytes: boxes of 128 rows (half a trunk chunk) and 72
+// rows (half a head chunk), copied verbatim (the image is already in the UMMA swizzle, so the map itself uses none).
+static int weight_tensor_maps(const void* packed, CUtensorMap* trunk, CUtensorMap* head) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  SW_REQUIRE(encode, "tc_mlp_fwd: cuTensorMapEncodeTiled is not available in this driver");
+  const cuuint64_t dims[2] = {128, (cuuint64_t)(PK_CHUNK_BYTES / 128)};
+  const cuuint64_t strides[1] = {128};
+  const cuuint32_t estr[2] = {1, 1};
+  for (int h = 0; h < 2; ++h) {
+    const cuuint32_t box[2] = {128, h ? (cuuint32_t)(HEAD_N / 2) : 128u};
+    CUresult r = encode(h ? head : trunk, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(packed), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SW_REQUIRE(r == CUDA_SUCCESS, "tc_mlp_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+  }
+  return SWNERF_OK;
+}
+
+// -1 = automatic (inference: CTA pairs with two tile slots; training: one CTA per tile - the faster one for each,
+// DESIGN.md section 4), 0 = always one CTA per tile, 1 = always CTA pairs.  SWNERF_FWD_PAIR=0/1 presets it.
+static std::atomic<int> g_fwd_variant{[] { const char* e = getenv("SWNERF_FWD_PAIR"); return e ? (atoi(e) ? 1 : 0) : -1; }()};
 
 static int fwd_impl(const float* rays, int ray_stride, int view_col, const float* z_vals, const float* pts,
                     int64_t n_rays, int n_samples, const void* packed, float* out, void* workspace, int training,
@@ -952,7 +973,8 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   { static const char* ko = getenv("SWNERF_KO"); g.ko = ko ? atoi(ko) : 0; }
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
-  if (g_fwd_variant.load() == 1) {        // experimental CTA-pair kernel (swnerf_tc_set_fwd_variant)
+  const int variant = g_fwd_variant.load();
+  if (variant == 1 || (variant < 0 && !training)) {        // CTA-pair kernel
     static std::once_flag once;
     std::call_once(once, [] {
       cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
@@ -960,8 +982,11 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
     });
     const int64_t num_quads = (g.num_tiles + 3) / 4;
     const int grid4 = 2 * (int)(num_quads < sm_count() / 2 ? num_quads : sm_count() / 2);
-    if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g);
-    else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g);
+    CUtensorMap tm_trunk, tm_head;
+    int rc = weight_tensor_maps(packed, &tm_trunk, &tm_head);
+    if (rc) return rc;
+    if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+    else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
     return check_launch("tc_mlp_fwd");
   }
   if (training) {
@@ -977,7 +1002,7 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
 }
 
 int swnerf_tc_set_fwd_variant(int variant) {
-  SW_REQUIRE(variant == 0 || variant == 1, "tc_set_fwd_variant: variant must be 0 or 1");
+  SW_REQUIRE(variant >= -1 && variant <= 1, "tc_set_fwd_variant: variant must be -1 (automatic), 0 or 1");
   g_fwd_variant.store(variant);
   return SWNERF_OK;
 }

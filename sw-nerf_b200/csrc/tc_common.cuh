@@ -227,6 +227,16 @@ template <int COLS>
 __device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr) {
   asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(COLS) : "memory");
 }
+// Tiled 2-D tensor-map load into THIS CTA's shared memory that reports its bytes to an mbarrier given by its
+// shared::cluster address - with .cta_group::2 that may be the pair leader's barrier (a plain cp.async.bulk can only
+// signal the CTA it writes to).
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tmap, int32_t c0, int32_t c1,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
+      : "memory");
+}
 // M = 256 across the pair: each CTA supplies its own 128 rows of A and its half (N/2 rows) of B from the SAME
 // shared-memory offsets, and receives its 128 rows of D in its own tensor memory.  Issued by the leader CTA only.
 __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

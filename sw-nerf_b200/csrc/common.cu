@@ -2,6 +2,7 @@
 #include "common.cuh"
 #include "../../include/swnerf_b200.h"
 #include <stdarg.h>
+#include <cuda.h>
 
 namespace swnerf {
 
@@ -22,6 +23,31 @@ int check_launch(const char* what) {
   __atomic_fetch_add(&g_launches, 1ULL, __ATOMIC_RELAXED);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SWNERF_OK;
+}
+
+int encode_u8_tensor_map(void* map, const void* base, int ndim, const unsigned long long* dims,
+                         const unsigned long long* strides, const unsigned int* box) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static EncodeFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      fn = nullptr;
+    return reinterpret_cast<EncodeFn>(fn);
+  }();
+  if (!encode) return set_err(SWNERF_ERR_UNSUPPORTED, "cuTensorMapEncodeTiled is not available in this driver");
+  cuuint64_t d[3], st[2];
+  cuuint32_t b[3], es[3] = {1, 1, 1};
+  for (int i = 0; i < ndim; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+  for (int i = 0; i + 1 < ndim; ++i) st[i] = strides[i];
+  CUresult r = encode(reinterpret_cast<CUtensorMap*>(map), CU_TENSOR_MAP_DATA_TYPE_UINT8, (cuuint32_t)ndim,
+                      const_cast<void*>(base), d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return set_err(SWNERF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return SWNERF_OK;
 }
 

@@ -19,6 +19,11 @@ int set_err(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
 
+// u8 tensor map (1..3 dims, no swizzle / interleave) through the driver entry point fetched at run time, so the
+// library does not link libcuda.  `map` points to a 128-byte CUtensorMap.  strides[] has ndim - 1 entries (bytes).
+int encode_u8_tensor_map(void* map, const void* base, int ndim, const unsigned long long* dims,
+                         const unsigned long long* strides, const unsigned int* box);
+
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 #define SW_REQUIRE(cond, ...)                                          \

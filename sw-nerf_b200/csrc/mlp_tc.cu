@@ -43,22 +43,37 @@ struct ParamPtrs {
 };
 
 // W_fv = W_v[:, :256] W_f (128 x 256), b_fv = W_v[:, :256] b_f + b_v      -> fold[128][257] fp32
-__global__ void fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= 128 * 257) return;
-  if (P.kind == 1) { fold[idx] = 0.f; return; }
-  int r = idx / 257, c = idx % 257;
-  const float* wv = P.p[16] + (size_t)r * 283;
-  float acc = 0.f;
-  if (c < 256) {
-    const float* wf = P.p[18];
-    for (int j = 0; j < 256; ++j) acc = fmaf(wv[j], wf[(size_t)j * 256 + c], acc);
+// blocks 0..31: one 32 x 32 tile of W_fv each (shared-memory tiles over the 256-long reduction); blocks 32..35: 32
+// rows of the bias column each.
+__global__ void __launch_bounds__(1024) fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
+  __shared__ float As[32][33], Bs[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t = blockIdx.x;
+  if (t < 32) {
+    const int r0 = (t >> 3) * 32, c0 = (t & 7) * 32;
+    float acc = 0.f;
+    if (P.kind == 0) {
+      for (int j0 = 0; j0 < 256; j0 += 32) {
+        As[ty][tx] = P.p[16][(size_t)(r0 + ty) * 283 + j0 + tx];       // W_v[r, j]
+        Bs[ty][tx] = P.p[18][(size_t)(j0 + ty) * 256 + c0 + tx];       // W_f[j, c]
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc = fmaf(As[ty][j], Bs[j][tx], acc);
+        __syncthreads();
+      }
+    }
+    fold[(r0 + ty) * 257 + c0 + tx] = acc;
   } else {
-    const float* bf = P.p[19];
-    for (int j = 0; j < 256; ++j) acc = fmaf(wv[j], bf[j], acc);
-    acc += P.p[17][r];
+    const int r = (t - 32) * 32 + ty;
+    float acc = 0.f;
+    if (P.kind == 0) {
+      for (int j = tx; j < 256; j += 32) acc = fmaf(P.p[16][(size_t)r * 283 + j], P.p[19][j], acc);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      acc += P.p[17][r];
+    }
+    if (tx == 0) fold[r * 257 + 256] = acc;
   }
-  fold[idx] = acc;
 }
 
 __device__ __forceinline__ float fwd_weight(const ParamPtrs& P, const float* fold, int c, int n, int k) {
@@ -908,7 +923,7 @@ static int pack_impl(const float* const* params, int kind, const float* tpe_host
   for (int i = 0; i < 24; ++i) P.tpe[i] = (kind == 1 && i < 21) ? tpe_host[i] : 0.f;
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
-  fold_head_kernel<<<(128 * 257 + 255) / 256, 256, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
+  fold_head_kernel<<<36, 1024, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
   int rc = check_launch("tc_fold_head");
   if (rc) return rc;
   pack_fwd_kernel<<<(PK_CHUNK_BYTES / 16 + 255) / 256, 256, 0, s>>>(P, pk);
@@ -927,27 +942,12 @@ int swnerf_tc_pack_weights_time(const float* const* params, const float* time_em
 // Tensor maps over the packed weight image seen as rows of 128 bytes: boxes of 128 rows (half a trunk chunk) and 72
 // rows (half a head chunk), copied verbatim (the image is already in the UMMA swizzle, so the map itself uses none).
 static int weight_tensor_maps(const void* packed, CUtensorMap* trunk, CUtensorMap* head) {
-  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-  static EncodeFn encode = [] {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess ||
-        q != cudaDriverEntryPointSuccess)
-      fn = nullptr;
-    return reinterpret_cast<EncodeFn>(fn);
-  }();
-  SW_REQUIRE(encode, "tc_mlp_fwd: cuTensorMapEncodeTiled is not available in this driver");
-  const cuuint64_t dims[2] = {128, (cuuint64_t)(PK_CHUNK_BYTES / 128)};
-  const cuuint64_t strides[1] = {128};
-  const cuuint32_t estr[2] = {1, 1};
+  const unsigned long long dims[2] = {128, (unsigned long long)(PK_CHUNK_BYTES / 128)};
+  const unsigned long long strides[1] = {128};
   for (int h = 0; h < 2; ++h) {
-    const cuuint32_t box[2] = {128, h ? (cuuint32_t)(HEAD_N / 2) : 128u};
-    CUresult r = encode(h ? head : trunk, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(packed), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    SW_REQUIRE(r == CUDA_SUCCESS, "tc_mlp_fwd: cuTensorMapEncodeTiled failed (%d)", (int)r);
+    const unsigned int box[2] = {128, h ? (unsigned)(HEAD_N / 2) : 128u};
+    int rc = encode_u8_tensor_map(h ? head : trunk, packed, 2, dims, strides, box);
+    if (rc) return rc;
   }
   return SWNERF_OK;
 }

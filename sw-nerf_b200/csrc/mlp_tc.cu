@@ -511,6 +511,11 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
 }
 
 
+// fp32 block of the packed weights (trunk biases, folded head bias, rgb_linear) for the CTA-pair kernel: staged per
+// call with a device-to-device copy on the launching stream.  Every access is warp-uniform, so constant-cache reads
+// cost the same as the shared-memory broadcast they replace, and the 10 KB of shared memory buy a 4th ring stage.
+__constant__ float c_f32[F32_COUNT];
+
 // ======================================================================================================
 // Forward kernel on CTA pairs (cta_group::2), two tile slots per CTA.
 //
@@ -529,11 +534,11 @@ template <bool TRAIN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_kernel(const __grid_constant__ FwdArgs g, const __grid_constant__ CUtensorMap tm_trunk,
                                                                                    const __grid_constant__ CUtensorMap tm_head) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw;                // no alignment slack (shared memory is full): checked instead
+  if (smem_u32(smem) & 1023u) __trap();
   uint8_t* s_act = smem + S4_ACT;          // [2 slots][4 blocks]
   uint8_t* s_enc = smem + S4_ENC;          // [2 slots]
   uint8_t* s_ring = smem + S4_RING;
-  float* s_f32 = reinterpret_cast<float*>(smem + S4_F32);
   float4* s_scr = reinterpret_cast<float4*>(smem + S4_SCR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S4_BAR);
   uint64_t* w_full = bars;                 // [NST4] leader: both CTAs' halves of the stage have landed (tensor-map loads)
@@ -561,10 +566,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
       mbar_init(&act_full[t], 16); mbar_init(&img_ready[t], 8); mbar_init(&st_done[t], 1);
     }
     mbar_fence_init();
-  }
-  {
-    const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF);
-    for (int i = threadIdx.x; i < F32_COUNT; i += blockDim.x) s_f32[i] = __ldg(src + i);
   }
   __syncthreads();
   cluster_sync_all();                      // both CTAs' barriers are initialised before anyone signals the other
@@ -675,7 +676,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(act_full_l + t * 8);
           } else if (li < 8) {
-            const float* bias = s_f32 + li * 256 + hh * 32;
+            const float* bias = c_f32 + li * 256 + hh * 32;
             // software pipeline over the four 64-column blocks: the TMEM load of block j+1 is in flight while
             // block j is converted and handed to the MMA thread
             if (TRAIN && wcnt > 0) mbar_wait(&st_done[t], (wcnt - 1) & 1);   // the image's bulk store still reads it
@@ -692,7 +693,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
               const float4* b4 = reinterpret_cast<const float4*>(bias + j * 64);
 #pragma unroll
               for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 bb = b4[i4];                         // broadcast LDS.128
+                const float4 bb = b4[i4];                         // warp-uniform constant-cache read
                 float a0 = __uint_as_float(v[4 * i4]) + bb.x, a1 = __uint_as_float(v[4 * i4 + 1]) + bb.y;
                 float a2 = __uint_as_float(v[4 * i4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * i4 + 3]) + bb.w;
                 if (TRAIN)
@@ -719,8 +720,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             }
           } else {
             // head: cols 0..127 = relu -> h9, col 128 = sigma; rgb = W_rgb h9 + b_rgb in fp32
-            const float* bh = s_f32 + F32_BHEAD;
-            const float* wr = s_f32 + F32_WRGB;
+            const float* bh = c_f32 + F32_BHEAD;
+            const float* wr = c_f32 + F32_WRGB;
             float pr = 0.f, pg = 0.f, pb = 0.f;
             // training: h9 goes into blocks 0 / 1 of the slot (this thread writes block hh); blocks 2,3 are not
             // rewritten by the head, so their store counters advance without a store (see the store warp)
@@ -777,7 +778,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             named_bar_sync(1, 256);
             if (hh == 0 && g.kind == 0) {
               float4 o = s_scr[row];
-              const float* br = s_f32 + F32_BRGB;
+              const float* br = c_f32 + F32_BRGB;
               if (idx < g.P)
                 reinterpret_cast<float4*>(g.raw)[idx] = make_float4(pr + o.x + br[0], pg + o.y + br[1], pb + o.z + br[2], o.w);
             }
@@ -952,8 +953,33 @@ static int weight_tensor_maps(const void* packed, CUtensorMap* trunk, CUtensorMa
   return SWNERF_OK;
 }
 
-// -1 = automatic (inference: CTA pairs with two tile slots; training: one CTA per tile - the faster one for each,
-// DESIGN.md section 4), 0 = always one CTA per tile, 1 = always CTA pairs.  SWNERF_FWD_PAIR=0/1 presets it.
+// Copies a network's fp32 block into c_f32 on the launching stream.  The buffer is process-wide: a call on a different
+// stream than the previous one first waits for that one's kernel (event), so concurrent streams serialise instead of
+// racing.  (While a stream is being captured into a CUDA graph only same-stream use is supported.)
+static int stage_f32_block(const uint8_t* src, cudaStream_t s) {
+  static std::mutex mu;
+  static cudaStream_t last = nullptr;
+  static bool have_last = false;
+  static cudaEvent_t ev = nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(s, &cap);
+  if (cap == cudaStreamCaptureStatusNone) {
+    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    if (have_last && last != s) {
+      cudaEventRecord(ev, last);
+      cudaStreamWaitEvent(s, ev, 0);
+    }
+    last = s; have_last = true;
+  }
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_f32, src, F32_COUNT * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+  if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: staging the bias block failed: %s", cudaGetErrorString(e));
+  return SWNERF_OK;
+}
+
+// -1 = automatic (the CTA-pair kernel: 17 % faster in inference, 2-5 % in training),
+// 0 = one CTA per tile (the first-generation kernel, kept as the bit-identity reference), 1 = CTA pairs.
+// SWNERF_FWD_PAIR=0/1 presets it.
 static std::atomic<int> g_fwd_variant{[] { const char* e = getenv("SWNERF_FWD_PAIR"); return e ? (atoi(e) ? 1 : 0) : -1; }()};
 
 static int fwd_impl(const float* rays, int ray_stride, int view_col, const float* z_vals, const float* pts,
@@ -974,7 +1000,7 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
   const int variant = g_fwd_variant.load();
-  if (variant == 1 || (variant < 0 && !training)) {        // CTA-pair kernel
+  if (variant != 0) {        // CTA-pair kernel
     static std::once_flag once;
     std::call_once(once, [] {
       cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
@@ -984,6 +1010,8 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
     const int grid4 = 2 * (int)(num_quads < sm_count() / 2 ? num_quads : sm_count() / 2);
     CUtensorMap tm_trunk, tm_head;
     int rc = weight_tensor_maps(packed, &tm_trunk, &tm_head);
+    if (rc) return rc;
+    rc = stage_f32_block(reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF, s);
     if (rc) return rc;
     if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
     else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);

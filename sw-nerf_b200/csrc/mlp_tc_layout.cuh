@@ -32,15 +32,15 @@ constexpr int PK_FOLD_OFF = PK_F32_OFF + ((F32_COUNT * 4 + 255) / 256) * 256; //
 constexpr int PK_TOTAL_BYTES = PK_FOLD_OFF + 128 * 257 * 4;
 
 // ---- shared memory of the CTA-pair forward kernel (per CTA; two tile slots; offsets from a 1024-aligned base)
-constexpr int NST4 = 3;                   // weight ring depth; a stage holds this CTA's half of one chunk
+constexpr int NST4 = 4;                   // weight ring depth; a stage holds this CTA's half of one chunk
 constexpr int STG4_B = CHUNK_B / 2;       // [128 x 64] fp16 (head chunks use 72 rows of it)
 constexpr int S4_ACT = 0;                                 // [2 slots] activation images [128 x 256] fp16, in place
 constexpr int S4_ENC = S4_ACT + 2 * ACT_BYTES;            // [2 slots] encoding image: PE (layers 0, 5), then the view encoding (head)
 constexpr int S4_RING = S4_ENC + 2 * ACT_BLK;
-constexpr int S4_F32 = S4_RING + NST4 * STG4_B;
-constexpr int S4_SCR = S4_F32 + ((F32_COUNT * 4 + 127) / 128) * 128;
+constexpr int S4_SCR = S4_RING + NST4 * STG4_B;
 constexpr int S4_BAR = S4_SCR + TILE * 16;
-constexpr int S4_TOTAL = S4_BAR + 512 + 1024;                                 // + alignment slack
+constexpr int S4_TOTAL = S4_BAR + 512;    // biases live in constant memory and the base must be 1024-aligned (checked):
+                                          // that is what makes room for the 4th ring stage
 static_assert(S4_TOTAL <= 232448, "shared memory budget");
 
 // ---- shared memory of the forward kernel v1 (offsets from a 1024-aligned base)

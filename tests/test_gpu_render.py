@@ -574,8 +574,8 @@ def test_render_full_frame_chunked_tc_vs_fp32():
 
 @needs_tc_bwd
 def test_cta_pair_forward_variant_matches_default():
-    """The CTA-pair forward kernel (cta_group::2, two tile slots per CTA; default for inference) and the one-CTA-per-tile
-    kernel (default for training) must agree bit for bit: same fp16 operands, same fp32 accumulation order per output."""
+    """The CTA-pair forward kernel (cta_group::2, two tile slots per CTA; the default) and the first-generation
+    one-CTA-per-tile kernel must agree bit for bit: same fp16 operands, same fp32 accumulation order per output."""
     from swnerf_b200 import _lib
     N = 300                                           # 300 x 64 = 150 tiles: ragged quads and a ragged last tile
     rays = T(O.blender_rays(N, 77))

@@ -194,7 +194,8 @@ int swnerf_tc_probe(int variant, int N, int iters, float* cycles_per_mma, void* 
 
 /* CTA-pair (cta_group::2) self-test and rate probe (tests / tools only): D[256,N] = A[256,K] . B[N,K]^T on a cluster
  * of two CTAs, M = 256 MMAs issued by the leader.  iters > 1 repeats the K loop; n_pairs clusters run the same problem;
- * cycles_per_mma[n_pairs] (optional) receives SM cycles per MMA.  D is written by pair 0 (may be NULL). */
+ * cycles_per_mma[n_pairs] (optional) receives SM cycles per MMA.  D is written by pair 0 (may be NULL).
+ * iters == 0 selects the MN-major form (the weight-gradient shape): D[256,N] = A[K,256]^T . B[K,N], N in {128,256}. */
 int swnerf_tc_selftest_pair(const float* A, const float* B, float* D, int N, int K, int iters, int n_pairs,
                             float* cycles_per_mma, void* scratch, void* stream);
 

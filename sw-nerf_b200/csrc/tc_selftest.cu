@@ -162,11 +162,13 @@ __global__ void __launch_bounds__(128, 1) probe_kernel(int variant, int N, int i
 // iters > 1 repeats the K loop (accumulating) to measure cycles per MMA; iters >> 20 = multicast commits per group.
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
 pair_gemm_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ b_img, int N, int K, float* __restrict__ D,
-                 int iters, float* __restrict__ cycles) {
+                 int iters, float* __restrict__ cycles, int mn) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // K-major: per 64-wide K block an image of [rows x 64]; MN-major (mn): per 64-wide M/N block an image of [K x 64]
   const int kb_n = K / 64;
-  const int a_bytes = kb_n * 128 * 128, b_bytes = kb_n * (N / 2) * 128;
+  const int a_bytes = mn ? 2 * K * 128 : kb_n * 128 * 128;
+  const int b_bytes = mn ? (N / 128) * K * 128 : kb_n * (N / 2) * 128;
   uint8_t* sa = smem;
   uint8_t* sb = smem + a_bytes;
   __shared__ uint64_t bar_full, bar_peer, bar_done, bar_x[2];
@@ -206,9 +208,18 @@ pair_gemm_kernel(const uint8_t* __restrict__ a_img, const uint8_t* __restrict__ 
     if (rank == 0) {
       mbar_wait_cluster(&bar_peer, 0);
       tc_fence_after();
-      const uint32_t idesc = umma_idesc_f16(256, N, 0, 0);
+      const uint32_t idesc = umma_idesc_f16(256, N, mn, mn);
       const uint32_t sa32 = smem_u32(sa), sb32 = smem_u32(sb);
       long long t0 = clock64();
+      if (mn) {
+        // each CTA: A = its 128 M-columns (two [K x 64] blocks, LBO = block stride), B = its N/2 columns likewise
+        if (elect_one()) {
+          for (int ks = 0; ks < K / 16; ++ks)
+            umma_f16_pair(tmem, umma_desc_mnmajor(sa32 + ks * 2048, (uint32_t)K * 128),
+                          umma_desc_mnmajor(sb32 + ks * 2048, (uint32_t)K * 128), idesc, ks ? 1u : 0u);
+        }
+        __syncwarp();
+      } else
       for (int it = 0; it < iters; ++it) {
         for (int kb = 0; kb < kb_n; ++kb) {
           if (elect_one()) {
@@ -263,6 +274,21 @@ extern "C" int swnerf_tc_probe(int variant, int N, int iters, float* cycles_per_
 extern "C" int swnerf_tc_selftest_pair(const float* A, const float* B, float* D, int N, int K, int iters, int n_pairs,
                                        float* cycles_per_mma, void* scratch, void* stream) {
   SW_REQUIRE(A && B && scratch, "tc_selftest_pair: null pointer");
+  if (iters == 0) {
+    // MN-major form (the weight-gradient shape): D[256 x N] = P[K x 256]^T . Q[K x N], A = P, B = Q, N in {128, 256}
+    SW_REQUIRE((N == 128 || N == 256) && (K == 64 || K == 128) && D, "tc_selftest_pair: MN-major form needs N in {128,256}, K in {64,128}");
+    cudaStream_t s = (cudaStream_t)stream;
+    uint8_t* sc = reinterpret_cast<uint8_t*>(scratch);
+    // selftest_pack_kernel writes one [rows x 64] image per 64-column block: P -> 4 blocks, Q -> N/64 blocks; CTA r
+    // takes blocks 2r, 2r+1 of P and blocks r*(N/128).. of Q, which are contiguous in that order
+    const int a_all = 4 * K * 128, b_all = (N / 64) * K * 128;
+    selftest_pack_kernel<<<(K * 256 + 255) / 256, 256, 0, s>>>(A, K, 256, sc);
+    selftest_pack_kernel<<<(K * N + 255) / 256, 256, 0, s>>>(B, K, N, sc + a_all);
+    size_t smem = (size_t)a_all / 2 + b_all / 2 + 2048;
+    cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    pair_gemm_kernel<<<2, 128, smem, s>>>(sc, sc + a_all, N, K, D, 1, nullptr, 1);
+    return check_launch("tc_selftest_pair");
+  }
   SW_REQUIRE(N % 32 == 0 && N >= 32 && N <= 256, "tc_selftest_pair: N must be a multiple of 32 in [32, 256]");
   SW_REQUIRE(K % 64 == 0 && K >= 64 && K <= 256, "tc_selftest_pair: K in {64,128,192,256}");
   SW_REQUIRE((iters & 0xfffff) >= 1 && n_pairs >= 1, "tc_selftest_pair: bad sizes");
@@ -277,7 +303,7 @@ extern "C" int swnerf_tc_selftest_pair(const float* A, const float* B, float* D,
   }
   size_t smem = (size_t)a_bytes + b_half + 2048;
   cudaFuncSetAttribute(pair_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  pair_gemm_kernel<<<2 * n_pairs, 128, smem, s>>>(sc, sc + 2 * (size_t)a_bytes, N, K, D, iters, cycles_per_mma);
+  pair_gemm_kernel<<<2 * n_pairs, 128, smem, s>>>(sc, sc + 2 * (size_t)a_bytes, N, K, D, iters, cycles_per_mma, 0);
   return check_launch("tc_selftest_pair");
 }
 

@@ -64,3 +64,18 @@ def test_umma_cta_pair(N, K):
     ref = A.half().double() @ B.half().double().t()
     err = float((D.double() - ref).abs().max() / ref.abs().max())
     assert err < 1e-5, err
+
+
+@pytest.mark.parametrize("N,K", [(256, 64), (256, 128), (128, 64)])
+def test_umma_cta_pair_mnmajor(N, K):
+    """cta_group::2 with MN-major operands (the weight-gradient shape): D = P^T Q, K = samples."""
+    g = torch.Generator(device="cuda").manual_seed(N + K + 3)
+    P = torch.randn(K, 256, device="cuda", generator=g)
+    Q = torch.randn(K, N, device="cuda", generator=g)
+    D = torch.empty((256, N), dtype=torch.float32, device="cuda")
+    scratch = torch.empty(1024 * 1024, dtype=torch.uint8, device="cuda")
+    call("swnerf_tc_selftest_pair", P.data_ptr(), Q.data_ptr(), D.data_ptr(), N, K, 0, 1, None, scratch.data_ptr(), stream())
+    torch.cuda.synchronize()
+    ref = P.half().double().t() @ Q.half().double()
+    err = float((D.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-5, err

@@ -14,6 +14,8 @@
 //  3. un-fold: d W_fv, d b_fv -> feature_linear / views_linears gradients (fp32 SIMT GEMMs, tiny).
 // Gradients are scaled by a power of two (from max|d_raw|, on device) before the fp16 conversion and
 // unscaled in the fp32 flush.
+#include <cuda.h>
+#include <mutex>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_tc_layout.cuh"
@@ -530,6 +532,154 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 2b. backward weights of the seven 256 x 256 trunk layers on CTA pairs (cta_group::2)
+//
+// dW_l = dy_l^T x_l with M = 256 output channels split over the two CTAs of a cluster: CTA r streams only ITS half of
+// dy_l (blocks 2r, 2r+1 = its 128 output channels, the A operand) and ITS half of x_l (blocks 2r, 2r+1 = half of the
+// N = 256 input channels, the B operand the pair shares), so a 64-sample stage is 32 KB per SM instead of 64 KB, the
+// ring is 6 stages deep instead of 3, a stage's MMAs take 4 x 128 cycles instead of 8 x 161, and each CTA's
+// accumulator is 256 TMEM columns - which leaves room for the bias gradient as one more MMA against a block of ones
+// (column sums on the tensor pipe; the CUDA-core sums out of shared memory cost 0.25 ms per step).  Work is the
+// concatenation of the seven layers' tile lists cut into equal slices, one per pair (at most two layers per pair).
+// Loads are tensor-map copies that report to the leader's barrier; completion is a multicast commit.
+struct WgPairArgs {
+  int64_t num_tiles;
+  float* grads[24];
+  const uint32_t* absmax; float fixed_scale;
+  int kind;
+};
+struct WgPairMaps { CUtensorMap fwd, dy; };      // workspace as [16-KB block][128 rows][128 B], box = 2 blocks x 64 rows
+constexpr int WGP_STAGE = 4 * HALF_BLK;           // dy half (2 blocks) | x half (2 blocks), 64 samples each
+constexpr int WGP_NST = 6;
+constexpr int WGP_SMEM = WGP_NST * WGP_STAGE + HALF_BLK + 1024;      // + ones block + alignment slack
+constexpr int WGP_JOBS = 7;                       // c_jobs[kind][1..7]
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
+mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_constant__ WgPairMaps tm) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_ones = smem + WGP_NST * WGP_STAGE;
+  __shared__ uint64_t s_full[WGP_NST], s_empty[WGP_NST], s_done, flush_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t n_pairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  // this pair's slice of the work list (layer-major tiles)
+  const int64_t W = (int64_t)WGP_JOBS * g.num_tiles;
+  const int64_t w_begin = W * pair / n_pairs, w_end = W * (pair + 1) / n_pairs;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < WGP_NST; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1); }
+    mbar_init(&s_done, 1);
+    mbar_init(&flush_done, 8);               // leader: the four flush warps of both CTAs have read the accumulators
+    mbar_fence_init();
+  }
+  for (int i = threadIdx.x; i < HALF_BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3c003c00u;   // fp16 1.0
+  fence_async_smem();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_alloc_pair<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+
+  if (warp == 0) {
+    // ===================== producer: this CTA's halves of dy_l and x_l, 64 samples per stage =====================
+    if (lane == 0) {
+      const uint32_t s_full_l = mapa_u32(smem_u32(s_full), 0);
+      uint32_t cnt = 0;
+      for (int64_t w = w_begin; w < w_end; ++w) {
+        const int job = 1 + (int)(w / g.num_tiles);
+        const int64_t tile = w % g.num_tiles;
+        const WgJob& J = c_jobs[g.kind][job];
+        const int dy_blk = (int)(tile * 36) + J.pc[0].tile_off / ACT_BLK + 2 * (int)rank;
+        const int x_blk = (int)(tile * 36) + J.pc[1].tile_off / ACT_BLK + 2 * (int)rank;
+        for (int half = 0; half < 2; ++half, ++cnt) {
+          const uint32_t stage = cnt % WGP_NST, ph = (cnt / WGP_NST) & 1;
+          mbar_wait(&s_empty[stage], ph ^ 1);
+          if (leader) mbar_expect_tx(&s_full[stage], 2u * WGP_STAGE);
+          uint8_t* dst = smem + stage * WGP_STAGE;
+          tma_load_3d_pair(dst, &tm.dy, 0, half * 64, dy_blk, s_full_l + stage * 8);
+          tma_load_3d_pair(dst + 2 * HALF_BLK, &tm.fwd, 0, half * 64, x_blk, s_full_l + stage * 8);
+        }
+      }
+    }
+  } else if (warp == 1 && leader) {
+    // ===================== MMA issuer (leader) =====================
+    const uint32_t idesc = umma_idesc_f16(256, 256, 1, 1), idesc_b = umma_idesc_f16(256, 32, 1, 1);
+    const uint32_t smem0 = smem_u32(smem), ones = smem_u32(s_ones);
+    uint32_t cnt = 0, seg = 0;
+    for (int64_t w = w_begin; w < w_end; ++w) {
+      const bool first = (w == w_begin) || (w % g.num_tiles == 0);     // a new layer starts: fresh accumulators
+      const bool last = (w + 1 == w_end) || ((w + 1) % g.num_tiles == 0);
+      if (first && seg > 0) mbar_wait_cluster(&flush_done, (seg - 1) & 1);   // the previous layer's accumulators were read
+      for (int half = 0; half < 2; ++half, ++cnt) {
+        const uint32_t stage = cnt % WGP_NST;
+        mbar_wait(&s_full[stage], (cnt / WGP_NST) & 1);
+        tc_fence_after();
+        const uint32_t base = smem0 + stage * WGP_STAGE;
+        if (elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint32_t acc = (first && half == 0 && ks == 0) ? 0u : 1u;
+            const uint64_t ad = umma_desc_mnmajor(base + ks * 2048, HALF_BLK);
+            umma_f16_pair(tmem, ad, umma_desc_mnmajor(base + 2 * HALF_BLK + ks * 2048, HALF_BLK), idesc, acc);
+            umma_f16_pair(tmem + 256, ad, umma_desc_mnmajor(ones + ks * 2048, HALF_BLK), idesc_b, acc);   // column sums
+          }
+          umma_commit_pair(&s_empty[stage], 3);
+          if (last && half == 1) umma_commit_pair(&s_done, 3);
+        }
+        __syncwarp();
+      }
+      if (last) ++seg;
+    }
+  }
+  // (flush code below runs for warps 4-7 of both CTAs)
+  if (warp >= 4) {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
+    const uint32_t flush_done_l = mapa_u32(smem_u32(&flush_done), 0);
+    uint32_t seg = 0;
+    for (int64_t w = w_begin; w < w_end;) {
+      const int job = 1 + (int)(w / g.num_tiles);
+      int64_t seg_end = (int64_t)job * g.num_tiles;            // first work item of the next layer
+      if (seg_end > w_end) seg_end = w_end;
+      const WgJob& J = c_jobs[g.kind][job];
+      const WgMma& mm = J.mm[rank];
+      mbar_wait(&s_done, seg & 1);
+      tc_fence_after();
+      float* base = g.grads[mm.out_param] + mm.out_off + (size_t)r * mm.row_stride;
+      for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) atomicAdd(base + c0 + i, __uint_as_float(v[i]) * inv);
+      }
+      if (J.nbias > 0) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + 256, v);
+        tmem_ld_wait();
+        atomicAdd(g.grads[J.bs[0].out_param] + J.bs[0].out_off + rank * 128 + r, __uint_as_float(v[0]) * inv);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_remote(flush_done_l);
+      w = seg_end;
+      ++seg;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 2) tmem_dealloc_pair<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 // 3. un-fold of the head (model.py:50-55):  G = d W_fv [128,256], gb = d b_fv [128]
 //      dW_f[c][k]  += sum_u W_v[u][c] G[u][k]                     (64 tiles of 32x32)
 //      dW_v[u][c]  += sum_k G[u][k] W_f[c][k] + gb[u] b_f[c]       (32 tiles)
@@ -733,13 +883,14 @@ static void build_jobs(WgJob* jobs, int kind) {
 }
 
 static void assign_ctas(int n_cta, int* first, int kind) {
-  // CTAs per job in proportion to the bytes a job streams per tile
-  const int w[WG_JOBS] = {144, 128, 128, 128, 128, 128, 128, 128, kind == 1 ? 80 : 176};
+  // CTAs per job in proportion to the bytes a job streams per tile; the seven 256 x 256 trunk layers (jobs 1..7) run
+  // on the CTA-pair kernel and get no CTAs here
+  const int w[WG_JOBS] = {144, 0, 0, 0, 0, 0, 0, 0, kind == 1 ? 80 : 176};
   int tot = 0;
   for (int j = 0; j < WG_JOBS; ++j) tot += w[j];
   int cnt[WG_JOBS], used = 0;
-  for (int j = 0; j < WG_JOBS; ++j) { cnt[j] = n_cta * w[j] / tot; if (cnt[j] < 1) cnt[j] = 1; used += cnt[j]; }
-  for (int j = 0; used < n_cta; j = (j + 1) % WG_JOBS) { ++cnt[j]; ++used; }
+  for (int j = 0; j < WG_JOBS; ++j) { cnt[j] = n_cta * w[j] / tot; if (cnt[j] < 1 && w[j] > 0) cnt[j] = 1; used += cnt[j]; }
+  for (int j = 0; used < n_cta; j = (j + 1) % WG_JOBS) if (w[j] > 0) { ++cnt[j]; ++used; }
   first[0] = 0;
   for (int j = 0; j < WG_JOBS; ++j) first[j + 1] = first[j] + cnt[j];
 }
@@ -751,7 +902,7 @@ using namespace swnerf;
 // optional per-kernel device timing of the backward (bench.py): events on the launching stream
 // (process-wide, not thread-local: autograd runs the backward on its own engine thread)
 static int g_prof = 0;
-static cudaEvent_t g_ev[3] = {nullptr, nullptr, nullptr};
+static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int g_prof_valid = 0;
 
 extern "C" {
@@ -760,7 +911,7 @@ int swnerf_tc_set_profiling(int on) {
   g_prof = on;
   g_prof_valid = 0;
   if (on && !g_ev[0])
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 4; ++i)
       if (cudaEventCreate(&g_ev[i]) != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "cudaEventCreate failed");
   return SWNERF_OK;
 }
@@ -868,6 +1019,30 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   if (n_cta < WG_JOBS) n_cta = WG_JOBS;
   assign_ctas(n_cta, w.job_first_cta, kind);
   if (g_prof) cudaEventRecord(g_ev[1], s);
+  {
+    // trunk layers: CTA pairs
+    static std::once_flag once;
+    std::call_once(once, [] {
+      cudaFuncSetAttribute(mlp_bwd_weight_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGP_SMEM);
+    });
+    WgPairArgs pw;
+    pw.num_tiles = tiles; pw.absmax = absmax; pw.fixed_scale = grad_scale; pw.kind = kind;
+    for (int i = 0; i < 24; ++i) pw.grads[i] = i < np ? grads[i] : nullptr;
+    WgPairMaps maps;
+    static_assert(WS_TILE_BYTES == 36 * ACT_BLK && WS_DY_BYTES == 36 * ACT_BLK, "tile records are 36 blocks of 16 KB");
+    const unsigned long long dims[3] = {128, 128, (unsigned long long)tiles * 36};
+    const unsigned long long strides[2] = {128, (unsigned long long)ACT_BLK};
+    const unsigned int box[3] = {128, 64, 2};
+    rc = encode_u8_tensor_map(&maps.fwd, ws, 3, dims, strides, box);
+    if (rc) return rc;
+    rc = encode_u8_tensor_map(&maps.dy, ws + tiles * (WS_TILE_BYTES + WS_MASK_BYTES), 3, dims, strides, box);
+    if (rc) return rc;
+    const int n_pair_ctas = (sm_count() / 2) * 2;
+    mlp_bwd_weight_pair_kernel<<<n_pair_ctas, 256, WGP_SMEM, s>>>(pw, maps);
+    rc = check_launch("tc_mlp_bwd_weight_pair");
+    if (rc) return rc;
+    if (g_prof) cudaEventRecord(g_ev[3], s);
+  }
   mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w);
   if (g_prof) { cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
   rc = check_launch("tc_mlp_bwd_weight");

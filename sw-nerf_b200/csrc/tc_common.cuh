@@ -237,6 +237,13 @@ __device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const void* tma
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(bar_cluster_addr)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const void* tmap, int32_t c0, int32_t c1, int32_t c2,
+                                                 uint32_t bar_cluster_addr) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar_cluster_addr)
+      : "memory");
+}
 // M = 256 across the pair: each CTA supplies its own 128 rows of A and its half (N/2 rows) of B from the SAME
 // shared-memory offsets, and receives its 128 rows of D in its own tensor memory.  Issued by the leader CTA only.
 __device__ __forceinline__ void umma_f16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,

@@ -333,6 +333,14 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
 // a9/a10/a11  hierarchical resampling                         ray.py:96-153, nerf/run.py:396-400,416
 // One warp per ray.  smem per warp: cdf[M] | bins[M] | sort buffer[P] (P = pow2 >= S + Ni).
 // ---------------------------------------------------------------------------------------------
+// IEEE division that keeps a zero numerator off __fdiv_rn's slow path (a ~100-instruction subroutine the whole warp
+// executes when ANY lane has a zero / denormal operand: it was half of the resample kernel's instructions)
+__device__ __forceinline__ float div_rn_z(float a, float b) {
+  const bool z = (a == 0.f);
+  const float q = __fdiv_rn(z ? 1.f : a, b);
+  return z ? a : q;
+}
+
 __device__ __forceinline__ int upper_bound_smem(const float* a, int n, float v) {
   // number of elements <= v  == torch.searchsorted(right=True)
   int lo = 0, hi = n;
@@ -361,7 +369,7 @@ __device__ void warp_build_cdf(const float* __restrict__ w, int M, float* cdf, i
   if (lane == 0) cdf[0] = 0.f;
   for (int base = 0; base < M - 1; base += 32) {
     int i = base + lane;
-    float p = (i < M - 1) ? __fdiv_rn(__fadd_rn(__ldg(w + i), 1e-5f), tot) : 0.f;
+    float p = (i < M - 1) ? div_rn_z(__fadd_rn(__ldg(w + i), 1e-5f), tot) : 0.f;
     float inc = warp_scan_add(p, lane);
     if (i < M - 1) cdf[i + 1] = carry + inc;
     carry += __shfl_sync(0xffffffffu, inc, 31);
@@ -376,7 +384,7 @@ __device__ __forceinline__ float invert_cdf(const float* cdf, const float* bins,
   float bb = bins[below], ba = bins[above];
   float denom = __fsub_rn(ca, cb);
   if (denom < 1e-5f) denom = 1.f;                              // ray.py:149
-  float t = __fdiv_rn(__fsub_rn(u, cb), denom);
+  float t = div_rn_z(__fsub_rn(u, cb), denom);
   *ind_out = ind;
   return __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));       // ray.py:151
 }
@@ -439,16 +447,14 @@ __device__ __forceinline__ void smem_cswap(float* a, int i, int l) {
   if (x > y) { a[i] = y; a[l] = x; }
 }
 
-__global__ void __launch_bounds__(kWarpsPerBlock * 32)
-resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
-                int64_t N, int S, int Ni, int NiP, float* __restrict__ z_samples, float* __restrict__ z_fine,
-                float* __restrict__ z_std) {
-  extern __shared__ float smem[];
-  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
-  if (r >= N) return;
+// One ray on one warp, any S / Ni (the exact algorithm; also the fallback of the specialised kernel below).
+// row_smem: cdf[M] | bins[M] | z[S] | samples[NiP] | merged[S+Ni]
+__device__ void resample_row_generic(const float* __restrict__ z_vals, const float* __restrict__ weights,
+                                     const float* __restrict__ u_in, int64_t r, int S, int Ni, int NiP,
+                                     float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std,
+                                     float* row_smem, int lane) {
   const int M = S - 1;                               // bins = z_mid (S-1), weights[1:-1] (S-2)
-  float* cdf = smem + (size_t)warp * (2 * M + S + NiP + S + Ni);
+  float* cdf = row_smem;
   float* bs = cdf + M;
   float* zs = bs + M;
   float* sm = zs + S;
@@ -503,6 +509,184 @@ resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weig
   }
   __syncwarp();
   for (int i = lane; i < S + Ni; i += 32) z_fine[r * (S + Ni) + i] = outb[i];
+}
+
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
+                int64_t N, int S, int Ni, int NiP, float* __restrict__ z_samples, float* __restrict__ z_fine,
+                float* __restrict__ z_std) {
+  extern __shared__ float smem[];
+  int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= N) return;
+  resample_row_generic(z_vals, weights, u_in, r, S, Ni, NiP, z_samples, z_fine, z_std,
+                       smem + (size_t)warp * (2 * (S - 1) + S + NiP + S + Ni), lane);
+}
+
+// Specialisation for the reference configs' shape (64 coarse samples, 128 importance samples): everything a lane owns
+// stays in registers in a BLOCKED layout (z / weights 2 per lane, samples 4 per lane, merged output 6 per lane), the
+// inverse cdf walks forward from one binary search per lane (the uniforms are ascending), a sample's rank among the
+// z_vals follows from its bin (it lies between two z_mids, so only z[below+1] has to be compared), and the z_vals
+// drop into the holes the scattered samples leave (one prefix count).  ~4x fewer instructions than the generic
+// kernel.  Every step is verified with a warp vote (samples ascending, merged row ascending); a ray that fails -
+// rounding across a bin edge, degenerate spacing - is redone by the exact generic routine.
+__device__ __forceinline__ void cswap2(float& a, float& b, int& ia, int& ib) {
+  if (a > b) { float t = a; a = b; b = t; int ti = ia; ia = ib; ib = ti; }
+}
+
+template <bool RANDOM>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+resample64_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
+                  int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std) {
+  constexpr int S = 64, M = 63, Ni = 128;
+  constexpr int ROW = 2 * M + S + Ni + S + Ni;         // the generic routine's footprint (510 floats)
+  extern __shared__ float smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
+  if (r >= N) return;
+  float* row = smem + (size_t)warp * ROW;
+  float* cdf = row;            // [64] (63 used)
+  float* bs = row + 64;        // [64] (63 used)
+  float* zs = row + 128;       // [64]
+  float* outb = row + 192;     // [192]
+  const unsigned full = 0xffffffffu;
+
+  const float2 z2 = __ldg(reinterpret_cast<const float2*>(z_vals + r * S) + lane);
+  const float2 w2 = __ldg(reinterpret_cast<const float2*>(weights + r * S) + lane);
+  const float znext = __shfl_down_sync(full, z2.x, 1);
+  zs[2 * lane] = z2.x; zs[2 * lane + 1] = z2.y;
+  bs[2 * lane] = __fmul_rn(0.5f, __fadd_rn(z2.y, z2.x));                         // run.py:396
+  if (lane < 31) bs[2 * lane + 1] = __fmul_rn(0.5f, __fadd_rn(znext, z2.y));
+  // pdf over weights[1..62] (ray.py:111-114): lane l owns p[2l-1] = w[2l] and p[2l] = w[2l+1]
+  float pa = (lane >= 1) ? __fadd_rn(w2.x, 1e-5f) : 0.f;
+  float pb = (lane <= 30) ? __fadd_rn(w2.y, 1e-5f) : 0.f;
+  const float tot = warp_sum(pa + pb);
+  pa = div_rn_z(pa, tot); pb = div_rn_z(pb, tot);
+  const float inc = warp_scan_add(pa + pb, lane);
+  float ex = __shfl_up_sync(full, inc, 1);
+  if (lane == 0) ex = 0.f;
+  cdf[2 * lane] = (lane == 0) ? 0.f : fminf(ex + pa, inc);                       // non-decreasing by construction
+  if (lane <= 30) cdf[2 * lane + 1] = inc;
+  __syncwarp();
+
+  float u[4];
+  if (RANDOM) {
+    const float4 u4 = __ldg(reinterpret_cast<const float4*>(u_in + r * Ni) + lane);
+    u[0] = u4.x; u[1] = u4.y; u[2] = u4.z; u[3] = u4.w;
+    // bitonic sort of the 128 uniforms, element e = 4 lane + i: strides < 4 inside the lane, the rest by shuffle
+#pragma unroll
+    for (int k = 2; k <= Ni; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        if (j >= 4) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int e = 4 * lane + i;
+            const float o = __shfl_xor_sync(full, u[i], j >> 2);
+            const bool up = (e & k) == 0, low = (e & j) == 0;
+            u[i] = (low == up) ? fminf(u[i], o) : fmaxf(u[i], o);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            if ((i & j) == 0) {
+              const int e = 4 * lane + i;
+              const bool up = (e & k) == 0;
+              const float x = u[i], y = u[i | j];
+              if ((x > y) == up) { u[i] = y; u[i | j] = x; }
+            }
+          }
+        }
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = det_u(4 * lane + i, Ni);
+  }
+
+  // inverse cdf: one binary search, then walk forward (ray.py:136-151)
+  float sv[4];
+  int bl[4];
+  int ind = upper_bound_smem(cdf, M, u[0]);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    if (i > 0) while (ind < M && cdf[ind] <= u[i]) ++ind;
+    const int below = max(0, ind - 1), above = min(M - 1, ind);
+    const float cb = cdf[below], ca = cdf[above], bb = bs[below], ba = bs[above];
+    float denom = __fsub_rn(ca, cb);
+    if (denom < 1e-5f) denom = 1.f;
+    const float t = div_rn_z(__fsub_rn(u[i], cb), denom);
+    sv[i] = __fadd_rn(bb, __fmul_rn(t, __fsub_rn(ba, bb)));
+    bl[i] = below;
+  }
+  // one-ulp inversions across a bin edge: two odd-even passes (as the generic routine), then verify
+  cswap2(sv[0], sv[1], bl[0], bl[1]);
+  cswap2(sv[2], sv[3], bl[2], bl[3]);
+  cswap2(sv[1], sv[2], bl[1], bl[2]);
+  {
+    const float n0 = __shfl_down_sync(full, sv[0], 1), p3 = __shfl_up_sync(full, sv[3], 1);
+    const int nb0 = __shfl_down_sync(full, bl[0], 1), pb3 = __shfl_up_sync(full, bl[3], 1);
+    const bool sw_hi = lane < 31 && sv[3] > n0, sw_lo = lane > 0 && p3 > sv[0];
+    if (sw_hi) { sv[3] = n0; bl[3] = nb0; }
+    if (sw_lo) { sv[0] = p3; bl[0] = pb3; }
+  }
+  bool ok = sv[0] <= sv[1] && sv[1] <= sv[2] && sv[2] <= sv[3];
+  {
+    const float n0 = __shfl_down_sync(full, sv[0], 1);
+    ok = ok && (lane == 31 || sv[3] <= n0);
+  }
+  // rank among the z_vals: the sample lies in [z_mid[below], z_mid[below+1]], so only z[below+1] can tie or precede it
+  int pos[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int rank = bl[i] + 1 + (sv[i] >= zs[bl[i] + 1] ? 1 : 0);
+    pos[i] = 4 * lane + i + rank;
+    ok = ok && sv[i] >= zs[bl[i]] && (bl[i] + 2 >= S || sv[i] < zs[bl[i] + 2]);
+  }
+  const int SENT = 0x7fc00123;
+#pragma unroll
+  for (int j = 0; j < 6; ++j) outb[lane + 32 * j] = __int_as_float(SENT);
+  __syncwarp();
+  if (__all_sync(full, ok)) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) outb[pos[i]] = sv[i];
+    __syncwarp();
+    // the z_vals fill the holes in order: hole ordinal = position - samples before it
+    float v[6];
+    int ns = 0;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) { v[j] = outb[6 * lane + j]; ns += (__float_as_int(v[j]) != SENT); }
+    int before = ns;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(full, before, o); if (lane >= o) before += t; }
+    before -= ns;                                   // samples in lower lanes
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (__float_as_int(v[j]) == SENT) v[j] = zs[6 * lane + j - before]; else ++before;
+    }
+    bool ok2 = v[0] <= v[1] && v[1] <= v[2] && v[2] <= v[3] && v[3] <= v[4] && v[4] <= v[5];
+    const float nv = __shfl_down_sync(full, v[0], 1);
+    ok2 = ok2 && (lane == 31 || v[5] <= nv);
+    if (__all_sync(full, ok2)) {
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 6; ++j) outb[6 * lane + j] = v[j];
+      // population std of the samples (run.py:416), two-pass
+      const float mean = warp_sum((sv[0] + sv[1]) + (sv[2] + sv[3])) / (float)Ni;
+      float s2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float d = sv[i] - mean; s2 += d * d; }
+      s2 = warp_sum(s2);
+      if (lane == 0 && z_std) z_std[r] = sqrtf(s2 / (float)Ni);
+      if (z_samples) reinterpret_cast<float4*>(z_samples + r * Ni)[lane] = make_float4(sv[0], sv[1], sv[2], sv[3]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 6; ++j) z_fine[r * (S + Ni) + lane + 32 * j] = outb[lane + 32 * j];
+      return;
+    }
+  }
+  __syncwarp();
+  resample_row_generic(z_vals, weights, RANDOM ? u_in : nullptr, r, S, Ni, Ni, z_samples, z_fine, z_std, row, lane);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -647,6 +831,14 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const bool al = aligned16(z_vals) && aligned16(weights) && (det || aligned16(u)) && (!z_samples || aligned16(z_samples));
+  if (n_samples == 64 && n_importance == 128 && al) {
+    if (det) resample64_kernel<false><<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+                 z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);
+    else resample64_kernel<true><<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
+             z_vals, weights, u, n_rays, z_samples, z_fine, z_std);
+    return check_launch("resample");
+  }
   resample_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
       z_vals, weights, det ? nullptr : u, n_rays, n_samples, n_importance, P, z_samples, z_fine, z_std);
   return check_launch("resample");

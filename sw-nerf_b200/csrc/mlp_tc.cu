@@ -681,6 +681,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             // block j is converted and handed to the MMA thread
             if (TRAIN && wcnt > 0) mbar_wait(&st_done[t], (wcnt - 1) & 1);   // the image's bulk store still reads it
             uint32_t va[32], vb[32];
+            uint32_t masks[4];
             tmem_ld32(acc + hh * 32, va);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -707,7 +708,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
               for (int u = 0; u < 4; ++u)
                 *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) =
                     make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
-              if (TRAIN && tvalid && !(g.ko & 2)) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = mask;
+              masks[j] = mask;
             }
             // one proxy fence and one arrival for the whole layer output: the next layer of this slot is issued after
             // the other slot's layer anyway, and the fence is the expensive part of the hand-off
@@ -717,6 +718,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             if (lane == 0) {
               mbar_arrive_remote(act_full_l + t * 8);
               if (TRAIN) mbar_arrive(&img_ready[t]);
+            }
+            // the sign masks go out AFTER the hand-off: in front of it the proxy fence and the release-arrive would
+            // wait for these global stores (ncu: 15 % of the kernel's stall samples sat on that ERRBAR / arrive)
+            if (TRAIN && tvalid && !(g.ko & 2)) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = masks[j];
             }
           } else {
             // head: cols 0..127 = relu -> h9, col 128 = sigma; rgb = W_rgb h9 + b_rgb in fp32

@@ -882,12 +882,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
             uint8_t* img = s_act + t * ACT_BYTES;
             mbar_wait(&img_ready[t], rc & 1);
-            if (tile < g.num_tiles && !(g.ko & 8)) {
-              if (li < 8) bulk_s2g(ws_tile + WS_H_OFF + li * ACT_BYTES, img, ACT_BYTES);
-              else bulk_s2g(ws_tile + WS_H9_OFF, img, 2 * ACT_BLK);          // h9 in blocks 0,1
+            // one 16-KB bulk store at a time (0.959 -> 0.946 ms against one 64-KB store; 8-KB pieces: no further gain):
+            // the TMA unit also carries the weight ring's loads
+            const int nblk = (li < 8) ? 4 : 2;                                 // h9 sits in blocks 0,1
+            uint8_t* dst = ws_tile + (li < 8 ? WS_H_OFF + li * ACT_BYTES : WS_H9_OFF);
+            for (int j = 0; j < nblk; ++j) {
+              if (tile < g.num_tiles && !(g.ko & 8)) bulk_s2g(dst + j * ACT_BLK, img + j * ACT_BLK, ACT_BLK);
+              bulk_commit();
+              bulk_wait_read0();
             }
-            bulk_commit();
-            bulk_wait_read0();
             mbar_arrive(&st_done[t]);
           }
         }

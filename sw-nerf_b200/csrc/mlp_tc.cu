@@ -692,16 +692,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
               uint32_t pk[16];
               uint32_t mask = 0;
               const float4* b4 = reinterpret_cast<const float4*>(bias + j * 64);
+              if (TRAIN) {
+                // sign masks at two instructions per element: n = -(acc + bias) (negations ride on the FADD), its sign
+                // bit is funnel-shifted into the mask, the fp16 pack takes -n.  Elements go last to first so bit k
+                // ends up being column k.  (An exact +0 pre-activation counts as active: its activation is 0 either way.)
 #pragma unroll
-              for (int i4 = 0; i4 < 8; ++i4) {
-                const float4 bb = b4[i4];                         // warp-uniform constant-cache read
-                float a0 = __uint_as_float(v[4 * i4]) + bb.x, a1 = __uint_as_float(v[4 * i4 + 1]) + bb.y;
-                float a2 = __uint_as_float(v[4 * i4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * i4 + 3]) + bb.w;
-                if (TRAIN)
-                  mask |= (a0 > 0.f ? 1u : 0u) << (4 * i4) | (a1 > 0.f ? 1u : 0u) << (4 * i4 + 1) |
-                          (a2 > 0.f ? 1u : 0u) << (4 * i4 + 2) | (a3 > 0.f ? 1u : 0u) << (4 * i4 + 3);
-                pk[2 * i4] = pack_half2_relu(a0, a1);
-                pk[2 * i4 + 1] = pack_half2_relu(a2, a3);
+                for (int i4 = 7; i4 >= 0; --i4) {
+                  const float4 bb = b4[i4];                       // warp-uniform constant-cache read
+                  const float n0 = -__uint_as_float(v[4 * i4]) - bb.x, n1 = -__uint_as_float(v[4 * i4 + 1]) - bb.y;
+                  const float n2 = -__uint_as_float(v[4 * i4 + 2]) - bb.z, n3 = -__uint_as_float(v[4 * i4 + 3]) - bb.w;
+                  mask = __funnelshift_l(__float_as_uint(n3), mask, 1);
+                  mask = __funnelshift_l(__float_as_uint(n2), mask, 1);
+                  mask = __funnelshift_l(__float_as_uint(n1), mask, 1);
+                  mask = __funnelshift_l(__float_as_uint(n0), mask, 1);
+                  pk[2 * i4] = pack_half2_relu(-n0, -n1);
+                  pk[2 * i4 + 1] = pack_half2_relu(-n2, -n3);
+                }
+              } else {
+#pragma unroll
+                for (int i4 = 0; i4 < 8; ++i4) {
+                  const float4 bb = b4[i4];                       // warp-uniform constant-cache read
+                  float a0 = __uint_as_float(v[4 * i4]) + bb.x, a1 = __uint_as_float(v[4 * i4 + 1]) + bb.y;
+                  float a2 = __uint_as_float(v[4 * i4 + 2]) + bb.z, a3 = __uint_as_float(v[4 * i4 + 3]) + bb.w;
+                  pk[2 * i4] = pack_half2_relu(a0, a1);
+                  pk[2 * i4 + 1] = pack_half2_relu(a2, a3);
+                }
               }
               uint8_t* blk = img + j * ACT_BLK;
 #pragma unroll

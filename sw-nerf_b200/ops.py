@@ -113,6 +113,9 @@ class CompositeFn(torch.autograd.Function):
         ctx.save_for_backward(raw, z_vals, rays, noise, acc, depth)
         ctx.d_col, ctx.white = d_col, bool(white_bkgd)
         ctx.mark_non_differentiable()
+        # outputs the loss does not use (disp, acc, weights, depth in training) reach backward as None instead of
+        # zero-filled tensors: four fill kernels and four gradient streams less per call
+        ctx.set_materialize_grads(False)
         return rgb, disp, acc, weights, depth
 
     @staticmethod
@@ -123,6 +126,8 @@ class CompositeFn(torch.autograd.Function):
         def c(g):
             return None if g is None else ptr(g.contiguous(), F32, "grad")
         keep = [None if g is None else g.contiguous() for g in (g_rgb, g_disp, g_acc, g_w, g_depth)]
+        if all(g is None for g in keep):
+            return None, None, None, None, None, None
         d_raw = torch.empty_like(raw)
         rp, stride = _rays(rays)
         call("swnerf_composite_bwd", raw.data_ptr(), z_vals.data_ptr(), rp, stride, ctx.d_col,

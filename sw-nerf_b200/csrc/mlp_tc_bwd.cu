@@ -337,6 +337,255 @@ __global__ void __launch_bounds__(384, 1) mlp_bwd_data_kernel(BwdArgs g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// 1b. backward data on CTA pairs (cta_group::2), two tile slots per CTA - the structure of mlp_fwd4_kernel:
+// the leader issues M=256 MMAs over both CTAs' dy images and the two halves of each transposed weight chunk
+// (tensor-map loads that report to the leader's barrier), the two slots' layers alternate so one slot's epilogue
+// (TMEM -> ReLU gate -> fp16 -> dy image in place, one proxy fence and one arrival per layer) runs under the other
+// slot's MMAs, completion is multicast.  Shared memory per CTA: 2 x 64 KB dy images + 5 x 16 KB weight ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int NST5 = 5;
+constexpr int S5_ACT = 0;
+constexpr int S5_RING = S5_ACT + 2 * ACT_BYTES;
+constexpr int S5_WRGB = S5_RING + NST5 * (CHUNK_B / 2);
+constexpr int S5_BAR = S5_WRGB + 384 * 4;
+constexpr int S5_TOTAL = S5_BAR + 512 + 1024;
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+mlp_bwd_data_pair_kernel(const __grid_constant__ BwdArgs g, const __grid_constant__ CUtensorMap tm_wt) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_act = smem + S5_ACT;          // [2 slots][4 blocks]
+  uint8_t* s_ring = smem + S5_RING;
+  float* s_wrgb = reinterpret_cast<float*>(smem + S5_WRGB);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S5_BAR);
+  uint64_t* w_full = bars;                 // [NST5] leader: both halves of the stage have landed
+  uint64_t* w_empty = bars + 8;            // [NST5] multicast
+  uint64_t* act_full = bars + 16;          // [2] leader, 16 arrivals: slot's dy image written in both CTAs
+  uint64_t* d_full = bars + 18;            // [2] multicast: slot's accumulator complete
+  uint64_t* img_ready = bars + 20;         // [2] local: image written (store warp)
+  uint64_t* st_done = bars + 22;           // [2] local: image's bulk stores have read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int64_t num_quads = (g.num_tiles + 3) >> 2;
+  const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NST5; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&act_full[t], 16); mbar_init(&d_full[t], 1); mbar_init(&img_ready[t], 8); mbar_init(&st_done[t], 1);
+    }
+    mbar_fence_init();
+  }
+  {
+    const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF) + F32_WRGB;
+    for (int i = threadIdx.x; i < 384; i += blockDim.x) s_wrgb[i] = __ldg(src + i);
+  }
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 10) tmem_alloc_pair<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const float scale = grad_scale_from(g.absmax, g.fixed_scale);
+  const int64_t mask_base = g.num_tiles * WS_TILE_BYTES;
+  const int64_t dy_base = mask_base + g.num_tiles * WS_MASK_BYTES;
+  const uint32_t act_full_l = mapa_u32(smem_u32(act_full), 0);
+
+  // warp roles: 0-7 epilogue | 8 producer | 9 MMA issuer (leader) | 10 TMEM alloc | 11 store
+  if (warp == 8) {
+    if (lane == 0) {
+      const uint32_t w_full_l = mapa_u32(smem_u32(w_full), 0);
+      uint32_t cnt = 0;
+      for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+        int cbase = 0;
+        for (int t = 0; t < 8; ++t) {
+          const int nch = (t == 0) ? 3 : 4;
+          for (int sl = 0; sl < 2; ++sl)
+            for (int ci = 0; ci < nch; ++ci, ++cnt) {
+              const uint32_t stage = cnt % NST5, ph = (cnt / NST5) & 1;
+              mbar_wait(&w_empty[stage], ph ^ 1);
+              if (leader) mbar_expect_tx(&w_full[stage], CHUNK_B);
+              tma_load_2d_pair(s_ring + stage * (CHUNK_B / 2), &tm_wt, 0, (cbase + ci) * 256 + (int)rank * 128,
+                               w_full_l + stage * 8);
+            }
+          cbase += nch;
+        }
+      }
+    }
+  } else if (warp == 9 && leader) {
+    const uint32_t idesc = umma_idesc_f16(256, 256, 0, 0);
+    const uint32_t act_u32 = smem_u32(s_act), ring_u32 = smem_u32(s_ring);
+    uint32_t cnt = 0;
+    for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+      for (int t = 0; t < 8; ++t) {
+        const int nch = (t == 0) ? 3 : 4;
+        for (int sl = 0; sl < 2; ++sl) {
+          // the slot's image (head image for t = 0, dy of the layer above otherwise) is written and its accumulator read
+          mbar_wait_cluster(&act_full[sl], t & 1);
+          const uint32_t d_tmem = tmem + sl * 256;
+          for (int ci = 0; ci < nch; ++ci, ++cnt) {
+            const uint32_t stage = cnt % NST5;
+            mbar_wait(&w_full[stage], (cnt / NST5) & 1);
+            tc_fence_after();
+            const uint32_t a_base = act_u32 + sl * ACT_BYTES + ci * ACT_BLK;
+            const uint32_t b_base = ring_u32 + stage * (CHUNK_B / 2);
+            const int nks = (t == 0 && ci == 2) ? 1 : 4;           // sigma block: only the first 16 columns
+            if (elect_one()) {
+              for (int ks = 0; ks < nks; ++ks)
+                umma_f16_pair(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
+                              (ci > 0 || ks > 0) ? 1u : 0u);
+              umma_commit_pair(&w_empty[stage], 3);
+              if (ci == nch - 1) umma_commit_pair(&d_full[sl], 3);
+            }
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else if (warp < 8) {
+    const int q = warp & 3, hh = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    uint32_t dcnt = 0, wstep = 0;         // d_full completions per slot so far; images written per slot so far
+    const uint32_t* mask0 = reinterpret_cast<const uint32_t*>(g.ws + mask_base);
+    for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+      // ---- head prep of both slots: d_raw -> [dy9 | d_sigma | d_rgb] operand image
+      uint32_t cur_m[2][4];
+#pragma unroll
+      for (int sl = 0; sl < 2; ++sl) {
+        const int64_t tile = quad * 4 + sl * 2 + rank;
+        const bool tvalid = tile < g.num_tiles;
+        const uint32_t* ws_mask = mask0 + tile * (9 * 8 * 128);
+        float4 dr = load_dout(g, tile * TILE + row);
+        dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+        uint32_t hm[2] = {0u, 0u};
+        if (tvalid) {
+          hm[0] = __ldg(ws_mask + (8 * 8 + hh * 2 + 0) * 128 + row);
+          hm[1] = __ldg(ws_mask + (8 * 8 + hh * 2 + 1) * 128 + row);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) cur_m[sl][j] = tvalid ? __ldg(ws_mask + (7 * 8 + j * 2 + hh) * 128 + row) : 0u;
+        if (wstep > 0) mbar_wait(&st_done[sl], (wstep - 1) & 1);     // the previous image's stores have read it
+        uint8_t* img = s_act + sl * ACT_BYTES;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c0 = hh * 64 + jj * 32;
+          const uint32_t m = hm[jj];
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = dr.x * s_wrgb[c0 + i] + dr.y * s_wrgb[128 + c0 + i] + dr.z * s_wrgb[256 + c0 + i];
+            val[i] = (g.kind == 0 && ((m >> i) & 1u)) ? v : 0.f;      // the deformation net has no view branch
+          }
+          uint8_t* blk = img + hh * ACT_BLK;
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(blk + tile_unit_off(row, jj * 4 + u)) =
+                make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
+                           pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
+        }
+        uint8_t* blk = img + (2 + hh) * ACT_BLK;
+        uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
+        if (g.kind == 1) {     // [d_dx0, d_dx1, d_dx2, 0..] in the sigma block; nothing in the rgb block
+          if (hh == 0) { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
+        } else if (hh == 0) u0.x = pack_half2(dr.w, 0.f);
+        else { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
+        *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 0)) = u0;
+        *reinterpret_cast<uint4*>(blk + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_remote(act_full_l + sl * 8); mbar_arrive(&img_ready[sl]); }
+      }
+      ++wstep;
+      // ---- layers 7..0: dh_l (TMEM) gated by the layer's sign bits -> dy_l, in place
+      for (int t = 0; t < 8; ++t, ++dcnt) {
+        const int l = 7 - t;
+#pragma unroll
+        for (int sl = 0; sl < 2; ++sl) {
+          const int64_t tile = quad * 4 + sl * 2 + rank;
+          const bool tvalid = tile < g.num_tiles;
+          const uint32_t* ws_mask = mask0 + tile * (9 * 8 * 128);
+          uint32_t nxt_m[4] = {0u, 0u, 0u, 0u};
+          if (t < 7 && tvalid) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) nxt_m[j] = __ldg(ws_mask + ((l - 1) * 8 + j * 2 + hh) * 128 + row);
+          }
+          mbar_wait(&d_full[sl], dcnt & 1);
+          tc_fence_after();
+          mbar_wait(&st_done[sl], (wstep - 1) & 1);       // the previous image's stores have read it
+          uint8_t* img = s_act + sl * ACT_BYTES;
+          const uint32_t acc = tmem + lane_addr + sl * 256 + hh * 32;
+          uint32_t va[32], vb[32];
+          tmem_ld32(acc, va);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t (&v)[32] = (j & 1) ? vb : va;
+            uint32_t (&vn)[32] = (j & 1) ? va : vb;
+            tmem_ld_wait_on(v);
+            if (j < 3) tmem_ld32(acc + (j + 1) * 64, vn);
+            const uint32_t m = cur_m[sl][j];
+            uint8_t* blk = img + j * ACT_BLK;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              uint32_t pk[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int i = 8 * u + 2 * e;
+                float a = ((m >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+                float b = ((m >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
+                pk[e] = pack_half2(a, b);
+              }
+              *reinterpret_cast<uint4*>(blk + tile_unit_off(row, hh * 4 + u)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            }
+          }
+          fence_async_smem();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) {
+            if (t < 7) mbar_arrive_remote(act_full_l + sl * 8);
+            mbar_arrive(&img_ready[sl]);
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) cur_m[sl][j] = nxt_m[j];
+        }
+        ++wstep;
+      }
+    }
+  } else if (warp == 11) {
+    // dy-image store warp: one image per (slot, step), in 16-KB pieces
+    if (lane == 0) {
+      uint32_t step = 0;
+      for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
+        for (int sidx = 0; sidx < 9; ++sidx, ++step) {        // head image, then layers 7..0
+          for (int sl = 0; sl < 2; ++sl) {
+            const int64_t tile = quad * 4 + sl * 2 + rank;
+            uint8_t* dst = g.ws + dy_base + tile * WS_DY_BYTES + (sidx == 0 ? (size_t)WS_DYH_OFF : (size_t)(8 - sidx) * ACT_BYTES);
+            uint8_t* img = s_act + sl * ACT_BYTES;
+            mbar_wait(&img_ready[sl], step & 1);
+            for (int j = 0; j < 4; ++j) {
+              if (tile < g.num_tiles) bulk_s2g(dst + j * ACT_BLK, img + j * ACT_BLK, ACT_BLK);
+              bulk_commit();
+              bulk_wait_read0();
+            }
+            mbar_arrive(&st_done[sl]);
+          }
+        }
+      }
+      bulk_wait_all0();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 10) tmem_dealloc_pair<512>(tmem);
+}
+
+// ------------------------------------------------------------------------------------------------
 // 2. backward weights
 // ------------------------------------------------------------------------------------------------
 constexpr int WG_MAX_PIECES = 4, WG_MAX_MMA = 5, WG_JOBS = 9;
@@ -999,8 +1248,26 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (g_prof) cudaEventRecord(g_ev[0], s);
-  mlp_bwd_data_kernel<<<grid, 384, SMB_TOTAL, s>>>(b);
-  int rc = check_launch("tc_mlp_bwd_data");
+  int rc = SWNERF_OK;
+  static const int dg_variant = [] { const char* e = getenv("SWNERF_BWD_PAIR"); return e ? atoi(e) : -1; }();
+  if (dg_variant == 1 || (dg_variant < 0 && tiles > 2 * (int64_t)sm_count())) {
+    static std::once_flag once_dg;
+    std::call_once(once_dg, [] {
+      cudaFuncSetAttribute(mlp_bwd_data_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S5_TOTAL);
+    });
+    CUtensorMap tm_wt;
+    const unsigned long long dims[2] = {128, (unsigned long long)NT_CHUNKS * 256};
+    const unsigned long long strides[1] = {128};
+    const unsigned int box[2] = {128, 128};
+    rc = encode_u8_tensor_map(&tm_wt, packed_t, 2, dims, strides, box);
+    if (rc) return rc;
+    const int64_t quads = (tiles + 3) / 4;
+    const int grid_p = 2 * (int)(quads < sm_count() / 2 ? quads : sm_count() / 2);
+    mlp_bwd_data_pair_kernel<<<grid_p, 384, S5_TOTAL, s>>>(b, tm_wt);
+  } else {
+    mlp_bwd_data_kernel<<<grid, 384, SMB_TOTAL, s>>>(b);
+  }
+  rc = check_launch("tc_mlp_bwd_data");
   if (rc) return rc;
 
   if (d_pts) {

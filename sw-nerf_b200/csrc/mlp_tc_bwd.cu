@@ -1131,10 +1131,11 @@ static void build_jobs(WgJob* jobs, int kind) {
   }
 }
 
-static void assign_ctas(int n_cta, int* first, int kind) {
-  // CTAs per job in proportion to the bytes a job streams per tile; the seven 256 x 256 trunk layers (jobs 1..7) run
-  // on the CTA-pair kernel and get no CTAs here
-  const int w[WG_JOBS] = {144, 0, 0, 0, 0, 0, 0, 0, kind == 1 ? 80 : 176};
+static void assign_ctas(int n_cta, int* first, int kind, bool edge_only) {
+  // CTAs per job in proportion to the bytes a job streams per tile; with edge_only the seven 256 x 256 trunk layers
+  // (jobs 1..7) run on the CTA-pair kernel and get no CTAs here
+  const int t = edge_only ? 0 : 128;
+  const int w[WG_JOBS] = {144, t, t, t, t, t, t, t, kind == 1 ? 80 : 176};
   int tot = 0;
   for (int j = 0; j < WG_JOBS; ++j) tot += w[j];
   int cnt[WG_JOBS], used = 0;
@@ -1284,9 +1285,10 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   for (int i = 0; i < 24; ++i) w.grads[i] = i < np ? grads[i] : nullptr;
   int n_cta = sm_count();
   if (n_cta < WG_JOBS) n_cta = WG_JOBS;
-  assign_ctas(n_cta, w.job_first_cta, kind);
+  const bool wg_pair = tiles > 2 * (int64_t)sm_count();      // small launches: every job on the one-CTA kernel
+  assign_ctas(n_cta, w.job_first_cta, kind, wg_pair);
   if (g_prof) cudaEventRecord(g_ev[1], s);
-  {
+  if (wg_pair) {
     // trunk layers: CTA pairs
     static std::once_flag once;
     std::call_once(once, [] {

@@ -77,6 +77,13 @@ int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf,
  * z_samples is returned in ASCENDING order (the reference only uses it through std and the sort). */
 int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
                     int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream);
+/* Kernel used for the 64 + 128 shape of the reference configs: 1 (default) = eight lanes per ray, four rays per
+ * warp; 0 = the first specialisation, one warp per ray.  Both are verified per ray and fall back to the generic
+ * routine, so the results are identical; the switch exists for A/B timing (tools/bench_ray_kernels.py). */
+int swnerf_set_resample_variant(int variant);
+/* Diagnostic (host-synchronising, not for the hot path): number of rays the eight-lane kernel handed to the generic
+ * routine since the last reset.  Well-formed inputs should keep this at a fraction of a percent. */
+int swnerf_resample_fallbacks(unsigned long long* count, int reset, void* stream);
 
 /* ---- a6 (check path): fp32 SIMT GEMM with the nn.Linear epilogue (model.py:43-57).
  *  op 0: C[M,N] = A[M,K] . B[N,K]^T  (+bias[N]) (+C if accumulate) (relu)          forward  x W^T

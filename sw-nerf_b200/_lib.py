@@ -52,6 +52,8 @@ _SIG = {
     "swnerf_tc_selftest": [_I32, _VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "swnerf_tc_probe": [_I32, _I32, _I32, _VP, _VP],
     "swnerf_tc_set_fwd_variant": [_I32],
+    "swnerf_set_resample_variant": [_I32],
+    "swnerf_resample_fallbacks": [_VP, _I32, _VP],
     "swnerf_tc_selftest_pair": [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP],
     "swnerf_tc_mlp_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
 }
@@ -111,6 +113,13 @@ def call(name, *args):
 
 def launch_count(reset=False):
     return int(lib().swnerf_launch_count(1 if reset else 0))
+
+
+def resample_fallbacks(reset=True):
+    """Rays the eight-lane resample kernel handed to its exact generic routine since the last reset (diagnostic)."""
+    n = ctypes.c_ulonglong(0)
+    call("swnerf_resample_fallbacks", ctypes.addressof(n), 1 if reset else 0, stream())
+    return int(n.value)
 
 
 def stream():

@@ -689,6 +689,308 @@ resample64_kernel(const float* __restrict__ z_vals, const float* __restrict__ we
   resample_row_generic(z_vals, weights, RANDOM ? u_in : nullptr, r, S, Ni, Ni, z_samples, z_fine, z_std, row, lane);
 }
 
+// Second specialisation of the 64+128 shape: EIGHT lanes per ray (four rays per warp), so that every shuffle scan,
+// vote and reduction serves four rays and has three steps instead of five.  The kernel is bound by shared-memory
+// wavefronts, not by instruction issue, so the layout is chosen for conflict-free access:
+//   * a lane owns z / weights 8g..8g+7 while the cdf is built, but SAMPLES g, g+8, g+16, ... : at any instruction the
+//     eight lanes of a ray look up neighbouring uniforms, i.e. the same or adjacent cdf entries (broadcast or distinct
+//     banks), and the four rays of a warp sit 8 banks apart (row stride = 8 mod 32);
+//   * the inverse cdf is one BRANCHLESS 6-probe search per sample (the first two probes compare registers);
+//   * what a sample needs after the search sits in ONE 16-byte record per bin {cdf_b, z_mid_b, 1/denom, z_mid_a -
+//     z_mid_b}, stored at k ^ (k >> 3) so that building the records is conflict-free too; 1/denom is the MUFU
+//     reciprocal (1 ulp) - t in [0,1] scales a bin width (~0.06), so a sample moves by < 2e-8, far below one ulp of z;
+//     the pdf is normalised by the correctly rounded reciprocal of the sum (the sum's own rounding already differs from
+//     torch.sum by its order);
+//   * the uniforms of the random mode are sorted in registers (16 per lane, all-ascending bitonic network) and
+//     transposed to the interleaved ownership through shared memory; deterministic uniforms are computed;
+//   * samples scatter to their ranks in a sentinel-filled row, each lane reads 24 consecutive slots back, fills the
+//     holes with the z_vals in order (read from a 9-strided copy, conflict-free) and stores the row itself.
+// Exactness is by construction, guarded by per-ray checks made while the records are built: z_mid[k] < z[k+1]
+// strictly, z_mid_b + (z_mid_a - z_mid_b) <= z_mid_a, cdf non-decreasing, every u >= 0.  With those, t clamped to 1 and
+// ascending uniforms, the samples are ascending and a sample's rank among the z_vals is below + 1 + (s >= z[below+1]).
+// A ray that fails a check (equal or one-ulp-apart z_vals, NaNs) is redone by resample_row_generic.
+__device__ __forceinline__ float lds_f32(unsigned a) {
+  float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v;
+}
+__device__ __forceinline__ float4 lds_f32x4(unsigned a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a));
+  return v;
+}
+__device__ __forceinline__ float rcp_approx(float x) {         // MUFU.RCP, 1 ulp; callers keep x in [1e-5, 1]
+  float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+}
+
+// one probe of the branchless upper-bound search over a float array in shared memory: pa += 4 ST if a[ST-1] <= u
+template <int ST>
+__device__ __forceinline__ void probe_step(unsigned& pa, float uu) {
+  const float cv = lds_f32(pa + 4 * (ST - 1));
+  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
+      : "+r"(pa) : "f"(cv), "f"(uu), "n"(4 * ST));
+}
+
+__device__ __forceinline__ void sort2(float& a, float& b) {
+  const float lo = fminf(a, b), hi = fmaxf(a, b);
+  a = lo; b = hi;
+}
+
+// rays the eight-lane kernel handed to the generic routine since the last reset (diagnostic: swnerf_resample_fallbacks)
+__device__ unsigned long long g_resample_fallbacks = 0ull;
+
+// floats per ray: cdf[64] | z[64] | z 9-strided[72] | rec[64 x 4] (the 136-float transpose buffer of the random mode
+// and, later, the merged row outb[192] alias rec).  456 = 8 mod 32: the four rays of a warp start 8 banks apart.
+constexpr int kQRow = 456;
+constexpr int kQWarps = 4;                 // warps per block (16 rays): 29 KB of shared memory, 7 blocks per SM
+
+template <bool RANDOM>
+__global__ void __launch_bounds__(kQWarps * 32, 6)
+resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
+                   int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std) {
+  constexpr int S = 64, Ni = 128;
+  extern __shared__ __align__(16) float smem[];
+  const unsigned full = 0xffffffffu;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int sub = lane >> 3, g = lane & 7;
+  const int64_t r0 = ((int64_t)blockIdx.x * kQWarps + warp) * 4;
+  if (r0 >= N) return;                                         // whole warp out of range
+  const int64_t r = r0 + sub;
+  const bool valid = r < N;
+  const int64_t rr = valid ? r : N - 1;                        // out-of-range groups shadow the last ray, store nothing
+  float* wbase = smem + (size_t)warp * 4 * kQRow;
+  float* row = wbase + sub * kQRow;
+  float* cdf = row;                                            // [64] (cdf[63] = cdf[62], never probed)
+  float* zs = row + 64;                                        // [64]
+  float* zsw = row + 128;                                      // z[k] at k + (k >> 3)
+  float* recf = row + 200;                                     // record k at (k ^ (k >> 3)) * 4
+  float* outb = recf;                                          // [192], after the last read of the records
+
+  float u[16];
+  if (RANDOM) {
+    const float4* up = reinterpret_cast<const float4*>(u_in + rr * Ni) + 4 * g;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 t = __ldg(up + j);
+      u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
+    }
+  }
+  float ze[10], q[8];
+  {
+    const float4* zp = reinterpret_cast<const float4*>(z_vals + rr * S) + 2 * g;
+    const float4* wp = reinterpret_cast<const float4*>(weights + rr * S) + 2 * g;
+    const float4 a = __ldg(zp), b = __ldg(zp + 1), c = __ldg(wp), d = __ldg(wp + 1);
+    ze[0] = a.x; ze[1] = a.y; ze[2] = a.z; ze[3] = a.w; ze[4] = b.x; ze[5] = b.y; ze[6] = b.z; ze[7] = b.w;
+    q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w; q[4] = d.x; q[5] = d.y; q[6] = d.z; q[7] = d.w;
+  }
+  if (RANDOM) {
+    // bitonic sort of the ray's 128 uniforms, element e = 16 g + i, in the all-ascending form: each merge of size k
+    // starts with the mirror step (e against e ^ (k-1)) and continues with the strides k/4 .. 1, and the lower
+    // index always keeps the minimum, so comparators inside a lane have no run-time direction
+#pragma unroll
+    for (int k = 2; k <= Ni; k <<= 1) {
+      if (k <= 16) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          if ((i & (k >> 1)) == 0) sort2(u[i], u[i ^ (k - 1)]);
+        }
+      } else {
+        const bool keep_min = (g & (k >> 5)) == 0;              // bit k/2 of e clear
+        float o[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] = __shfl_xor_sync(full, u[15 - i], (k >> 4) - 1);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) u[i] = keep_min ? fminf(u[i], o[i]) : fmaxf(u[i], o[i]);
+      }
+#pragma unroll
+      for (int j = k >> 2; j > 0; j >>= 1) {
+        if (j >= 16) {
+          const bool keep_min = (g & (j >> 4)) == 0;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float o = __shfl_xor_sync(full, u[i], j >> 4);
+            u[i] = keep_min ? fminf(u[i], o) : fmaxf(u[i], o);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if ((i & j) == 0) sort2(u[i], u[i | j]);
+          }
+        }
+      }
+    }
+    // blocked (16 g + i) -> interleaved (g + 8 i) ownership through shared memory, element e at e + (e >> 4)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) recf[17 * g + i] = u[i];
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 16; ++i) u[i] = recf[g + 8 * i + (i >> 1)];
+    __syncwarp();
+  } else {
+    // torch.linspace(0, 1, 128), symmetric evaluation (linspace01), sample j = g + 8 i
+    const float step = 1.0f / (float)(Ni - 1), fg = (float)g;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) u[i] = __fmul_rn(step, fg + (float)(8 * i));
+#pragma unroll
+    for (int i = 8; i < 16; ++i) u[i] = __fsub_rn(1.0f, __fmul_rn(step, (float)(Ni - 1 - 8 * i) - fg));
+  }
+
+  bool ok = true;
+  ze[8] = __shfl_down_sync(full, ze[0], 1);
+  ze[9] = __shfl_down_sync(full, ze[1], 1);
+  if (g == 7) { ze[8] = ze[7]; ze[9] = ze[7]; }
+  reinterpret_cast<float4*>(zs)[2 * g] = make_float4(ze[0], ze[1], ze[2], ze[3]);
+  reinterpret_cast<float4*>(zs)[2 * g + 1] = make_float4(ze[4], ze[5], ze[6], ze[7]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) zsw[9 * g + i] = ze[i];
+  // pdf over weights[1..62] (ray.py:111-112); with q[0] = q[63] = 0, cdf[k] = inclusive prefix of q at k (ray.py:113-114)
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = __fadd_rn(q[i], 1e-5f);
+  if (g == 0) q[0] = 0.f;
+  if (g == 7) q[7] = 0.f;
+  float tot = ((q[0] + q[1]) + (q[2] + q[3])) + ((q[4] + q[5]) + (q[6] + q[7]));
+  tot += __shfl_xor_sync(full, tot, 1);
+  tot += __shfl_xor_sync(full, tot, 2);
+  tot += __shfl_xor_sync(full, tot, 4);
+  const float rtot = __frcp_rn(tot);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = __fmul_rn(q[i], rtot);
+#pragma unroll
+  for (int i = 1; i < 8; ++i) q[i] = __fadd_rn(q[i - 1], q[i]);          // local inclusive prefix, non-decreasing
+  float inc = q[7];
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const float t = __shfl_up_sync(full, inc, o, 8);
+    if (g >= o) inc += t;
+  }
+  float ex = __shfl_up_sync(full, inc, 1, 8);
+  if (g == 0) ex = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q[i] = __fadd_rn(ex, q[i]);
+  reinterpret_cast<float4*>(cdf)[2 * g] = make_float4(q[0], q[1], q[2], q[3]);
+  reinterpret_cast<float4*>(cdf)[2 * g + 1] = make_float4(q[4], q[5], q[6], q[7]);
+  {
+    float cnext = __shfl_down_sync(full, q[0], 1);             // cdf[8g + 8]
+    if (g == 7) cnext = q[7];
+    ok = ok && (q[7] <= cnext);                                // non-decreasing across lanes (inside: by construction)
+    float m[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) m[i] = __fmul_rn(0.5f, __fadd_rn(ze[i + 1], ze[i]));   // z_mid, run.py:396
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int k = 8 * g + i;                                 // bin k: below = k, above = k + 1 (ray.py:137-151)
+      float denom = __fsub_rn(i < 7 ? q[i + 1] : cnext, q[i]);
+      if (denom < 1e-5f) denom = 1.f;                          // ray.py:149
+      float rden = rcp_approx(denom);
+      float dbin = __fsub_rn(m[i + 1], m[i]);
+      const bool last = (g == 7) && (i >= 6);                  // k = 62: below = above (u >= cdf[62]); k = 63 unused
+      if (last) { rden = 1.f; dbin = 0.f; }
+      ok = ok && ((g == 7 && i == 7) || m[i] < ze[i + 1]);
+      ok = ok && (last || __fadd_rn(m[i], dbin) <= m[i + 1]);
+      reinterpret_cast<float4*>(recf)[k ^ g] = make_float4(q[i], m[i], rden, dbin);
+    }
+  }
+  __syncwarp();
+
+  // inverse cdf (ray.py:136-151) and the sample's rank among the z_vals
+  const unsigned cdf_sa = (unsigned)__cvta_generic_to_shared(cdf);
+  const unsigned zs_sa = (unsigned)__cvta_generic_to_shared(zs);
+  const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(recf);
+  const float c15 = cdf[15], c31 = cdf[31], c47 = cdf[47];
+  float sv[16];
+  int pos[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float uu = u[i];
+    // number of cdf entries <= u (searchsorted right=True) as a byte address: the first two probes hit registers
+    unsigned pa = cdf_sa;
+    asm("{\n\t.reg .pred p;\n\t.reg .f32 c;\n\t"
+        "setp.le.f32 p, %1, %4;\n\t@p add.u32 %0, %0, 128;\n\tselp.f32 c, %3, %2, p;\n\t"
+        "setp.le.f32 p, c, %4;\n\t@p add.u32 %0, %0, 64;\n\t}"
+        : "+r"(pa) : "f"(c31), "f"(c15), "f"(c47), "f"(uu));
+    probe_step<8>(pa, uu); probe_step<4>(pa, uu); probe_step<2>(pa, uu); probe_step<1>(pa, uu);
+    const unsigned pb = pa - cdf_sa;                           // 4 x count
+    ok = ok && (pb != 0);                                      // u >= cdf[0] = 0
+    const unsigned x = max(pb, 4u) - 4u;                       // 4 x below (ray.py:137)
+    const float z1 = lds_f32(zs_sa + x + 4);                   // z[below + 1]
+    const float4 rb = lds_f32x4(rec_sa + ((x << 2) ^ ((x >> 1) & 0x70u)));
+    const float t = fminf(__fmul_rn(__fsub_rn(uu, rb.x), rb.z), 1.f);
+    const float s = __fadd_rn(rb.y, __fmul_rn(t, rb.w));       // ray.py:151
+    sv[i] = s;
+    pos[i] = g + 8 * i + (int)(x >> 2) + 1 + (s >= z1 ? 1 : 0);
+  }
+  const unsigned okmask = __ballot_sync(full, ok);
+  __syncwarp();                                                // every read of the records precedes the writes below
+  const bool st_ok = valid && ((okmask >> (8 * sub)) & 0xffu) == 0xffu;
+
+  // merged row: samples scatter to their ranks, the z_vals fill the holes in order
+  const int SENT = 0x7fc00123;
+  {
+    const float sn = __int_as_float(SENT);
+#pragma unroll
+    for (int j = 0; j < 6; ++j) reinterpret_cast<float4*>(outb)[g + 8 * j] = make_float4(sn, sn, sn, sn);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 16; ++i) outb[pos[i]] = sv[i];           // pos in [0, 192) whatever the data
+  __syncwarp();
+  float v[24];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const float4 t = reinterpret_cast<const float4*>(outb)[6 * g + j];
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+  int ns = 0;
+#pragma unroll
+  for (int j = 0; j < 24; ++j) ns += (__float_as_int(v[j]) != SENT) ? 1 : 0;
+  int before = ns;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const int t = __shfl_up_sync(full, before, o, 8);
+    if (g >= o) before += t;
+  }
+  int zi = 24 * g - (before - ns);                             // next z_val to place; stays inside the row on bad rays
+#pragma unroll
+  for (int j = 0; j < 24; ++j) {
+    if (__float_as_int(v[j]) == SENT) { v[j] = zsw[zi + (zi >> 3)]; ++zi; }
+  }
+  // population std of the samples (run.py:416), two-pass
+  float s1 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s1 += sv[i];
+  s1 += __shfl_xor_sync(full, s1, 1);
+  s1 += __shfl_xor_sync(full, s1, 2);
+  s1 += __shfl_xor_sync(full, s1, 4);
+  const float mean = s1 / (float)Ni;
+  float s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { const float d = sv[i] - mean; s2 += d * d; }
+  s2 += __shfl_xor_sync(full, s2, 1);
+  s2 += __shfl_xor_sync(full, s2, 2);
+  s2 += __shfl_xor_sync(full, s2, 4);
+  if (st_ok) {
+    if (g == 0 && z_std) z_std[r] = sqrtf(s2 / (float)Ni);
+    if (z_samples) {
+      float* zo = z_samples + r * Ni + g;                      // 32-B runs per ray and instruction
+#pragma unroll
+      for (int i = 0; i < 16; ++i) zo[8 * i] = sv[i];
+    }
+    float4* fo = reinterpret_cast<float4*>(z_fine + r * (S + Ni)) + 6 * g;             // 96 B per lane
+#pragma unroll
+    for (int j = 0; j < 6; ++j) fo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (okmask == full) return;
+  // rays that failed a check: the exact generic routine, one ray at a time on the whole warp
+  __syncwarp();
+#pragma unroll 1
+  for (int sb = 0; sb < 4; ++sb) {
+    if (((okmask >> (8 * sb)) & 0xffu) == 0xffu || r0 + sb >= N) continue;
+    if (lane == 0) atomicAdd(&g_resample_fallbacks, 1ull);
+    resample_row_generic(z_vals, weights, RANDOM ? u_in : nullptr, r0 + sb, S, Ni, Ni, z_samples, z_fine, z_std,
+                         wbase, lane);
+    __syncwarp();
+  }
+}
+
+
 // ---------------------------------------------------------------------------------------------
 // a13  torchsearchsorted-compatible batched search              searchsorted_cuda_kernel.cu:83-107
 // ---------------------------------------------------------------------------------------------
@@ -710,6 +1012,7 @@ __global__ void searchsorted_kernel(const float* __restrict__ a, const float* __
   out[idx] = lo;
 }
 
+static int g_resample_variant = 1;      // 64+128 shape: 1 = resample64q_kernel (default), 0 = resample64_kernel
 static inline int next_pow2(int x) { int p = 1; while (p < x) p <<= 1; return p; }
 
 }  // namespace swnerf
@@ -819,6 +1122,25 @@ int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf,
   return check_launch("sample_pdf");
 }
 
+int swnerf_set_resample_variant(int variant) {
+  SW_REQUIRE(variant == 0 || variant == 1, "set_resample_variant: 0 (one warp per ray) or 1 (eight lanes per ray)");
+  g_resample_variant = variant;
+  return SWNERF_OK;
+}
+
+int swnerf_resample_fallbacks(unsigned long long* count, int reset, void* stream) {
+  SW_REQUIRE(count, "resample_fallbacks: null pointer");
+  cudaStream_t s = (cudaStream_t)stream;
+  cudaError_t e = cudaStreamSynchronize(s);
+  if (e == cudaSuccess) e = cudaMemcpyFromSymbol(count, g_resample_fallbacks, sizeof(unsigned long long));
+  if (e == cudaSuccess && reset) {
+    const unsigned long long zero = 0ull;
+    e = cudaMemcpyToSymbol(g_resample_fallbacks, &zero, sizeof(zero));
+  }
+  if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "resample_fallbacks: %s", cudaGetErrorString(e));
+  return SWNERF_OK;
+}
+
 int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
                     int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream) {
   SW_REQUIRE(z_vals && weights && z_fine, "resample: null pointer");
@@ -832,6 +1154,22 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const bool al = aligned16(z_vals) && aligned16(weights) && (det || aligned16(u)) && (!z_samples || aligned16(z_samples));
+  if (n_samples == 64 && n_importance == 128 && al && aligned16(z_fine) && g_resample_variant != 0) {
+    // eight lanes per ray, four rays per warp
+    const size_t qsmem = (size_t)kQWarps * 4 * kQRow * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      cudaFuncSetAttribute(resample64q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      cudaFuncSetAttribute(resample64q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      attr_done = true;
+    }
+    const unsigned qblocks = (unsigned)((n_rays + 4 * kQWarps - 1) / (4 * kQWarps));
+    if (det) resample64q_kernel<false><<<qblocks, kQWarps * 32, qsmem, (cudaStream_t)stream>>>(
+                 z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);
+    else resample64q_kernel<true><<<qblocks, kQWarps * 32, qsmem, (cudaStream_t)stream>>>(
+             z_vals, weights, u, n_rays, z_samples, z_fine, z_std);
+    return check_launch("resample");
+  }
   if (n_samples == 64 && n_importance == 128 && al) {
     if (det) resample64_kernel<false><<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
                  z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);

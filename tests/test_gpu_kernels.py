@@ -170,13 +170,32 @@ def test_sample_pdf_from_weights(golden):
 
 @pytest.mark.parametrize("N,S_,Ni,det", [(513, 64, 128, True), (513, 64, 128, False), (77, 64, 64, False),
                                         (33, 16, 7, False), (4096, 64, 128, False)])
-def test_resample(N, S_, Ni, det):
+@pytest.mark.parametrize("variant", [1, 0])
+def test_resample(N, S_, Ni, det, variant):
+    """variant: kernel of the 64+128 shape (1 = eight lanes per ray, the default; 0 = one warp per ray); other
+    shapes always run the generic kernel."""
+    if variant == 0 and (S_, Ni) != (64, 128):
+        pytest.skip("variant only concerns the 64+128 shape")
     rs = np.random.RandomState(N + Ni)
     z = np.sort(rs.uniform(2, 6, size=(N, S_)).astype(np.float32), -1)
     w = (rs.uniform(0, 1, size=(N, S_)).astype(np.float32)) ** 6
     w[0] = 0
+    # degenerate rays (the verified fast paths must hand them to the exact routine): all z equal, z one ulp apart,
+    # one dominant bin, and a pair of equal neighbours
     u = rs.rand(N, Ni).astype(np.float32)
-    zs, zf, zstd = ops.resample(T(z), T(w), Ni, det=det, u=None if det else T(u))
+    if N >= 77:
+        z[1] = 3.0
+        z[2] = np.float32(3.0) + np.arange(S_, dtype=np.float32) * np.spacing(np.float32(3.0))
+        w[3] = 0; w[3, S_ // 2] = 1.0
+        z[4, S_ // 2 + 1] = z[4, S_ // 2]
+        u[5, 0] = 0.0
+    from swnerf_b200 import _lib
+    _lib.call("swnerf_set_resample_variant", variant)
+    try:
+        zs, zf, zstd = ops.resample(T(z), T(w), Ni, det=det, u=None if det else T(u))
+        torch.cuda.synchronize()
+    finally:
+        _lib.call("swnerf_set_resample_variant", 1)
     zt, wt = torch.from_numpy(z), torch.from_numpy(w)
     z_mid = 0.5 * (zt[:, 1:] + zt[:, :-1])
     zs_ref = O.sample_pdf(z_mid, wt[:, 1:-1], Ni, det=det, u=None if det else torch.from_numpy(u))
@@ -189,3 +208,32 @@ def test_resample(N, S_, Ni, det):
     assert bool((zf_c[:, 1:] >= zf_c[:, :-1]).all())
     assert torch.equal(zf_c, torch.sort(torch.cat([zt, zs_c], -1), -1)[0])
     close(zstd, torch.std(zs_c, dim=-1, unbiased=False), rtol=1e-4, atol=1e-6)
+
+
+def test_resample_variants_agree_at_render_size():
+    """The two kernels of the 64+128 shape on a 32,768-ray render chunk (+3 so the last warp is ragged): identical
+    merged rows up to the samples' own rounding (the pdf is normalised by a reciprocal in one and a division in the
+    other), both exactly sorted and exactly the multiset union."""
+    from swnerf_b200 import _lib
+    N = 32768 + 3
+    _lib.resample_fallbacks(reset=True)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    z = torch.sort(torch.rand(N, 64, device="cuda", generator=g) * 4 + 2, -1)[0]
+    w = torch.rand(N, 64, device="cuda", generator=g) ** 4
+    u = torch.rand(N, 128, device="cuda", generator=g)
+    outs = {}
+    for det in (True, False):
+        for variant in (0, 1):
+            _lib.call("swnerf_set_resample_variant", variant)
+            try:
+                outs[(det, variant)] = ops.resample(z, w, 128, det=det, u=None if det else u)
+            finally:
+                _lib.call("swnerf_set_resample_variant", 1)
+        (zs0, zf0, sd0), (zs1, zf1, sd1) = outs[(det, 0)], outs[(det, 1)]
+        for zs_, zf_ in ((zs0, zf0), (zs1, zf1)):
+            assert bool((zf_[:, 1:] >= zf_[:, :-1]).all())
+            assert torch.equal(zf_, torch.sort(torch.cat([z, zs_], -1), -1)[0])
+        assert float(((zs0 - zs1).abs() > 1e-4).float().mean()) < 1e-3
+        # z_std follows the samples: a sample that changes bin moves by a bin width
+        assert float(((sd0 - sd1).abs() > 1e-3 * sd0.abs() + 1e-5).float().mean()) < 2e-2
+    assert _lib.resample_fallbacks() < 0.01 * N          # well-formed rays stay on the fast path

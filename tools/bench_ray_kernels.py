@@ -50,9 +50,12 @@ for N in (4096, 32768, 262144):
     w = torch.rand(N, 64, device=dev)
     zs = torch.empty(N, 128, device=dev); zf = torch.empty(N, 192, device=dev); zstd = torch.empty(N, device=dev)
     u = torch.rand(N, 128, device=dev)
-    ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), None, 1, N, 64, 128, zs.data_ptr(), zf.data_ptr(), zstd.data_ptr(), st()))
-    b = N * 4 * (64 + 64 + 128 + 192 + 1)
-    print("resample(det)  N=%6d        %8.3f ms  %7.1f GB/s  %.2f" % (N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
-    ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), u.data_ptr(), 0, N, 64, 128, zs.data_ptr(), zf.data_ptr(), zstd.data_ptr(), st()))
-    b = N * 4 * (64 + 64 + 128 + 128 + 192 + 1)
-    print("resample(rand) N=%6d        %8.3f ms  %7.1f GB/s  %.2f" % (N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
+    for variant in (0, 1):        # 0: one warp per ray, 1: eight lanes per ray (default)
+        call("swnerf_set_resample_variant", variant)
+        ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), None, 1, N, 64, 128, zs.data_ptr(), zf.data_ptr(), zstd.data_ptr(), st()))
+        b = N * 4 * (64 + 64 + 128 + 192 + 1)
+        print("resample(det)  v%d N=%6d        %8.3f ms  %7.1f GB/s  %.2f" % (variant, N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
+        ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), u.data_ptr(), 0, N, 64, 128, zs.data_ptr(), zf.data_ptr(), zstd.data_ptr(), st()))
+        b = N * 4 * (64 + 64 + 128 + 128 + 192 + 1)
+        print("resample(rand) v%d N=%6d        %8.3f ms  %7.1f GB/s  %.2f" % (variant, N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
+    call("swnerf_set_resample_variant", 1)

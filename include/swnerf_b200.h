@@ -86,12 +86,19 @@ int swnerf_set_resample_variant(int variant);
 int swnerf_resample_fallbacks(unsigned long long* count, int reset, void* stream);
 
 /* ---- a6 (check path): fp32 SIMT GEMM with the nn.Linear epilogue (model.py:43-57).
- *  op 0: C[M,N] = A[M,K] . B[N,K]^T  (+bias[N]) (+C if accumulate) (relu)          forward  x W^T
- *  op 1: C[M,N] = A[M,K] . B[K,N]    (+C if accumulate) (zero where mask[m,n] <= 0)  dgrad    dy W
- *  op 2: C[M,N] (+)= A[K,M]^T . B[K,N]                                              wgrad    dy^T x */
+ *  op 0: C[M,N] = A[M,K] . B[N,K]^T  (+bias[N]) (+C if accumulate) (activation)     forward  x W^T
+ *  op 1: C[M,N] = A[M,K] . B[K,N]    (+C if accumulate) (times act'(mask[m,n]))      dgrad    dy W
+ *  op 2: C[M,N] (+)= A[K,M]^T . B[K,N]                                              wgrad    dy^T x
+ * act_flags: bits 0-1 = epilogue activation (0 none, 1 ReLU as model.py:43, 2 ELU as TNeRF's layers,
+ * model.py:163-171); bits 4-5 = how `mask` (the saved activation OUTPUT) scales the result: 0 ReLU' = (mask > 0),
+ * 1 ELU' = (mask > 0 ? 1 : mask + 1).  The values 0 / 1 keep the earlier relu-flag meaning. */
 int swnerf_sgemm(int op, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
-                 int64_t N, int64_t K, const float* bias, int accumulate, int relu, const float* mask,
+                 int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
                  int64_t ldmask, void* stream);
+/* out[rows, cols] = d * act'(y) from the activation's output y; kind 0 ReLU, 1 ELU (TNeRF's colour head ends in a
+ * ReLU, model.py:183-186). */
+int swnerf_act_bwd(const float* d, int64_t ldd, const float* y, int64_t ldy, int64_t rows, int cols, int kind,
+                   float* out, int64_t ldo, void* stream);
 /* out[cols] (+)= sum over rows of x[rows, ld]  (bias gradients). */
 int swnerf_colsum(const float* x, int64_t ld, int64_t rows, int cols, float* out, int accumulate, void* stream);
 

@@ -837,8 +837,13 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   ze[8] = __shfl_down_sync(full, ze[0], 1);
   ze[9] = __shfl_down_sync(full, ze[1], 1);
   if (g == 7) { ze[8] = ze[7]; ze[9] = ze[7]; }
-  reinterpret_cast<float4*>(zs)[2 * g] = make_float4(ze[0], ze[1], ze[2], ze[3]);
-  reinterpret_cast<float4*>(zs)[2 * g + 1] = make_float4(ze[4], ze[5], ze[6], ze[7]);
+  // a lane's two float4 go out in swapped order in the upper half of the group (lanes g and g+4 share bank groups)
+  const bool hi = g >= 4;
+  {
+    const float4 a = make_float4(ze[0], ze[1], ze[2], ze[3]), b = make_float4(ze[4], ze[5], ze[6], ze[7]);
+    reinterpret_cast<float4*>(zs)[2 * g + (hi ? 1 : 0)] = hi ? b : a;
+    reinterpret_cast<float4*>(zs)[2 * g + (hi ? 0 : 1)] = hi ? a : b;
+  }
 #pragma unroll
   for (int i = 0; i < 8; ++i) zsw[9 * g + i] = ze[i];
   // pdf over weights[1..62] (ray.py:111-112); with q[0] = q[63] = 0, cdf[k] = inclusive prefix of q at k (ray.py:113-114)
@@ -865,8 +870,11 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   if (g == 0) ex = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = __fadd_rn(ex, q[i]);
-  reinterpret_cast<float4*>(cdf)[2 * g] = make_float4(q[0], q[1], q[2], q[3]);
-  reinterpret_cast<float4*>(cdf)[2 * g + 1] = make_float4(q[4], q[5], q[6], q[7]);
+  {
+    const float4 a = make_float4(q[0], q[1], q[2], q[3]), b = make_float4(q[4], q[5], q[6], q[7]);
+    reinterpret_cast<float4*>(cdf)[2 * g + (hi ? 1 : 0)] = hi ? b : a;
+    reinterpret_cast<float4*>(cdf)[2 * g + (hi ? 0 : 1)] = hi ? a : b;
+  }
   {
     float cnext = __shfl_down_sync(full, q[0], 1);             // cdf[8g + 8]
     if (g == 7) cnext = q[7];
@@ -932,11 +940,18 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
 #pragma unroll
   for (int i = 0; i < 16; ++i) outb[pos[i]] = sv[i];           // pos in [0, 192) whatever the data
   __syncwarp();
+  // each lane takes 24 consecutive slots (six float4 at 6g .. 6g+5).  Lanes g and g+4 would meet in the same 16-byte
+  // bank group, so the upper half of the group walks its six float4 one step ahead (j+1 mod 6): conflict-free
   float v[24];
+  {
+    float4 t[6];
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const float4 t = reinterpret_cast<const float4*>(outb)[6 * g + j];
-    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+    for (int j = 0; j < 6; ++j) t[j] = reinterpret_cast<const float4*>(outb)[6 * g + (hi ? (j + 1) % 6 : j)];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {                              // t[j] of an upper lane is its float4 (j+1) % 6
+      const float4 a = t[j], b = t[(j + 5) % 6];
+      v[4 * j] = hi ? b.x : a.x; v[4 * j + 1] = hi ? b.y : a.y; v[4 * j + 2] = hi ? b.z : a.z; v[4 * j + 3] = hi ? b.w : a.w;
+    }
   }
   int ns = 0;
 #pragma unroll
@@ -966,6 +981,14 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   s2 += __shfl_xor_sync(full, s2, 1);
   s2 += __shfl_xor_sync(full, s2, 2);
   s2 += __shfl_xor_sync(full, s2, 4);
+  // the row goes back to shared memory (same rotated order) so that the global stores are 128-byte runs per ray
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
+    const int a = 4 * j, b = 4 * ((j + 1) % 6);
+    reinterpret_cast<float4*>(outb)[6 * g + (hi ? (j + 1) % 6 : j)] =
+        make_float4(hi ? v[b] : v[a], hi ? v[b + 1] : v[a + 1], hi ? v[b + 2] : v[a + 2], hi ? v[b + 3] : v[a + 3]);
+  }
+  __syncwarp();
   if (st_ok) {
     if (g == 0 && z_std) z_std[r] = sqrtf(s2 / (float)Ni);
     if (z_samples) {
@@ -973,9 +996,9 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
 #pragma unroll
       for (int i = 0; i < 16; ++i) zo[8 * i] = sv[i];
     }
-    float4* fo = reinterpret_cast<float4*>(z_fine + r * (S + Ni)) + 6 * g;             // 96 B per lane
+    float4* fo = reinterpret_cast<float4*>(z_fine + r * (S + Ni));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) fo[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    for (int j = 0; j < 6; ++j) fo[g + 8 * j] = reinterpret_cast<const float4*>(outb)[g + 8 * j];
   }
   if (okmask == full) return;
   // rays that failed a check: the exact generic routine, one ray at a time on the whole warp

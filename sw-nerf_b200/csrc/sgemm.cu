@@ -17,7 +17,9 @@ struct GemmArgs {
   int64_t M, N, K;
   const float* bias;                  // [N] or null
   const float* mask; int64_t ldmask;  // C *= (mask[m,n] > 0) or null
-  int accumulate, relu;
+  int accumulate;
+  int act;                            // epilogue activation: 0 none, 1 ReLU, 2 ELU(alpha=1)
+  int mask_kind;                      // 0: C *= (mask > 0) (ReLU'), 1: C *= (mask > 0 ? 1 : mask + 1) (ELU' from its output)
   int64_t k_per_split;                // split-K slab (atomics when gridDim.z > 1)
 };
 
@@ -84,11 +86,26 @@ __global__ void __launch_bounds__(NT) sgemm_kernel(GemmArgs g) {
       if (split) { atomicAdd(c, v); continue; }
       if (g.bias) v += __ldg(g.bias + n);
       if (g.accumulate) v += *c;
-      if (g.relu) v = fmaxf(v, 0.f);
-      if (g.mask) v = (__ldg(g.mask + m * g.ldmask + n) > 0.f) ? v : 0.f;
+      if (g.act == 1) v = fmaxf(v, 0.f);
+      else if (g.act == 2) v = v > 0.f ? v : expm1f(v);
+      if (g.mask) {
+        const float y = __ldg(g.mask + m * g.ldmask + n);
+        v = (y > 0.f) ? v : (g.mask_kind == 1 ? v * (y + 1.f) : 0.f);
+      }
       *c = v;
     }
   }
+}
+
+// d_out[m,n] = d[m,n] * act'(y[m,n]) from the activation's OUTPUT y: kind 0 ReLU (y > 0), kind 1 ELU (y > 0 ? 1 : y + 1)
+__global__ void act_bwd_kernel(const float* __restrict__ d, int64_t ldd, const float* __restrict__ y, int64_t ldy,
+                               int64_t rows, int cols, int kind, float* __restrict__ out, int64_t ldo) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= rows * cols) return;
+  const int64_t m = idx / cols;
+  const int n = (int)(idx - m * cols);
+  const float yv = __ldg(y + m * ldy + n), dv = __ldg(d + m * ldd + n);
+  out[m * ldo + n] = (yv > 0.f) ? dv : (kind == 1 ? dv * (yv + 1.f) : 0.f);
 }
 
 // out[n] (+)= sum_m x[m*ld + n]
@@ -118,15 +135,17 @@ using namespace swnerf;
 extern "C" {
 
 int swnerf_sgemm(int op, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
-                 int64_t N, int64_t K, const float* bias, int accumulate, int relu, const float* mask,
+                 int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
                  int64_t ldmask, void* stream) {
+  const int relu = act_flags & 3, mask_kind = (act_flags >> 4) & 3;
   SW_REQUIRE(A && B && C, "sgemm: null pointer");
+  SW_REQUIRE(relu <= 2 && mask_kind <= 1 && (act_flags & ~0x33) == 0, "sgemm: bad act_flags");
   SW_REQUIRE(op >= 0 && op <= 2, "sgemm: op must be 0 (x W^T), 1 (dy W) or 2 (dy^T x)");
   SW_REQUIRE(M >= 0 && N >= 0 && K >= 0, "sgemm: negative size");
   if (M == 0 || N == 0) return SWNERF_OK;
   GemmArgs g;
   g.A = A; g.B = B; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
-  g.bias = bias; g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate; g.relu = relu;
+  g.bias = bias; g.mask = mask; g.ldmask = ldmask; g.accumulate = accumulate; g.act = relu; g.mask_kind = mask_kind;
   g.k_per_split = K > 0 ? K : 1;
   dim3 grid((unsigned)((N + BN - 1) / BN), (unsigned)((M + BM - 1) / BM), 1);
   cudaStream_t s = (cudaStream_t)stream;
@@ -158,6 +177,17 @@ int swnerf_sgemm(int op, const float* A, int64_t lda, const float* B, int64_t ld
     sgemm_kernel<false, false><<<grid, NT, 0, s>>>(g);
   }
   return check_launch("sgemm");
+}
+
+int swnerf_act_bwd(const float* d, int64_t ldd, const float* y, int64_t ldy, int64_t rows, int cols, int kind,
+                   float* out, int64_t ldo, void* stream) {
+  SW_REQUIRE(d && y && out, "act_bwd: null pointer");
+  SW_REQUIRE(kind == 0 || kind == 1, "act_bwd: kind must be 0 (ReLU) or 1 (ELU)");
+  SW_REQUIRE(rows >= 0 && cols >= 0, "act_bwd: negative size");
+  if (rows == 0 || cols == 0) return SWNERF_OK;
+  const int64_t n = rows * cols;
+  act_bwd_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d, ldd, y, ldy, rows, cols, kind, out, ldo);
+  return check_launch("act_bwd");
 }
 
 int swnerf_colsum(const float* x, int64_t ld, int64_t rows, int cols, float* out, int accumulate, void* stream) {

@@ -187,7 +187,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
     dev = ray_batch.device
     view_col = C - 3 if C > 9 else -1                                             # run_dnerf.py:402
     cur_time = _host_time(ray_batch)
-    z_samples = z_std = None
+    z_std = None
     rgb_map_0 = disp_map_0 = acc_map_0 = position_delta_0 = None
 
     if z_vals is None:                                                            # run_dnerf.py:408
@@ -209,7 +209,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                     _, _, _, weights, _ = ops.composite(raw, z_vals, ray_batch, 3, noise, white_bkgd)
             det = (perturb == 0.)
             u = pytest_uniform([N_rays, N_importance], dev) if (pytest and not det) else None
-            z_samples, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u)
+            _, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u, want_samples=False)
     else:
         z_vals = z_vals.contiguous().float()
 
@@ -231,7 +231,7 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
             ret['acc0'] = acc_map_0
         if position_delta_0 is not None:
             ret['position_delta_0'] = position_delta_0
-        if z_samples is not None:
+        if z_std is not None:
             ret['z_std'] = z_std
     return ret
 

@@ -158,19 +158,20 @@ def sample_pdf(bins, weights, n_samples: int, det=False, u=None, cdf=None, retur
     return (samples, inds) if return_inds else samples
 
 
-def resample(z_vals, weights, n_importance: int, det=False, u=None):
+def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples=True):
     """Returns (z_samples, z_fine, z_std): nerf/run.py:396-400 and :416.  z_samples comes back in ascending
-    order (the reference uses it only through std() and the sort, both order-free)."""
+    order (the reference uses it only through std() and the sort, both order-free); render_rays passes
+    want_samples=False - it only needs z_std, which the kernel computes itself - and gets None for it."""
     N, S = z_vals.shape
     dev = z_vals.device
     if not det and u is None:
         u = torch.rand((N, n_importance), dtype=F32, device=dev)
-    z_samples = torch.empty((N, n_importance), dtype=F32, device=dev)
+    z_samples = torch.empty((N, n_importance), dtype=F32, device=dev) if want_samples else None
     z_fine = torch.empty((N, S + n_importance), dtype=F32, device=dev)
     z_std = torch.empty((N,), dtype=F32, device=dev)
     call("swnerf_resample", ptr(z_vals, F32, "z_vals"), ptr(weights, F32, "weights"),
-         None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance, z_samples.data_ptr(),
-         z_fine.data_ptr(), z_std.data_ptr(), stream())
+         None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance,
+         z_samples.data_ptr() if want_samples else None, z_fine.data_ptr(), z_std.data_ptr(), stream())
     return z_samples, z_fine, z_std
 
 

@@ -59,3 +59,10 @@ for N in (4096, 32768, 262144):
         b = N * 4 * (64 + 64 + 128 + 128 + 192 + 1)
         print("resample(rand) v%d N=%6d        %8.3f ms  %7.1f GB/s  %.2f" % (variant, N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
     call("swnerf_set_resample_variant", 1)
+    # as render_rays calls it: no z_samples output (only z_std is consumed, run.py:416)
+    ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), None, 1, N, 64, 128, None, zf.data_ptr(), zstd.data_ptr(), st()))
+    b = N * 4 * (64 + 64 + 192 + 1)
+    print("resample(det, no z_samples) v1 N=%6d  %8.3f ms  %7.1f GB/s  %.2f" % (N, ms, b / ms / 1e6, b / ms / 1e6 / peak))
+    ms = timeit(lambda: call("swnerf_resample", z.data_ptr(), w.data_ptr(), u.data_ptr(), 0, N, 64, 128, None, zf.data_ptr(), zstd.data_ptr(), st()))
+    b = N * 4 * (64 + 64 + 128 + 192 + 1)
+    print("resample(rand, no z_samples) v1 N=%6d %8.3f ms  %7.1f GB/s  %.2f" % (N, ms, b / ms / 1e6, b / ms / 1e6 / peak))

@@ -270,6 +270,53 @@ def gen_render_rays_dnerf(ref):
     np.savez_compressed(os.path.join(OUT, "render_rays_dnerf.npz"), **d)
 
 
+def gen_render_rays_tnerf():
+    """T-NeRF: the reference's TNeRF.forward on random embedded inputs, and its render_rays
+    (t_nerf/run_tnerf.py:396-500) deterministic and perturbed, with gradient summaries."""
+    rt = ref_import.load_reference_tnerf()
+    d = {}
+    d["seed"] = np.int64(521)
+    params = O.make_params(O.tnerf_param_shapes(), 521)
+    args = Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=0, N_samples=64,
+                     netdepth=8, netwidth=256, netchunk=65536, lrate=5e-4, ft_path=None,
+                     basedir="/tmp/_swnerf_golden", expname="gt", no_reload=True, perturb=1.0, white_bkgd=True,
+                     raw_noise_std=0.0, dataset_type="blender", no_ndc=False, lindisp=False, nerf_type="tnerf",
+                     do_half_precision=False)
+    os.makedirs(os.path.join(args.basedir, args.expname), exist_ok=True)
+    kw_train, kw_test, _, _, _ = rt.create_nerf(args)
+    model = kw_train["network_fn"]
+    load_params(model, params)
+    # module forward on random embedded inputs (the [1, M, 4] output shape of model.py:205-208 is kept)
+    rs = np.random.RandomState(7)
+    M = 37
+    x = rs.uniform(-1, 1, size=(M, 90)).astype(np.float32)
+    tt = rs.uniform(-1, 1, size=(M, 21)).astype(np.float32)
+    d["mlp/x"], d["mlp/t"] = x, tt
+    d["mlp/out"] = model(torch.from_numpy(x), torch.from_numpy(x[:, 63:]), torch.from_numpy(tt)).detach().numpy()
+    N = 12
+    for tag, kw0, tval in [("det", kw_test, 0.37), ("pert", kw_train, 0.6)]:
+        kw = dict(kw0)
+        kw.pop("use_viewdirs"); kw.pop("ndc")
+        rays = O.blender_rays(N, seed=41, frame_time=tval)
+        target = np.random.RandomState(42).uniform(0, 1, size=(N, 3)).astype(np.float32)
+        d[f"{tag}/rays"], d[f"{tag}/target"] = rays, target
+        model.zero_grad()
+        # pytest=True scales the stratified draw by raw_noise_std (run_tnerf.py:466-469, as shipped): the
+        # perturbed case therefore runs with raw_noise_std = 0.5 so that the draw is not all zeros
+        if tag == "pert":
+            kw["raw_noise_std"] = 0.5
+        ret = rt.render_rays(torch.from_numpy(rays), retraw=True, pytest=True, **kw)
+        loss = torch.mean((ret["rgb_map"] - torch.from_numpy(target)) ** 2)
+        loss.backward()
+        for k, v in ret.items():
+            d[f"{tag}/{k}"] = v.detach().numpy()
+        d[f"{tag}/loss"] = np.float64(loss.item())
+        grads = {k: (p.grad if p.grad is not None else torch.zeros_like(p)) for k, p in model.named_parameters()}
+        for k, v in grad_summary(grads).items():
+            d[f"{tag}/{k}"] = v
+    np.savez_compressed(os.path.join(OUT, "render_rays_tnerf.npz"), **d)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.manual_seed(0)
@@ -283,6 +330,7 @@ def main():
     gen_searchsorted()
     gen_render_rays(ref)
     gen_render_rays_dnerf(ref)
+    gen_render_rays_tnerf()
     for f in sorted(os.listdir(OUT)):
         print(f, os.path.getsize(os.path.join(OUT, f)))
 

@@ -373,6 +373,71 @@ def render_rays_dnerf(ray_batch, p, N_samples, N_importance, L_pos=10, L_time=10
 
 
 # ----------------------------------------------------------------------------
+# f4  T-NeRF                 reference: model.py:152-210, t_nerf/run_tnerf.py:45-86, 396-500
+# ----------------------------------------------------------------------------
+def tnerf_param_shapes(depth=8, in_feat=63, dir_feat=27, time_feat=21, net_dim=128,
+                       skip_layer=4) -> Dict[str, Tuple[int, ...]]:
+    """state_dict of model.TNeRF (model.py:153-186): layers.{i}.0, density.0, feature.0, layer_9.0, color.0."""
+    sh: Dict[str, Tuple[int, ...]] = {}
+    for i in range(depth):
+        k = (in_feat + time_feat) if i == 0 else net_dim
+        if i % (skip_layer + 1) == 0 and i > 0:                         # model.py:163
+            k = net_dim + in_feat + time_feat
+        sh[f"layers.{i}.0.weight"] = (net_dim, k)
+        sh[f"layers.{i}.0.bias"] = (net_dim,)
+    sh["density.0.weight"], sh["density.0.bias"] = (1, net_dim), (1,)
+    sh["feature.0.weight"], sh["feature.0.bias"] = (net_dim, net_dim), (net_dim,)
+    sh["layer_9.0.weight"], sh["layer_9.0.bias"] = (net_dim // 2, net_dim + dir_feat), (net_dim // 2,)
+    sh["color.0.weight"], sh["color.0.bias"] = (3, net_dim // 2), (3,)
+    return sh
+
+
+def tnerf_forward(p, inp, vdir, dyn_t, depth=8, in_feat=63, skip_layer=4):
+    """model.py:188-210.  inp [M, >= in_feat], vdir [M, dir_feat], dyn_t [M, time_feat] -> [M, 4] (rgb, sigma)."""
+    x0 = torch.cat([inp[:, :in_feat], dyn_t], -1)                       # model.py:189-190
+    x = x0
+    for i in range(depth):
+        x = torch.nn.functional.elu(_lin(p, f"layers.{i}.0", x))        # model.py:197
+        if i % skip_layer == 0 and i > 0:                               # model.py:198-199
+            x = torch.cat([x0, x], -1)
+    sigma = _lin(p, "density.0", x)                                     # model.py:201
+    x = _lin(p, "feature.0", x)                                         # model.py:202
+    x = torch.nn.functional.elu(_lin(p, "layer_9.0", torch.cat([x, vdir], -1)))   # model.py:203-204
+    rgb = torch.relu(_lin(p, "color.0", x))                             # model.py:205
+    return torch.cat([rgb, sigma], -1)                                  # model.py:209
+
+
+def run_network_tnerf(p, pts, viewdirs, frame_time: float, L_pos=10, L_time=10, L_dir=4, **kw):
+    """run_tnerf.py:45-86."""
+    flat = pts.reshape(-1, 3)
+    emb = embed(flat, L_pos)                                            # :56-57
+    t = torch.full((flat.shape[0], 1), float(frame_time), dtype=F32)    # :61-63
+    emb_t = embed(t, L_time)                                            # :64
+    dirs = viewdirs[:, None].expand(pts.shape).reshape(-1, 3)
+    ed = embed(dirs, L_dir)                                             # :70-73
+    out = tnerf_forward(p, torch.cat([emb, ed], -1), ed, emb_t, in_feat=emb.shape[-1], **kw)
+    return out.reshape(list(pts.shape[:-1]) + [4])
+
+
+def render_rays_tnerf(ray_batch, p, N_samples, L_pos=10, L_time=10, L_dir=4, lindisp=False, perturb=0.0,
+                      white_bkgd=False, raw_noise_std=0.0, t_rand=None, z_vals=None, retraw=False, depth=8):
+    """run_tnerf.py:396-500 (single network, single pass)."""
+    rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
+    viewdirs = ray_batch[:, -3:]                                        # :440 (use_viewdirs configs)
+    near, far = ray_batch[:, 6:7], ray_batch[:, 7:8]
+    frame_time = float(ray_batch[0, 8])                                 # :441-442 (+ :53 single time)
+    if z_vals is None:
+        z_vals = stratified_z(near, far, N_samples, lindisp, perturb, t_rand)   # :447-470
+    pts = points(rays_o, rays_d, z_vals)
+    raw = run_network_tnerf(p, pts, viewdirs, frame_time, L_pos, L_time, L_dir, depth=depth)
+    rgb_map, disp_map, acc_map, weights, _ = raw2outputs(raw, z_vals, rays_d, raw_noise_std, white_bkgd)
+    ret = dict(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map, z_vals=z_vals)
+    if retraw:
+        ret["raw"] = raw
+    return ret
+
+
+# ----------------------------------------------------------------------------
 # Deterministic parameters / inputs shared by the golden generator and the tests
 # ----------------------------------------------------------------------------
 def make_params(shapes: Dict[str, Tuple[int, ...]], seed: int, gain: float = 1.0) -> Dict[str, torch.Tensor]:
@@ -399,6 +464,12 @@ def make_params(shapes: Dict[str, Tuple[int, ...]], seed: int, gain: float = 1.0
             out[name] = out[name] * 6.0
         elif name.endswith("_time_out.weight"):
             out[name] = out[name] * 2.0
+        elif name.endswith("density.0.weight"):                 # TNeRF heads, same purpose
+            out[name] = out[name] * 24.0
+        elif name.endswith("density.0.bias"):
+            out[name] = out[name] * 0.0 + 0.5
+        elif name.endswith("color.0.weight"):
+            out[name] = out[name] * 6.0
     return out
 
 

@@ -79,6 +79,16 @@ def load_reference():
     return ns
 
 
+def load_reference_tnerf():
+    """t_nerf/run_tnerf.py, unmodified (it resolves its own `device` at import: CPU here)."""
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_ROOT)
+    _install_stubs()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    return _load("ref_tnerf_run", "t_nerf/run_tnerf.py")
+
+
 def load_reference_searchsorted_numpy():
     """The reference's own numpy oracle for its torchsearchsorted extension
     (d_nerf/torchsearchsorted/src/torchsearchsorted/utils.py:4-14, UTF-16LE)."""

@@ -165,6 +165,57 @@ class DirectTemporalNeRF(nn.Module):
         return out, dx
 
 
+class TNeRF(nn.Module):
+    """model.py:152-210: time-conditioned NeRF of t_nerf/run_tnerf.py - `depth` ELU layers of width `net_dim` on
+    [emb_pts | emb_t], the input re-injected after layer 4, density / feature heads, a view branch (ELU) and a
+    colour head that ends in a ReLU.  Same sub-module names as the reference, so state_dicts interchange.  The
+    forward runs on the library's fp32 GEMM kernels with the ELU epilogue (ops.mlp_fp32)."""
+
+    def __init__(self, depth, in_feat, dir_feat, time_feat, net_dim=128, skip_layer=4):
+        super().__init__()
+        self.depth, self.skip_layer, self.in_feat = depth, skip_layer, in_feat
+        self.dir_feat, self.time_feat, self.net_dim = dir_feat, time_feat, net_dim
+        # the reference WIDENS layer i when i % (skip_layer+1) == 0 (model.py:163) but CONCATENATES after layer i when
+        # i % skip_layer == 0 (model.py:198): the two agree only for one re-injection after layer 4 (6 <= depth <= 8)
+        widened = [i for i in range(1, depth) if i % (skip_layer + 1) == 0]
+        concat_after = [i for i in range(1, depth) if i % skip_layer == 0]
+        if [i + 1 for i in concat_after] != widened:
+            raise ValueError("TNeRF: depth=%d, skip_layer=%d is inconsistent in the reference itself "
+                             "(model.py:163 vs :198)" % (depth, skip_layer))
+        self._skips = tuple(concat_after)
+        units = [in_feat + time_feat] + [net_dim] * (depth + 1)
+        self.layers = nn.ModuleList([])
+        self.bnorm_layers = nn.ModuleList([])
+        for i in range(depth):
+            fan_in = units[i] + (in_feat + time_feat if i in widened else 0)
+            self.layers.append(nn.Sequential(nn.Linear(fan_in, units[i + 1]), nn.ELU()))
+        self.density = nn.Sequential(nn.Linear(net_dim, 1))
+        self.feature = nn.Sequential(nn.Linear(net_dim, net_dim))
+        self.layer_9 = nn.Sequential(nn.Linear(net_dim + dir_feat, net_dim // 2), nn.ELU())
+        self.color = nn.Sequential(nn.Linear(net_dim // 2, 3), nn.ReLU())
+
+    @property
+    def spec(self) -> MLPSpec:
+        return MLPSpec(self.depth, self.net_dim, self.in_feat, self.time_feat, self.dir_feat, self._skips,
+                       "viewdirs", 4, act="elu", skip_extra=True, rgb_relu=True)
+
+    def param_list(self):
+        """trunk, view branch (layer_9), feature, density, colour - the order ops.MLPSpec documents."""
+        ps = []
+        for l in self.layers:
+            ps += [l[0].weight, l[0].bias]
+        return ps + [self.layer_9[0].weight, self.layer_9[0].bias, self.feature[0].weight, self.feature[0].bias,
+                     self.density[0].weight, self.density[0].bias, self.color[0].weight, self.color[0].bias]
+
+    def forward(self, inp, vdir, dyn_t):
+        """inp [M, >= in_feat] (embedded points first), vdir [M, dir_feat], dyn_t [M, time_feat] -> [1, M, 4]
+        (rgb after the ReLU, sigma), the reference's odd leading 1 included (model.py:205-208)."""
+        M = inp.shape[0]
+        x_pts = inp[:, :self.in_feat]
+        out = ops.mlp_fp32(self.spec, x_pts, dyn_t, vdir if self.dir_feat else None, self.param_list())
+        return out.reshape(-1, M, 4)
+
+
 class NeRF:
     @staticmethod
     def get_by_name(type, *args, **kwargs):                                        # model.py:214-225

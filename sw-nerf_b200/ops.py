@@ -197,9 +197,14 @@ def searchsorted(a, v, out=None, side="left"):
 # ------------------------------------------------------------------------------------------------
 # a6 / a7  fp32 layered MLP (check path + general shapes)                    model.py:39-62, 128-136
 # ------------------------------------------------------------------------------------------------
-def _gemm(op, A, B, C, M, N, K, bias=None, accumulate=False, relu=False, mask=None):
-    """A, B, C, mask: (ptr, ld) pairs."""
-    call("swnerf_sgemm", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), int(relu),
+_ACT = {None: 0, False: 0, True: 1, "relu": 1, "elu": 2}
+
+
+def _gemm(op, A, B, C, M, N, K, bias=None, accumulate=False, relu=False, mask=None, mask_act="relu"):
+    """A, B, C, mask: (ptr, ld) pairs.  relu: False / True / "relu" / "elu" (the epilogue activation);
+    mask_act: which activation produced `mask` (its derivative scales the result)."""
+    flags = _ACT[relu] | ((1 if mask_act == "elu" else 0) << 4)
+    call("swnerf_sgemm", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), flags,
          None if mask is None else mask[0], 0 if mask is None else mask[1], stream())
 
 
@@ -220,14 +225,25 @@ class MLPSpec:
     Parameter order: trunk (w, b) x D, then for 'viewdirs': views_linears.0, feature_linear,
     alpha_linear, rgb_linear; for 'output' / 'linear': the output layer."""
 
-    def __init__(self, D=8, W=256, in_pts=63, in_extra=0, in_views=27, skips=(4,), head="viewdirs", out_ch=4):
+    def __init__(self, D=8, W=256, in_pts=63, in_extra=0, in_views=27, skips=(4,), head="viewdirs", out_ch=4,
+                 act="relu", skip_extra=False, rgb_relu=False):
+        """act: trunk / view-branch activation ("relu", or "elu" for TNeRF, model.py:163-171,182);
+        skip_extra: the skip concatenation re-injects [pts | extra] instead of pts alone (TNeRF, model.py:189-199);
+        rgb_relu: the colour head ends in a ReLU (TNeRF, model.py:183-186)."""
         self.D, self.W, self.in_pts, self.in_extra, self.in_views = D, W, in_pts, in_extra, in_views
         self.skips, self.head, self.out_ch = tuple(skips), head, out_ch
+        self.act, self.skip_extra, self.rgb_relu = act, bool(skip_extra), bool(rgb_relu)
+        if act not in ("relu", "elu"):
+            raise ValueError("act must be 'relu' or 'elu'")
+
+    @property
+    def skip_in(self):
+        return self.in_pts + (self.in_extra if self.skip_extra else 0)
 
     def trunk_in(self, i):
         if i == 0:
             return self.in_pts + self.in_extra
-        return self.W + self.in_pts if (i - 1) in self.skips else self.W
+        return self.W + self.skip_in if (i - 1) in self.skips else self.W
 
     @property
     def out_dim(self):
@@ -255,6 +271,7 @@ class MLPFp32Fn(torch.autograd.Function):
         xv = _mat(x_views, "x_views") if s.head == "viewdirs" and s.in_views else None
         hs: List[torch.Tensor] = []
         h_prev = None
+        act = s.act
         n_buf = s.D if need_grad else 2
         bufs = [torch.empty((M, W), dtype=F32, device=dev) for _ in range(min(n_buf, s.D))]
         for i in range(s.D):
@@ -264,14 +281,16 @@ class MLPFp32Fn(torch.autograd.Function):
             if i == 0:
                 if s.in_extra:
                     _gemm(0, xp, wi, hm, M, W, s.in_pts)
-                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, bias=bi, accumulate=True, relu=True)
+                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, bias=bi, accumulate=True, relu=act)
                 else:
-                    _gemm(0, xp, wi, hm, M, W, s.in_pts, bias=bi, relu=True)
+                    _gemm(0, xp, wi, hm, M, W, s.in_pts, bias=bi, relu=act)
             elif (i - 1) in s.skips:
                 _gemm(0, xp, wi, hm, M, W, s.in_pts)
-                _gemm(0, h_prev, _off(wi, s.in_pts), hm, M, W, W, bias=bi, accumulate=True, relu=True)
+                if s.skip_extra and s.in_extra:
+                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, accumulate=True)
+                _gemm(0, h_prev, _off(wi, s.skip_in), hm, M, W, W, bias=bi, accumulate=True, relu=act)
             else:
-                _gemm(0, h_prev, wi, hm, M, W, W, bias=bi, relu=True)
+                _gemm(0, h_prev, wi, hm, M, W, W, bias=bi, relu=act)
             h_prev = hm
             hs.append(h)
         out = torch.empty((M, s.out_dim), dtype=F32, device=dev)
@@ -288,10 +307,10 @@ class MLPFp32Fn(torch.autograd.Function):
             _gemm(0, h_prev, wf, fm, M, W, W, bias=bf)                                # model.py:50
             if xv is not None:
                 _gemm(0, fm, wv, hvm, M, W // 2, W)                                   # model.py:51-55
-                _gemm(0, xv, _off(wv, W), hvm, M, W // 2, s.in_views, bias=bv, accumulate=True, relu=True)
+                _gemm(0, xv, _off(wv, W), hvm, M, W // 2, s.in_views, bias=bv, accumulate=True, relu=act)
             else:
-                _gemm(0, fm, wv, hvm, M, W // 2, W, bias=bv, relu=True)
-            _gemm(0, hvm, wr, om, M, 3, W // 2, bias=br)                              # model.py:57
+                _gemm(0, fm, wv, hvm, M, W // 2, W, bias=bv, relu=act)
+            _gemm(0, hvm, wr, om, M, 3, W // 2, bias=br, relu=s.rgb_relu)             # model.py:57 / :183-186
         else:
             wo, bo = P[k], P[k + 1][0]
             _gemm(0, h_prev, wo, om, M, s.out_dim, W, bias=bo)                        # model.py:60 / :136
@@ -299,6 +318,7 @@ class MLPFp32Fn(torch.autograd.Function):
             ctx.spec = s
             ctx.x = (x_pts, x_extra, x_views)
             ctx.saved = (hs, feat, hv)
+            ctx.out = out if s.rgb_relu else None
             ctx.params = params
             ctx.pts_grad = x_pts.requires_grad
         return out
@@ -318,6 +338,12 @@ class MLPFp32Fn(torch.autograd.Function):
         xp = _mat(x_pts)
         xe = _mat(x_extra) if s.in_extra else None
         xv = _mat(x_views) if s.head == "viewdirs" and s.in_views else None
+        act = s.act
+        if s.head == "viewdirs" and s.rgb_relu:                 # d_rgb through the colour head's ReLU (model.py:185)
+            d_in = d_out
+            d_out = d_in.clone()
+            call("swnerf_act_bwd", d_in.data_ptr(), s.out_dim, ctx.out.data_ptr(), s.out_dim, M, 3, 0,
+                 d_out.data_ptr(), s.out_dim, stream())
         dm = (d_out.data_ptr(), s.out_dim)
         ga = torch.empty((M, W), dtype=F32, device=dev)
         gb = torch.empty((M, W), dtype=F32, device=dev)
@@ -333,7 +359,7 @@ class MLPFp32Fn(torch.autograd.Function):
             d_alpha = _off(dm, 3)
             _gemm(2, dm, hvm, GP[k + 6], 3, W // 2, M, accumulate=True)                # dW_rgb
             _colsum(dm, M, 3, G[k + 7].data_ptr())
-            _gemm(1, dm, wr, dhm, M, W // 2, 3, mask=hvm)                             # d_hv (masked)
+            _gemm(1, dm, wr, dhm, M, W // 2, 3, mask=hvm, mask_act=act)               # d_hv (masked)
             _gemm(2, dhm, fm, GP[k], W // 2, W, M, accumulate=True)                    # dW_v[:, :W]
             if xv is not None:
                 _gemm(2, dhm, xv, _off(GP[k], W), W // 2, s.in_views, M, accumulate=True)
@@ -346,12 +372,12 @@ class MLPFp32Fn(torch.autograd.Function):
             _gemm(2, d_alpha, hlast, GP[k + 4], 1, W, M, accumulate=True)              # dW_a
             _colsum(d_alpha, M, 1, G[k + 5].data_ptr())
             _gemm(1, dfm, wf, g, M, W, W)
-            _gemm(1, d_alpha, wa, g, M, W, 1, accumulate=True, mask=hlast)
+            _gemm(1, d_alpha, wa, g, M, W, 1, accumulate=True, mask=hlast, mask_act=act)
         else:
             wo = P[k]
             _gemm(2, dm, hlast, GP[k], s.out_dim, W, M, accumulate=True)
             _colsum(dm, M, s.out_dim, G[k + 1].data_ptr())
-            _gemm(1, dm, wo, g, M, W, s.out_dim, mask=hlast)
+            _gemm(1, dm, wo, g, M, W, s.out_dim, mask=hlast, mask_act=act)
         d_pts = torch.zeros((M, s.in_pts), dtype=F32, device=dev) if ctx.pts_grad else None
         dpm = (d_pts.data_ptr(), s.in_pts) if d_pts is not None else None
         for i in range(s.D - 1, -1, -1):
@@ -366,14 +392,16 @@ class MLPFp32Fn(torch.autograd.Function):
                     _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True)
             elif (i - 1) in s.skips:
                 _gemm(2, g, xp, GP[2 * i], W, s.in_pts, M, accumulate=True)
-                _gemm(2, g, hp, _off(GP[2 * i], s.in_pts), W, W, M, accumulate=True)
+                if s.skip_extra and s.in_extra:
+                    _gemm(2, g, xe, _off(GP[2 * i], s.in_pts), W, s.in_extra, M, accumulate=True)
+                _gemm(2, g, hp, _off(GP[2 * i], s.skip_in), W, W, M, accumulate=True)
                 if dpm is not None:
                     _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True)
-                _gemm(1, g, _off(wi, s.in_pts), g_next, M, W, W, mask=hp)
+                _gemm(1, g, _off(wi, s.skip_in), g_next, M, W, W, mask=hp, mask_act=act)
                 g, g_next = g_next, g
             else:
                 _gemm(2, g, hp, GP[2 * i], W, W, M, accumulate=True)
-                _gemm(1, g, wi, g_next, M, W, W, mask=hp)
+                _gemm(1, g, wi, g_next, M, W, W, mask=hp, mask_act=act)
                 g, g_next = g_next, g
         return (None, None, d_pts, None, None) + tuple(G)
 

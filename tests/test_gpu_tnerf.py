@@ -1,0 +1,156 @@
+"""GPU parity of the T-NeRF path (model.py:152-210, t_nerf/run_tnerf.py) against the
+golden vectors of the unmodified reference (tests/golden/render_rays_tnerf.npz, oracle/make_golden.py) and the
+oracle.  T-NeRF has no resampling step, so the fp32 path is compared at fp32-rounding tolerances end to end
+(north_star: <= 1e-5 class in the fp32-accumulate mode; written below per quantity)."""
+import os
+from argparse import Namespace
+
+import numpy as np
+import pytest
+import torch
+
+import swnerf_b200 as S
+from swnerf_b200 import ops, tnerf, _lib
+from oracle import nerf_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+T = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+
+
+def relmax(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+def _args(tmp):
+    os.makedirs(os.path.join(str(tmp), "e"), exist_ok=True)
+    return Namespace(multires=10, multires_views=4, i_embed=0, use_viewdirs=True, N_importance=0, N_samples=64,
+                     netdepth=8, netwidth=256, netchunk=65536, lrate=5e-4, ft_path=None, basedir=str(tmp),
+                     expname="e", no_reload=True, perturb=1.0, white_bkgd=True, raw_noise_std=0.0,
+                     dataset_type="blender", no_ndc=False, lindisp=False, nerf_type="tnerf",
+                     do_half_precision=False)
+
+
+def _model(seed):
+    m = S.TNeRF(depth=8, in_feat=63, dir_feat=27, time_feat=21).to(DEV)
+    m.load_state_dict({k: v.to(DEV) for k, v in O.make_params(O.tnerf_param_shapes(), seed).items()})
+    return m
+
+
+def test_tnerf_module_forward_golden(golden):
+    g = golden("render_rays_tnerf")
+    m = _model(int(g["seed"]))
+    x, t = T(g["mlp/x"]), T(g["mlp/t"])
+    before = _lib.launch_count()
+    out = m(x, x[:, 63:], t)
+    assert _lib.launch_count() > before                              # the library's kernels ran
+    assert tuple(out.shape) == (1, x.shape[0], 4)                    # model.py:205-208
+    # sigma carries a x24 gain in the synthetic scene; fp32 GEMM with another summation order than MKL
+    assert relmax(out, torch.from_numpy(g["mlp/out"])) < 2e-5
+    assert float(out[..., :3].min()) >= 0.0
+
+
+def test_tnerf_mlp_backward_vs_oracle():
+    """ELU trunk, [pts | t] re-injection, ReLU colour head: gradients of every parameter and of the embedded
+    points against autograd on the oracle's restatement."""
+    rs = np.random.RandomState(3)
+    M = 301
+    x = rs.uniform(-1, 1, size=(M, 90)).astype(np.float32)
+    tt = rs.uniform(-1, 1, size=(M, 21)).astype(np.float32)
+    gout = rs.normal(size=(M, 4)).astype(np.float32)
+    p = {k: v.requires_grad_() for k, v in O.make_params(O.tnerf_param_shapes(), 77).items()}
+    xo = torch.from_numpy(x).requires_grad_()
+    out_o = O.tnerf_forward(p, xo, xo[:, 63:].detach(), torch.from_numpy(tt))
+    (out_o * torch.from_numpy(gout)).sum().backward()
+    m = _model(77)
+    xg = T(x[:, :63]).requires_grad_()
+    out = ops.mlp_fp32(m.spec, xg, T(tt), T(x[:, 63:]), m.param_list())
+    assert relmax(out, out_o) < 2e-5
+    (out * T(gout)).sum().backward()
+    for n, prm in m.named_parameters():
+        ref = p[n].grad
+        err = float((prm.grad.cpu() - ref).norm() / ref.norm().clamp_min(1e-12))
+        assert err < 5e-4, (n, err)            # fp32, units within rounding of the ELU / ReLU kinks excepted
+    errx = float((xg.grad.cpu() - xo.grad[:, :63]).norm() / xo.grad[:, :63].norm())
+    assert errx < 5e-4, errx
+
+
+@pytest.mark.parametrize("tag", ["det", "pert"])
+def test_render_rays_tnerf_golden(golden, tag, tmp_path):
+    g = golden("render_rays_tnerf")
+    kw_train, kw_test, start, grad_vars, opt = tnerf.create_nerf(_args(tmp_path), device=torch.device(DEV))
+    model = kw_train["network_fn"]
+    assert isinstance(model, S.TNeRF) and kw_train["N_importance"] == 0 and start == 0
+    assert kw_test["perturb"] is False and kw_test["raw_noise_std"] == 0.
+    model.load_state_dict({k: v.to(DEV) for k, v in O.make_params(O.tnerf_param_shapes(), int(g["seed"])).items()})
+    kw = dict(kw_test if tag == "det" else kw_train)
+    kw.pop("use_viewdirs"); kw.pop("ndc")
+    if tag == "pert":
+        kw["raw_noise_std"] = 0.5              # as in oracle/make_golden.py (the pytest draw is scaled by it)
+    rays, target = T(g[f"{tag}/rays"]), T(g[f"{tag}/target"])
+    ret = tnerf.render_rays(rays, retraw=True, pytest=True, **kw)
+    assert set(ret) == {"rgb_map", "disp_map", "acc_map", "z_vals", "raw"}       # run_tnerf.py:487-489
+    assert relmax(ret["z_vals"], torch.from_numpy(g[f"{tag}/z_vals"])) < 1e-6
+    assert relmax(ret["raw"], torch.from_numpy(g[f"{tag}/raw"])) < 5e-5           # x24 sigma gain, L=10 encoding
+    for k in ["rgb_map", "acc_map", "disp_map"]:
+        assert relmax(ret[k], torch.from_numpy(g[f"{tag}/{k}"])) < 2e-5, k
+    loss = torch.mean((ret["rgb_map"] - target) ** 2)
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-6
+    loss.backward()
+    num = den = 0.0
+    for n, p in model.named_parameters():
+        sub = p.grad.reshape(-1)[::251].cpu().double()
+        ref = torch.from_numpy(g[f"{tag}/gsub/{n}"]).double()
+        num += float((sub - ref).pow(2).sum()); den += float(ref.pow(2).sum())
+        gn = float(g[f"{tag}/gnorm/{n}"])
+        assert abs(float(p.grad.double().norm()) - gn) <= 1e-3 * max(gn, 1e-12), n
+    assert (num / max(den, 1e-30)) ** 0.5 < 1e-3
+
+
+def test_tnerf_reference_signature_query_equals_ray_entry(tmp_path):
+    """network_query_fn(pts, viewdirs, frame_time, net) - what run_tnerf.py:474 calls - against the ray entry
+    render_rays uses (encoding from rays, broadcast time row), plus chunked evaluation (netchunk)."""
+    kw, _, _, _, _ = tnerf.create_nerf(_args(tmp_path), device=torch.device(DEV))
+    model, q = kw["network_fn"], kw["network_query_fn"]
+    model.load_state_dict({k: v.to(DEV) for k, v in O.make_params(O.tnerf_param_shapes(), 9).items()})
+    rays = T(O.blender_rays(50, seed=4, frame_time=0.25))
+    z = ops.stratified_z(rays, 64, near_col=6)
+    with torch.no_grad():
+        a = q.query_rays(rays, z, model, 9, 0.25)
+        pts = rays[:, None, 0:3] + rays[:, None, 3:6] * z[:, :, None]
+        b = q(pts, rays[:, 9:12], rays[:, 8:9], model)
+        q.netchunk = 1000                                           # ragged chunks
+        c = q(pts, rays[:, 9:12], rays[:, 8:9], model)
+    assert tuple(a.shape) == tuple(b.shape) == (50, 64, 4)
+    assert relmax(a, b) < 2e-5 and relmax(c, b) < 1e-6
+    with pytest.raises(AssertionError):                              # run_tnerf.py:53
+        bad = rays[:, 8:9].clone(); bad[0] = 0.5
+        q(pts, rays[:, 9:12], bad, model)
+
+
+def test_tnerf_render_frame_and_checkpoint_roundtrip(tmp_path):
+    args = _args(tmp_path)
+    kw, kw_test, _, grad_vars, opt = tnerf.create_nerf(args, device=torch.device(DEV))
+    model = kw["network_fn"]
+    assert len(grad_vars) == len(list(model.parameters())) == 24
+    H = W = 24
+    focal = 0.5 * W / np.tanh(0.5 * 0.6911112)
+    c2w = T(O.pose_spherical(30.0, -30.0, 4.0)[:3, :4].astype(np.float32))
+    with torch.no_grad():
+        rgb, disp, acc, extras = tnerf.render(H, W, focal, chunk=200, c2w=c2w, frame_time=0.4, near=2., far=6.,
+                                              **kw_test)
+    assert tuple(rgb.shape) == (H, W, 3) and tuple(disp.shape) == (H, W) and tuple(extras["z_vals"].shape) == (H, W, 64)
+    # one optimiser step, save in the reference's checkpoint layout (run_tnerf.py:748-757), reload
+    rays = T(O.blender_rays(64, seed=5, frame_time=0.4))
+    ret = tnerf.render_rays(rays, **{k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")})
+    ret["rgb_map"].square().mean().backward()
+    opt.step()
+    path = os.path.join(str(tmp_path), "e", "000001.tar")
+    torch.save({"global_step": 1, "network_fn_state_dict": model.state_dict(),
+                "optimizer_state_dict": opt.state_dict()}, path)
+    args.no_reload = False
+    kw2, _, start, _, _ = tnerf.create_nerf(args, device=torch.device(DEV))
+    assert start == 1
+    for (n, a), (_, b) in zip(model.state_dict().items(), kw2["network_fn"].state_dict().items()):
+        assert torch.equal(a, b), n

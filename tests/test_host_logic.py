@@ -131,3 +131,33 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert "oracle" not in src.replace("no oracle", ""), f
+
+
+def test_tnerf_module_layout_and_signatures():
+    """model.TNeRF / tnerf.* keep the reference's names, shapes and signatures (model.py:152-210, run_tnerf.py)."""
+    from swnerf_b200 import tnerf
+    m = S.TNeRF(depth=8, in_feat=63, dir_feat=27, time_feat=21, net_dim=128, skip_layer=4)
+    ref = O.tnerf_param_shapes()
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(ref.keys())                       # same registration order as the reference
+    for k, sh in ref.items():
+        assert tuple(sd[k].shape) == sh, k
+    assert tuple(m.layers[5][0].weight.shape) == (128, 128 + 63 + 21)   # the re-injection after layer 4
+    assert isinstance(m.layers[0][1], torch.nn.ELU) and isinstance(m.color[1], torch.nn.ReLU)
+    assert m.spec.act == "elu" and m.spec.skip_extra and m.spec.rgb_relu and m.spec.skips == (4,)
+    assert [tuple(p.shape) for p in m.param_list()[-8:]] == [(64, 155), (64,), (128, 128), (128,), (1, 128), (1,),
+                                                            (3, 64), (3,)]
+    torch.manual_seed(0)
+    a = S.TNeRF(8, 63, 27, 21)
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(84, 128)
+    assert torch.equal(a.layers[0][0].weight, lin.weight)            # same RNG consumption order
+    with pytest.raises(ValueError):
+        S.TNeRF(depth=10, in_feat=63, dir_feat=27, time_feat=21)     # inconsistent in the reference itself
+    sig = lambda f: list(inspect.signature(f).parameters)
+    assert sig(tnerf.render_rays) == sig(dnerf.render_rays)
+    assert sig(tnerf.run_network) == ["inputs", "viewdirs", "frame_time", "fn", "embed_fn", "embeddirs_fn",
+                                      "embedtime_fn", "netchunk", "embd_time_discr"]
+    assert sig(m.forward) == ["inp", "vdir", "dyn_t"]
+    with pytest.raises((RuntimeError, TypeError)):                   # no CPU path
+        m(torch.zeros(4, 90), torch.zeros(4, 27), torch.zeros(4, 21))

@@ -144,3 +144,38 @@ def test_render_rays_dnerf(golden, tag):
     loss.backward()
     named = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
     _grad_check(g, tag, named, rtol=1e-3)
+
+
+# ---------------------------------------------------------------- f4 T-NeRF (model.py:152-210, run_tnerf.py:396-500)
+def test_tnerf_mlp(golden):
+    g = golden("render_rays_tnerf")
+    p = O.make_params(O.tnerf_param_shapes(), int(g["seed"]))
+    x, t = T(g["mlp/x"]), T(g["mlp/t"])
+    out = O.tnerf_forward(p, x, x[:, 63:], t)
+    assert g["mlp/out"].shape == (1, x.shape[0], 4)                 # the reference's [-1, M, 4] reshape, model.py:205-208
+    close(out.numpy(), g["mlp/out"][0], rtol=1e-5, atol=1e-6)
+    assert float(out[:, :3].min()) >= 0.0                           # colour head ends in a ReLU
+
+
+@pytest.mark.parametrize("tag", ["det", "pert"])
+def test_render_rays_tnerf(golden, tag):
+    g = golden("render_rays_tnerf")
+    rays, target = T(g[f"{tag}/rays"]), T(g[f"{tag}/target"])
+    p = {k: v.requires_grad_() for k, v in O.make_params(O.tnerf_param_shapes(), int(g["seed"])).items()}
+    N = rays.shape[0]
+    kw = {}
+    std = 0.0
+    if tag == "pert":     # run_tnerf.py:466-469 as shipped: the pytest draw of t_rand is scaled by raw_noise_std
+        std = 0.5
+        np.random.seed(0); kw["t_rand"] = torch.Tensor(np.random.rand(N, 64) * std)
+    ret = O.render_rays_tnerf(rays, p, 64, perturb=1.0 if tag == "pert" else 0.0, white_bkgd=True, retraw=True, **kw)
+    if std > 0:           # the same hook draws the density noise (run_tnerf.py:372-376)
+        np.random.seed(0); noise = torch.Tensor(np.random.rand(N, 64) * std)
+        rgb_map, disp_map, acc_map, _, _ = O.raw2outputs(ret["raw"], ret["z_vals"], rays[:, 3:6], std, True, noise=noise)
+        ret.update(rgb_map=rgb_map, disp_map=disp_map, acc_map=acc_map)
+    for k in ["rgb_map", "disp_map", "acc_map", "z_vals", "raw"]:
+        close(ret[k].detach().numpy(), g[f"{tag}/{k}"], rtol=2e-4, atol=2e-5)
+    loss = torch.mean((ret["rgb_map"] - target) ** 2)
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-5
+    loss.backward()
+    _grad_check(g, tag, {k: v.grad for k, v in p.items()}, rtol=1e-3)

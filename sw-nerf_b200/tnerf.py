@@ -21,7 +21,9 @@ DEBUG = False
 
 
 def batchify(fn, chunk):
-    """run_tnerf.py:25-42."""
+    """run_tnerf.py:25-42.  TNeRF.forward returns [1, m, 4] (model.py:205-208) and the reference concatenates the
+    slabs along dim 0, which only works when every slab has the same length (it raises on a ragged last slab);
+    here 3-D slabs are joined along the sample axis - the same flat order run_network's final reshape sees."""
     if chunk is None:
         return fn
 
@@ -29,7 +31,7 @@ def batchify(fn, chunk):
         out_list = []
         for i in range(0, inputs_pos.shape[0], chunk):
             out_list += [fn(inputs_pos[i:i + chunk], viewdirs[i:i + chunk], dyn_t[i:i + chunk])]
-        return torch.cat(out_list, 0)
+        return torch.cat(out_list, 1 if out_list[0].dim() == 3 else 0)
     return ret
 
 

@@ -721,14 +721,6 @@ __device__ __forceinline__ float rcp_approx(float x) {         // MUFU.RCP, 1 ul
   float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
 }
 
-// one probe of the branchless upper-bound search over a float array in shared memory: pa += 4 ST if a[ST-1] <= u
-template <int ST>
-__device__ __forceinline__ void probe_step(unsigned& pa, float uu) {
-  const float cv = lds_f32(pa + 4 * (ST - 1));
-  asm("{\n\t.reg .pred p;\n\tsetp.le.f32 p, %1, %2;\n\t@p add.u32 %0, %0, %3;\n\t}"
-      : "+r"(pa) : "f"(cv), "f"(uu), "n"(4 * ST));
-}
-
 __device__ __forceinline__ void sort2(float& a, float& b) {
   const float lo = fminf(a, b), hi = fmaxf(a, b);
   a = lo; b = hi;
@@ -737,13 +729,13 @@ __device__ __forceinline__ void sort2(float& a, float& b) {
 // rays the eight-lane kernel handed to the generic routine since the last reset (diagnostic: swnerf_resample_fallbacks)
 __device__ unsigned long long g_resample_fallbacks = 0ull;
 
-// floats per ray: cdf[64] | z[64] | z 9-strided[72] | rec[64 x 4] (the 136-float transpose buffer of the random mode
+// floats per ray: cdf level tables[64] | z[64] | z 9-strided[72] | rec[64 x 4] (the 136-float transpose buffer of the random mode
 // and, later, the merged row outb[192] alias rec).  456 = 8 mod 32: the four rays of a warp start 8 banks apart.
 constexpr int kQRow = 456;
-constexpr int kQWarps = 4;                 // warps per block (16 rays): 29 KB of shared memory, 7 blocks per SM
+constexpr int kQWarps = 4;                 // warps per block (16 rays): 29 KB of shared memory; 5-6 blocks per SM (registers)
 
 template <bool RANDOM>
-__global__ void __launch_bounds__(kQWarps * 32, 6)
+__global__ void __launch_bounds__(kQWarps * 32, 5)
 resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
                    int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std) {
   constexpr int S = 64, Ni = 128;
@@ -758,7 +750,7 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   const int64_t rr = valid ? r : N - 1;                        // out-of-range groups shadow the last ray, store nothing
   float* wbase = smem + (size_t)warp * 4 * kQRow;
   float* row = wbase + sub * kQRow;
-  float* cdf = row;                                            // [64] (cdf[63] = cdf[62], never probed)
+  float* cdf = row;                                            // [64]: lv4[8] | lv2[16] | lv1[32] (see below)
   float* zs = row + 64;                                        // [64]
   float* zsw = row + 128;                                      // z[k] at k + (k >> 3)
   float* recf = row + 200;                                     // record k at (k ^ (k >> 3)) * 4
@@ -870,11 +862,17 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   if (g == 0) ex = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = __fadd_rn(ex, q[i]);
-  {
-    const float4 a = make_float4(q[0], q[1], q[2], q[3]), b = make_float4(q[4], q[5], q[6], q[7]);
-    reinterpret_cast<float4*>(cdf)[2 * g + (hi ? 1 : 0)] = hi ? b : a;
-    reinterpret_cast<float4*>(cdf)[2 * g + (hi ? 0 : 1)] = hi ? a : b;
-  }
+  // the cdf is stored in search order, one small table per probe level (the three upper levels live in registers):
+  // lv4[m] = cdf[8m+3], lv2[m] = cdf[4m+1], lv1[m] = cdf[2m].  Rays that probe neighbouring entries of a level are then
+  // a few banks apart, never a multiple of the 8-bank row skew (the linear array made two rays of a warp collide
+  // whenever their indices differed by 8)
+  cdf[g] = q[3];
+  reinterpret_cast<float2*>(cdf + 8)[g] = make_float2(q[1], q[5]);
+  reinterpret_cast<float4*>(cdf + 24)[g] = make_float4(q[0], q[2], q[4], q[6]);
+  const float c7 = __shfl_sync(full, q[7], 0, 8), c15 = __shfl_sync(full, q[7], 1, 8),
+              c23 = __shfl_sync(full, q[7], 2, 8), c31 = __shfl_sync(full, q[7], 3, 8),
+              c39 = __shfl_sync(full, q[7], 4, 8), c47 = __shfl_sync(full, q[7], 5, 8),
+              c55 = __shfl_sync(full, q[7], 6, 8);
   {
     float cnext = __shfl_down_sync(full, q[0], 1);             // cdf[8g + 8]
     if (g == 7) cnext = q[7];
@@ -902,20 +900,20 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   const unsigned cdf_sa = (unsigned)__cvta_generic_to_shared(cdf);
   const unsigned zs_sa = (unsigned)__cvta_generic_to_shared(zs);
   const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(recf);
-  const float c15 = cdf[15], c31 = cdf[31], c47 = cdf[47];
   float sv[16];
   int pos[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float uu = u[i];
-    // number of cdf entries <= u (searchsorted right=True) as a byte address: the first two probes hit registers
-    unsigned pa = cdf_sa;
-    asm("{\n\t.reg .pred p;\n\t.reg .f32 c;\n\t"
-        "setp.le.f32 p, %1, %4;\n\t@p add.u32 %0, %0, 128;\n\tselp.f32 c, %3, %2, p;\n\t"
-        "setp.le.f32 p, c, %4;\n\t@p add.u32 %0, %0, 64;\n\t}"
-        : "+r"(pa) : "f"(c31), "f"(c15), "f"(c47), "f"(uu));
-    probe_step<8>(pa, uu); probe_step<4>(pa, uu); probe_step<2>(pa, uu); probe_step<1>(pa, uu);
-    const unsigned pb = pa - cdf_sa;                           // 4 x count
+    // p = number of cdf entries <= u (searchsorted right=True): three probes on registers, three on the level tables
+    const bool h1 = c31 <= uu;
+    const bool h2 = (h1 ? c47 : c15) <= uu;
+    const bool h3 = (h1 ? (h2 ? c55 : c39) : (h2 ? c23 : c7)) <= uu;
+    unsigned pc = (h1 ? 32u : 0u) + (h2 ? 16u : 0u) + (h3 ? 8u : 0u);
+    pc += (lds_f32(cdf_sa + (pc >> 1)) <= uu) ? 4u : 0u;       // lv4[pc / 8]      = cdf[pc + 3]
+    pc += (lds_f32(cdf_sa + 32 + pc) <= uu) ? 2u : 0u;         // lv2[pc / 4]      = cdf[pc + 1]
+    pc += (lds_f32(cdf_sa + 96 + 2 * pc) <= uu) ? 1u : 0u;     // lv1[pc / 2]      = cdf[pc]
+    const unsigned pb = 4 * pc;
     ok = ok && (pb != 0);                                      // u >= cdf[0] = 0
     const unsigned x = max(pb, 4u) - 4u;                       // 4 x below (ray.py:137)
     const float z1 = lds_f32(zs_sa + x + 4);                   // z[below + 1]

@@ -119,6 +119,15 @@ def main():
     ap.add_argument("--render-frame", action="store_true", help="also time one 800x800 frame render (config #3)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+    # stdout carries exactly ONE line, the JSON record: everything libraries print while the run is in progress
+    # (NCCL's version banner, warnings written with print) is routed to stderr at the file-descriptor level
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -142,7 +151,7 @@ def main():
                                  "sample": "%d rays per step (bounded sample of the 4096-ray step), fwd+bwd+Adam, "
                                            "torch CPU fp32, %d threads" % (args.cpu_sample_rays, threads)},
                 "e2e": {"value": rps, "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        emit(line)
         return
 
     import torch.distributed as dist
@@ -362,7 +371,7 @@ def main():
                 "cuda_graph": use_graph, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
                 "kernel_ms_per_step": ktimes, "kernel_calls_per_step": kcalls}
         line.update(extra)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

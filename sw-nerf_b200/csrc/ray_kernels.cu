@@ -7,7 +7,8 @@
 // nerf/run.py:400,416 (sort, z_std), d_nerf/torchsearchsorted/src/cuda/searchsorted_cuda_kernel.cu.
 //
 // Mapping: one warp per ray, lanes stride the samples (coalesced float4 / float loads),
-// transmittance and cdf by warp shuffles scans with a running carry, so any S works.
+// transmittance and cdf by warp shuffles scans with a running carry, so any S works; the resampling of the
+// reference configs' 64 + 128 shape runs on eight lanes per ray (resample64q_kernel).
 #include "common.cuh"
 #include "../../include/swnerf_b200.h"
 
@@ -691,11 +692,13 @@ resample64_kernel(const float* __restrict__ z_vals, const float* __restrict__ we
 
 // Second specialisation of the 64+128 shape: EIGHT lanes per ray (four rays per warp), so that every shuffle scan,
 // vote and reduction serves four rays and has three steps instead of five.  The kernel is bound by shared-memory
-// wavefronts, not by instruction issue, so the layout is chosen for conflict-free access:
+// wavefronts (LSU data pipe ~88 % busy) as much as by instruction issue, so the layout is chosen for conflict-free access:
 //   * a lane owns z / weights 8g..8g+7 while the cdf is built, but SAMPLES g, g+8, g+16, ... : at any instruction the
 //     eight lanes of a ray look up neighbouring uniforms, i.e. the same or adjacent cdf entries (broadcast or distinct
 //     banks), and the four rays of a warp sit 8 banks apart (row stride = 8 mod 32);
-//   * the inverse cdf is one BRANCHLESS 6-probe search per sample (the first two probes compare registers);
+//   * the inverse cdf is one BRANCHLESS 6-probe search per sample: the three upper levels compare registers, the three
+//     lower ones read one small table per level (cdf[8m+3], cdf[4m+1], cdf[2m]) so that two rays probing neighbouring
+//     entries are a few banks apart instead of a multiple of the row skew;
 //   * what a sample needs after the search sits in ONE 16-byte record per bin {cdf_b, z_mid_b, 1/denom, z_mid_a -
 //     z_mid_b}, stored at k ^ (k >> 3) so that building the records is conflict-free too; 1/denom is the MUFU
 //     reciprocal (1 ulp) - t in [0,1] scales a bin width (~0.06), so a sample moves by < 2e-8, far below one ulp of z;
@@ -704,7 +707,9 @@ resample64_kernel(const float* __restrict__ z_vals, const float* __restrict__ we
 //   * the uniforms of the random mode are sorted in registers (16 per lane, all-ascending bitonic network) and
 //     transposed to the interleaved ownership through shared memory; deterministic uniforms are computed;
 //   * samples scatter to their ranks in a sentinel-filled row, each lane reads 24 consecutive slots back, fills the
-//     holes with the z_vals in order (read from a 9-strided copy, conflict-free) and stores the row itself.
+//     holes with the z_vals in order (read from a 9-strided copy, conflict-free) and writes them back, so that the row
+//     leaves for HBM in 128-byte runs per ray (two merges without the sentinel row - a rank loop, a shared-memory
+//     histogram of the ranks - were measured and were not faster: profiles/r1h_ncu_resample64q.md).
 // Exactness is by construction, guarded by per-ray checks made while the records are built: z_mid[k] < z[k+1]
 // strictly, z_mid_b + (z_mid_a - z_mid_b) <= z_mid_a, cdf non-decreasing, every u >= 0.  With those, t clamped to 1 and
 // ascending uniforms, the samples are ascending and a sample's rank among the z_vals is below + 1 + (s >= z[below+1]).

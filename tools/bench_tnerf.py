@@ -31,6 +31,54 @@ rays._swnerf_frame_time = 0.37
 tgt = torch.rand(N, 3, device=dev)
 
 
+def timeit(fn, reps=20):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps, out
+
+
+def fwd_bwd():
+    for p in gv:
+        if p.grad is not None:
+            p.grad.zero_()
+    ret = tnerf.render_rays(rays, **kw)
+    loss = torch.mean((ret["rgb_map"] - tgt) ** 2)
+    loss.backward()
+    return loss
+
+
+# 1. forward + backward captured once in a CUDA graph (static ray / target buffers, as bench.py does for the vanilla
+#    step), Adam after the replay.  This comes FIRST: autograd ties a parameter's gradient accumulation to the stream it
+#    first ran on, and a capture cannot wait on the legacy default stream.
+side = torch.cuda.Stream()
+side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        fwd_bwd()
+torch.cuda.current_stream().wait_stream(side)
+torch.cuda.synchronize()
+g = torch.cuda.CUDAGraph()
+with torch.cuda.graph(g):
+    gl = fwd_bwd()
+
+
+def graphed():
+    g.replay()
+    opt.step()
+    return gl
+
+
+for _ in range(3):
+    graphed()
+ms_g, lg = timeit(graphed)
+print("T-NeRF step, %d rays x 64 samples, CUDA graph of fwd+bwd: %.2f ms (%.0f rays/s), loss %.5f"
+      % (N, ms_g, N / ms_g * 1e3, lg.item()))
+
+
+# 2. the eager step: bound by the host (61 library calls + autograd bookkeeping per step)
 def step():
     opt.zero_grad()
     ret = tnerf.render_rays(rays, **kw)
@@ -41,16 +89,10 @@ def step():
 
 
 for _ in range(3):
-    l = step()
+    step()
 torch.cuda.synchronize()
 n0 = _lib.launch_count()
-e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-reps = 20
-e0.record()
-for _ in range(reps):
-    l = step()
-e1.record(); torch.cuda.synchronize()
-ms = e0.elapsed_time(e1) / reps
+ms, l = timeit(step)
 flop = 3 * 2 * N * 64 * sum(p.numel() for p in gv if p.dim() == 2)       # fwd + dgrad + wgrad
-print("T-NeRF step, %d rays x 64 samples: %.2f ms (%.0f rays/s), %.1f TFLOP/s fp32 SIMT, %d library launches/step, loss %.5f"
-      % (N, ms, N / ms * 1e3, flop / ms / 1e9, (_lib.launch_count() - n0) // reps, l.item()))
+print("T-NeRF step, %d rays x 64 samples, eager: %.2f ms (%.0f rays/s), %d library launches/step; graph: %.1f TFLOP/s "
+      "fp32 SIMT" % (N, ms, N / ms * 1e3, (_lib.launch_count() - n0) // 20, flop / ms_g / 1e9))

@@ -95,6 +95,19 @@ int swnerf_resample_fallbacks(unsigned long long* count, int reset, void* stream
 int swnerf_sgemm(int op, const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc, int64_t M,
                  int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
                  int64_t ldmask, void* stream);
+/* ---- a6 / a7 / f4 on the tensor cores for the shapes the fused kernels are not instantiated for (TNeRF, model.py:152-210;
+ * MultiRes encoding widths, multires_dnerf.py:665): swnerf_sgemm's ops 0 and 1 with fp16 operands and fp32
+ * accumulation (tcgen05), same epilogue and act_flags.  A is multiplied by a_scale (a power of two; gradients are
+ * lifted into fp16's normal range) before rounding and the product by 1 / a_scale; a non-null a_scale_dev (one float in
+ * device memory, see swnerf_pow2_scale) overrides a_scale.  Needs 16 <= N <= 256, K <= 256
+ * (swnerf_hgemm_tc_supported); everything else stays on swnerf_sgemm. */
+int swnerf_hgemm_tc_supported(int64_t N, int64_t K);
+int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                    int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
+                    int64_t ldmask, float a_scale, const float* a_scale_dev, void* stream);
+/* out[0] = 2^floor(log2(target / max|x|)) on the device (1 for an all-zero x): the a_scale_dev of a gradient chain, so
+ * that no host synchronisation is needed to choose it.  The fused backward scales its gradients the same way. */
+int swnerf_pow2_scale(const float* x, int64_t n, float target, float* out, void* stream);
 /* out[rows, cols] = d * act'(y) from the activation's output y; kind 0 ReLU, 1 ELU (TNeRF's colour head ends in a
  * ReLU, model.py:183-186). */
 int swnerf_act_bwd(const float* d, int64_t ldd, const float* y, int64_t ldy, int64_t rows, int cols, int kind,

@@ -1,0 +1,293 @@
+// Layer-at-a-time tcgen05 GEMM with the nn.Linear epilogue, for the network shapes the fused kernels (mlp_tc*.cu) are
+// not instantiated for: T-NeRF (W = 128, ELU, model.py:152-210), MultiRes D-NeRF levels with other encoding widths
+// (multires_dnerf.py:665), networks without view directions.  Same contract as swnerf_sgemm ops 0 / 1 (sgemm.cu), but
+// the contraction runs on the tensor cores with fp16 operands and fp32 accumulation - the precision of the fused path:
+//     C[M,N] = act( A[M,K] . B^T + bias ) (+ C) (* act'(mask)),     B = W[N,K]  (forward)  or  W[K,N] read transposed (dgrad)
+// A and C stay fp32 row-major in HBM (any row stride, any alignment): the kernel converts a 128-row tile of A to the
+// fp16 operand image itself (tc_common.cuh: rows of 128 B, 8-row atoms, 16-B units XOR-swizzled), and builds the image
+// of the small weight matrix once per CTA.  Persistent CTAs, 384 threads: warps 8-11 load / convert the next A tile and
+// one of their lanes issues the K/16 `tcgen05.mma.cta_group::1.kind::f16` of the tile; warps 0-7 read the fp32
+// accumulator (two 256-column TMEM buffers alternate) and run the epilogue, so a tile's stores overlap the next tile's
+// loads and MMAs.  HBM-bound by construction (fp32 activations in and out: 4 (K + N) bytes per row).
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "../../include/swnerf_b200.h"
+
+namespace swnerf {
+using namespace tc;
+
+struct HgArgs {
+  const float* A; int64_t lda;
+  const float* W; int64_t ldw; int trans_w;      // trans_w: B(n,k) = W[k*ldw + n] instead of W[n*ldw + k]
+  float* C; int64_t ldc;
+  int64_t M; int N, K;
+  const float* bias;
+  int accumulate, act, mask_kind;
+  const float* mask; int64_t ldmask;
+  int n_pad, k_chunks;                            // N rounded up to 16; number of 64-column K chunks
+  float a_scale;                                  // A is multiplied by a_scale before rounding, the product by 1 / a_scale
+  const float* a_scale_dev;                       // if set: the scale is read from device memory (swnerf_pow2_scale)
+  int vec_a, vec_c;                               // float4 access allowed (alignment checked on the host)
+};
+
+constexpr int HG_A_CHUNK = 128 * 128;             // one [128 x 64] fp16 image
+
+__global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t w_chunk = (uint32_t)g.n_pad * 128u;
+  uint8_t* sw = smem;
+  uint8_t* sa = smem + (((uint32_t)g.k_chunks * w_chunk + 1023u) & ~1023u);
+  __shared__ uint64_t a_free, acc_full[2], acc_free[2];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kpad = g.k_chunks * 64;
+  const float a_scale_ = g.a_scale_dev ? __ldg(g.a_scale_dev) : g.a_scale, c_scale = 1.f / a_scale_;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&a_free, 1);
+    mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
+    mbar_init(&acc_free[0], 8); mbar_init(&acc_free[1], 8);
+    mbar_fence_init();
+  }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  // weight image: B(n, k) for n < n_pad, k < kpad, zero outside [N x K]
+  for (int idx = threadIdx.x; idx < g.n_pad * kpad; idx += blockDim.x) {
+    int n, k;
+    if (g.trans_w) { n = idx % g.n_pad; k = idx / g.n_pad; } else { k = idx % kpad; n = idx / kpad; }
+    float v = 0.f;
+    if (n < g.N && k < g.K) v = g.trans_w ? __ldg(g.W + (int64_t)k * g.ldw + n) : __ldg(g.W + (int64_t)n * g.ldw + k);
+    *reinterpret_cast<__half*>(sw + (uint32_t)(k >> 6) * w_chunk + tile_off((uint32_t)n, (uint32_t)(k & 63))) =
+        __float2half_rn(v);
+  }
+  fence_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int64_t n_tiles = (g.M + 127) / 128;
+
+  if (warp >= 8) {
+    // ===================== loaders (+ the MMA issuer) =====================
+    const int t = threadIdx.x - 256;                       // 0..127
+    const uint32_t idesc = umma_idesc_f16(128, g.n_pad, 0, 0);
+    const int ksteps = (g.K + 15) / 16;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const int64_t m0 = tile * 128;
+      if (it > 0) mbar_wait(&a_free, (it - 1) & 1);        // the previous tile's MMAs have read the image
+      if (g.vec_a && (128 % (kpad >> 2)) == 0) {
+        // a thread keeps its column and walks down the rows, eight independent 16-byte loads in flight at a time
+        const int units = kpad >> 2, rstep = 128 / units;
+        const int c = (t % units) << 2, r0 = t / units;
+        const bool c_ok = c < g.K;
+        const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
+        for (int j0 = 0; j0 < units; j0 += 8) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t m = m0 + r0 + (j0 + u) * rstep;
+            v[u] = (c_ok && m < g.M) ? __ldg(reinterpret_cast<const float4*>(g.A + m * g.lda + c))
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + (j0 + u) * rstep;
+            uint2 p;
+            p.x = pack_half2(v[u].x * a_scale_, v[u].y * a_scale_);
+            p.y = pack_half2(v[u].z * a_scale_, v[u].w * a_scale_);
+            *reinterpret_cast<uint2*>(sa + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
+          }
+        }
+      } else if (g.vec_a) {
+        const int units = kpad >> 2;                       // float4 per row (kpad is a multiple of 64)
+        for (int idx = t; idx < 128 * units; idx += 128) {
+          const int r = idx / units, c = (idx - r * units) << 2;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          const int64_t m = m0 + r;
+          if (m < g.M && c < g.K) {                        // K is a multiple of 4 on this path
+            v = __ldg(reinterpret_cast<const float4*>(g.A + m * g.lda + c));
+            v.x *= a_scale_; v.y *= a_scale_; v.z *= a_scale_; v.w *= a_scale_;
+          }
+          uint2 p; p.x = pack_half2(v.x, v.y); p.y = pack_half2(v.z, v.w);
+          *reinterpret_cast<uint2*>(sa + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
+        }
+      } else if ((128 % (kpad >> 1)) == 0) {
+        // unaligned / odd-width A (first layers: encodings inside a wider row): same walk, two floats per step
+        const int pairs = kpad >> 1, rstep = 128 / pairs;
+        const int c = (t % pairs) << 1, r0 = t / pairs;
+        const bool x_ok = c < g.K, y_ok = c + 1 < g.K;
+        const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
+        for (int j0 = 0; j0 < pairs; j0 += 8) {
+          float x[8], y[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int64_t m = m0 + r0 + (j0 + u) * rstep;
+            const bool ok = m < g.M;
+            x[u] = (ok && x_ok) ? __ldg(g.A + m * g.lda + c) : 0.f;
+            y[u] = (ok && y_ok) ? __ldg(g.A + m * g.lda + c + 1) : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int r = r0 + (j0 + u) * rstep;
+            *reinterpret_cast<uint32_t*>(sa + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
+                pack_half2(x[u] * a_scale_, y[u] * a_scale_);
+          }
+        }
+      } else {
+        const int pairs = kpad >> 1;
+        for (int idx = t; idx < 128 * pairs; idx += 128) {
+          const int r = idx / pairs, c = (idx - r * pairs) << 1;
+          const int64_t m = m0 + r;
+          float x = 0.f, y = 0.f;
+          if (m < g.M) {
+            if (c < g.K) x = __ldg(g.A + m * g.lda + c) * a_scale_;
+            if (c + 1 < g.K) y = __ldg(g.A + m * g.lda + c + 1) * a_scale_;
+          }
+          *reinterpret_cast<uint32_t*>(sa + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
+              pack_half2(x, y);
+        }
+      }
+      fence_async_smem();
+      named_bar_sync(1, 128);
+      if (warp == 8) {
+        const uint32_t buf = it & 1;
+        if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);      // the epilogue has drained this accumulator
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sw);
+          for (int ks = 0; ks < ksteps; ++ks) {
+            const uint32_t kb = ks >> 2, ko = (ks & 3) * 32;
+            umma_f16(tmem + buf * 256, umma_desc_kmajor(a0 + kb * HG_A_CHUNK + ko),
+                     umma_desc_kmajor(b0 + kb * w_chunk + ko), idesc, ks > 0 ? 1u : 0u);
+          }
+          umma_commit(&a_free);
+          umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ===================== epilogue: bias, accumulate, activation, mask =====================
+    // warp w reads TMEM lanes 32 (w & 3) ..: warps 0-3 take the lower half of the 32-column blocks, warps 4-7 the upper
+    const int q = warp & 3, row = q * 32 + lane;
+    const int n_blk = (g.n_pad + 31) / 32, blk_lo = (warp < 4) ? 0 : (n_blk + 1) / 2,
+              blk_hi = (warp < 4) ? (n_blk + 1) / 2 : n_blk;
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+      const uint32_t buf = it & 1;
+      const int64_t m = tile * 128 + row;
+      mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc_fence_after();
+      for (int c0 = 32 * blk_lo; c0 < 32 * blk_hi; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0, v);
+        tmem_ld_wait();
+        if (m < g.M) {
+          float* crow = g.C + m * g.ldc + c0;
+          const float* mrow = g.mask ? g.mask + m * g.ldmask + c0 : nullptr;
+          float o[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const int n = c0 + i;
+            float x = __uint_as_float(v[i]) * c_scale;
+            if (n < g.N) {
+              if (g.bias) x += __ldg(g.bias + n);
+              if (g.accumulate) x += crow[i];
+              if (g.act == 1) x = fmaxf(x, 0.f);
+              else if (g.act == 2) x = x > 0.f ? x : expm1f(x);
+              if (mrow) {
+                const float y = __ldg(mrow + i);
+                x = (y > 0.f) ? x : (g.mask_kind == 1 ? x * (y + 1.f) : 0.f);
+              }
+            }
+            o[i] = x;
+          }
+          if (g.vec_c && c0 + 32 <= g.N) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(crow + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < g.N) crow[i] = o[i];
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_free[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// out[0] = 2^floor(log2(target / max|x|)) (1 if x is all zero): the power of two that lifts a gradient tensor into
+// fp16's normal range with `target` as its largest magnitude (the fused backward does the same, mlp_tc_bwd.cu)
+__global__ void __launch_bounds__(1024) pow2_scale_kernel(const float* __restrict__ x, int64_t n, float target,
+                                                          float* __restrict__ out) {
+  __shared__ float red[32];
+  float mx = 0.f;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) mx = fmaxf(mx, fabsf(__ldg(x + i)));
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    mx = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (threadIdx.x == 0) {
+      float sc = 1.f;
+      if (mx > 0.f && mx < 3.0e38f) sc = exp2f(fminf(fmaxf(floorf(log2f(target / mx)), -40.f), 40.f));
+      out[0] = sc;
+    }
+  }
+}
+
+}  // namespace swnerf
+
+using namespace swnerf;
+
+extern "C" {
+
+int swnerf_pow2_scale(const float* x, int64_t n, float target, float* out, void* stream) {
+  SW_REQUIRE(x && out && n >= 0 && target > 0.f, "pow2_scale: bad argument");
+  swnerf::pow2_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, target, out);
+  return swnerf::check_launch("pow2_scale");
+}
+
+int swnerf_hgemm_tc_supported(int64_t N, int64_t K) { return (N >= 16 && N <= 256 && K >= 1 && K <= 256) ? 1 : 0; }
+
+int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
+                    int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
+                    int64_t ldmask, float a_scale, const float* a_scale_dev, void* stream) {
+  SW_REQUIRE(A && W && C, "hgemm_tc: null pointer");
+  SW_REQUIRE(op == 0 || op == 1, "hgemm_tc: op must be 0 (x W^T) or 1 (dy W)");
+  SW_REQUIRE(M >= 0 && swnerf_hgemm_tc_supported(N, K), "hgemm_tc: needs 16 <= N <= 256 and 1 <= K <= 256");
+  const int act = act_flags & 3, mask_kind = (act_flags >> 4) & 3;
+  SW_REQUIRE(act <= 2 && mask_kind <= 1 && (act_flags & ~0x33) == 0, "hgemm_tc: bad act_flags");
+  SW_REQUIRE(a_scale > 0.f, "hgemm_tc: a_scale must be positive");
+  if (M == 0) return SWNERF_OK;
+  HgArgs g;
+  g.A = A; g.lda = lda; g.W = W; g.ldw = ldw; g.trans_w = op; g.C = C; g.ldc = ldc; g.M = M; g.N = (int)N; g.K = (int)K;
+  g.bias = bias; g.accumulate = accumulate; g.act = act; g.mask_kind = mask_kind; g.mask = mask; g.ldmask = ldmask;
+  g.n_pad = (int)((N + 15) / 16 * 16);
+  g.k_chunks = (int)((K + 63) / 64);
+  g.a_scale = a_scale; g.a_scale_dev = a_scale_dev;
+  g.vec_a = (aligned16(A) && lda % 4 == 0 && K % 4 == 0) ? 1 : 0;
+  g.vec_c = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
+  const size_t smem = (((size_t)g.k_chunks * g.n_pad * 128 + 1023) & ~(size_t)1023) + (size_t)g.k_chunks * HG_A_CHUNK + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // W <= 128 KB, A <= 64 KB
+    attr_done = true;
+  }
+  const int64_t tiles = (M + 127) / 128;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  hgemm_tc_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(g);
+  return check_launch("hgemm_tc");
+}
+
+}  // extern "C"

@@ -193,11 +193,12 @@ class TNeRF(nn.Module):
         self.feature = nn.Sequential(nn.Linear(net_dim, net_dim))
         self.layer_9 = nn.Sequential(nn.Linear(net_dim + dir_feat, net_dim // 2), nn.ELU())
         self.color = nn.Sequential(nn.Linear(net_dim // 2, 3), nn.ReLU())
+        self.tc_gemm = False      # layers on the tcgen05 GEMM (fp16 operands); set by tnerf.TNerfNetworkQuery
 
     @property
     def spec(self) -> MLPSpec:
         return MLPSpec(self.depth, self.net_dim, self.in_feat, self.time_feat, self.dir_feat, self._skips,
-                       "viewdirs", 4, act="elu", skip_extra=True, rgb_relu=True)
+                       "viewdirs", 4, act="elu", skip_extra=True, rgb_relu=True, tc=self.tc_gemm)
 
     def param_list(self):
         """trunk, view branch (layer_9), feature, density, colour - the order ops.MLPSpec documents."""

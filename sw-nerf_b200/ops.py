@@ -200,10 +200,16 @@ def searchsorted(a, v, out=None, side="left"):
 _ACT = {None: 0, False: 0, True: 1, "relu": 1, "elu": 2}
 
 
-def _gemm(op, A, B, C, M, N, K, bias=None, accumulate=False, relu=False, mask=None, mask_act="relu"):
+def _gemm(op, A, B, C, M, N, K, bias=None, accumulate=False, relu=False, mask=None, mask_act="relu", tc=False,
+          a_scale=1.0, a_scale_dev=None):
     """A, B, C, mask: (ptr, ld) pairs.  relu: False / True / "relu" / "elu" (the epilogue activation);
-    mask_act: which activation produced `mask` (its derivative scales the result)."""
+    mask_act: which activation produced `mask` (its derivative scales the result).  tc: run ops 0 / 1 on the
+    tensor cores (fp16 operands, fp32 accumulation) when the shape allows, else on the fp32 SIMT kernel."""
     flags = _ACT[relu] | ((1 if mask_act == "elu" else 0) << 4)
+    if tc and op in (0, 1) and 16 <= N <= 256 and 1 <= K <= 256:
+        call("swnerf_hgemm_tc", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), flags,
+             None if mask is None else mask[0], 0 if mask is None else mask[1], float(a_scale), a_scale_dev, stream())
+        return
     call("swnerf_sgemm", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), flags,
          None if mask is None else mask[0], 0 if mask is None else mask[1], stream())
 
@@ -226,13 +232,14 @@ class MLPSpec:
     alpha_linear, rgb_linear; for 'output' / 'linear': the output layer."""
 
     def __init__(self, D=8, W=256, in_pts=63, in_extra=0, in_views=27, skips=(4,), head="viewdirs", out_ch=4,
-                 act="relu", skip_extra=False, rgb_relu=False):
+                 act="relu", skip_extra=False, rgb_relu=False, tc=False):
         """act: trunk / view-branch activation ("relu", or "elu" for TNeRF, model.py:163-171,182);
         skip_extra: the skip concatenation re-injects [pts | extra] instead of pts alone (TNeRF, model.py:189-199);
         rgb_relu: the colour head ends in a ReLU (TNeRF, model.py:183-186)."""
         self.D, self.W, self.in_pts, self.in_extra, self.in_views = D, W, in_pts, in_extra, in_views
         self.skips, self.head, self.out_ch = tuple(skips), head, out_ch
         self.act, self.skip_extra, self.rgb_relu = act, bool(skip_extra), bool(rgb_relu)
+        self.tc = bool(tc)              # forward layers on the tcgen05 GEMM (fp16 operands) instead of fp32 SIMT
         if act not in ("relu", "elu"):
             raise ValueError("act must be 'relu' or 'elu'")
 
@@ -255,7 +262,9 @@ class MLPSpec:
 
 
 class MLPFp32Fn(torch.autograd.Function):
-    """Whole-network forward/backward on the fp32 SIMT GEMM kernels."""
+    """Whole-network forward/backward, one GEMM per layer: on the fp32 SIMT kernel (spec.tc False: the check mode, true
+    fp32 like the reference's nn.Linear), or with the forward and data-gradient GEMMs on the tcgen05 kernel (spec.tc
+    True: fp16 operands, fp32 accumulation; weight gradients stay fp32)."""
 
     @staticmethod
     def forward(ctx, spec: MLPSpec, need_grad, x_pts, x_extra, x_views, *params):
@@ -272,6 +281,7 @@ class MLPFp32Fn(torch.autograd.Function):
         hs: List[torch.Tensor] = []
         h_prev = None
         act = s.act
+        tc = s.tc
         n_buf = s.D if need_grad else 2
         bufs = [torch.empty((M, W), dtype=F32, device=dev) for _ in range(min(n_buf, s.D))]
         for i in range(s.D):
@@ -280,17 +290,17 @@ class MLPFp32Fn(torch.autograd.Function):
             wi, bi = P[2 * i], P[2 * i + 1][0]
             if i == 0:
                 if s.in_extra:
-                    _gemm(0, xp, wi, hm, M, W, s.in_pts)
-                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, bias=bi, accumulate=True, relu=act)
+                    _gemm(0, xp, wi, hm, M, W, s.in_pts, tc=tc)
+                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, bias=bi, accumulate=True, relu=act, tc=tc)
                 else:
-                    _gemm(0, xp, wi, hm, M, W, s.in_pts, bias=bi, relu=act)
+                    _gemm(0, xp, wi, hm, M, W, s.in_pts, bias=bi, relu=act, tc=tc)
             elif (i - 1) in s.skips:
-                _gemm(0, xp, wi, hm, M, W, s.in_pts)
+                _gemm(0, xp, wi, hm, M, W, s.in_pts, tc=tc)
                 if s.skip_extra and s.in_extra:
-                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, accumulate=True)
-                _gemm(0, h_prev, _off(wi, s.skip_in), hm, M, W, W, bias=bi, accumulate=True, relu=act)
+                    _gemm(0, xe, _off(wi, s.in_pts), hm, M, W, s.in_extra, accumulate=True, tc=tc)
+                _gemm(0, h_prev, _off(wi, s.skip_in), hm, M, W, W, bias=bi, accumulate=True, relu=act, tc=tc)
             else:
-                _gemm(0, h_prev, wi, hm, M, W, W, bias=bi, relu=act)
+                _gemm(0, h_prev, wi, hm, M, W, W, bias=bi, relu=act, tc=tc)
             h_prev = hm
             hs.append(h)
         out = torch.empty((M, s.out_dim), dtype=F32, device=dev)
@@ -303,17 +313,17 @@ class MLPFp32Fn(torch.autograd.Function):
             feat = torch.empty((M, W), dtype=F32, device=dev)
             hv = torch.empty((M, W // 2), dtype=F32, device=dev)
             fm, hvm = (feat.data_ptr(), W), (hv.data_ptr(), W // 2)
-            _gemm(0, h_prev, wa, _off(om, 3), M, 1, W, bias=ba)                       # model.py:49
-            _gemm(0, h_prev, wf, fm, M, W, W, bias=bf)                                # model.py:50
+            _gemm(0, h_prev, wa, _off(om, 3), M, 1, W, bias=ba, tc=tc)                       # model.py:49
+            _gemm(0, h_prev, wf, fm, M, W, W, bias=bf, tc=tc)                                # model.py:50
             if xv is not None:
-                _gemm(0, fm, wv, hvm, M, W // 2, W)                                   # model.py:51-55
-                _gemm(0, xv, _off(wv, W), hvm, M, W // 2, s.in_views, bias=bv, accumulate=True, relu=act)
+                _gemm(0, fm, wv, hvm, M, W // 2, W, tc=tc)                                   # model.py:51-55
+                _gemm(0, xv, _off(wv, W), hvm, M, W // 2, s.in_views, bias=bv, accumulate=True, relu=act, tc=tc)
             else:
-                _gemm(0, fm, wv, hvm, M, W // 2, W, bias=bv, relu=act)
-            _gemm(0, hvm, wr, om, M, 3, W // 2, bias=br, relu=s.rgb_relu)             # model.py:57 / :183-186
+                _gemm(0, fm, wv, hvm, M, W // 2, W, bias=bv, relu=act, tc=tc)
+            _gemm(0, hvm, wr, om, M, 3, W // 2, bias=br, relu=s.rgb_relu, tc=tc)             # model.py:57 / :183-186
         else:
             wo, bo = P[k], P[k + 1][0]
-            _gemm(0, h_prev, wo, om, M, s.out_dim, W, bias=bo)                        # model.py:60 / :136
+            _gemm(0, h_prev, wo, om, M, s.out_dim, W, bias=bo, tc=tc)                        # model.py:60 / :136
         if need_grad:
             ctx.spec = s
             ctx.x = (x_pts, x_extra, x_views)
@@ -345,6 +355,13 @@ class MLPFp32Fn(torch.autograd.Function):
             call("swnerf_act_bwd", d_in.data_ptr(), s.out_dim, ctx.out.data_ptr(), s.out_dim, M, 3, 0,
                  d_out.data_ptr(), s.out_dim, stream())
         dm = (d_out.data_ptr(), s.out_dim)
+        # data-gradient GEMMs on the tensor cores: one power-of-two scale, chosen on the device from max|d_out|, lifts
+        # the gradients into fp16's normal range (the weight-gradient GEMMs stay fp32)
+        tc, sc, scale_t = s.tc, None, None
+        if tc:
+            scale_t = torch.empty(1, dtype=F32, device=dev)
+            call("swnerf_pow2_scale", d_out.data_ptr(), M * s.out_dim, 32.0, scale_t.data_ptr(), stream())
+            sc = scale_t.data_ptr()
         ga = torch.empty((M, W), dtype=F32, device=dev)
         gb = torch.empty((M, W), dtype=F32, device=dev)
         g = (ga.data_ptr(), W)          # grad wrt pre-activation of the current trunk layer
@@ -359,25 +376,25 @@ class MLPFp32Fn(torch.autograd.Function):
             d_alpha = _off(dm, 3)
             _gemm(2, dm, hvm, GP[k + 6], 3, W // 2, M, accumulate=True)                # dW_rgb
             _colsum(dm, M, 3, G[k + 7].data_ptr())
-            _gemm(1, dm, wr, dhm, M, W // 2, 3, mask=hvm, mask_act=act)               # d_hv (masked)
+            _gemm(1, dm, wr, dhm, M, W // 2, 3, mask=hvm, mask_act=act, tc=tc, a_scale_dev=sc)               # d_hv (masked)
             _gemm(2, dhm, fm, GP[k], W // 2, W, M, accumulate=True)                    # dW_v[:, :W]
             if xv is not None:
                 _gemm(2, dhm, xv, _off(GP[k], W), W // 2, s.in_views, M, accumulate=True)
             _colsum(dhm, M, W // 2, G[k + 1].data_ptr())
             d_feat = torch.empty((M, W), dtype=F32, device=dev)
             dfm = (d_feat.data_ptr(), W)
-            _gemm(1, dhm, wv, dfm, M, W, W // 2)                                       # d_feature
+            _gemm(1, dhm, wv, dfm, M, W, W // 2, tc=tc, a_scale_dev=sc)                                       # d_feature
             _gemm(2, dfm, hlast, GP[k + 2], W, W, M, accumulate=True)                  # dW_f
             _colsum(dfm, M, W, G[k + 3].data_ptr())
             _gemm(2, d_alpha, hlast, GP[k + 4], 1, W, M, accumulate=True)              # dW_a
             _colsum(d_alpha, M, 1, G[k + 5].data_ptr())
-            _gemm(1, dfm, wf, g, M, W, W)
-            _gemm(1, d_alpha, wa, g, M, W, 1, accumulate=True, mask=hlast, mask_act=act)
+            _gemm(1, dfm, wf, g, M, W, W, tc=tc, a_scale_dev=sc)
+            _gemm(1, d_alpha, wa, g, M, W, 1, accumulate=True, mask=hlast, mask_act=act, tc=tc, a_scale_dev=sc)
         else:
             wo = P[k]
             _gemm(2, dm, hlast, GP[k], s.out_dim, W, M, accumulate=True)
             _colsum(dm, M, s.out_dim, G[k + 1].data_ptr())
-            _gemm(1, dm, wo, g, M, W, s.out_dim, mask=hlast, mask_act=act)
+            _gemm(1, dm, wo, g, M, W, s.out_dim, mask=hlast, mask_act=act, tc=tc, a_scale_dev=sc)
         d_pts = torch.zeros((M, s.in_pts), dtype=F32, device=dev) if ctx.pts_grad else None
         dpm = (d_pts.data_ptr(), s.in_pts) if d_pts is not None else None
         for i in range(s.D - 1, -1, -1):
@@ -389,19 +406,19 @@ class MLPFp32Fn(torch.autograd.Function):
                 if s.in_extra:
                     _gemm(2, g, xe, _off(GP[0], s.in_pts), W, s.in_extra, M, accumulate=True)
                 if dpm is not None:
-                    _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True)
+                    _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True, tc=tc, a_scale_dev=sc)
             elif (i - 1) in s.skips:
                 _gemm(2, g, xp, GP[2 * i], W, s.in_pts, M, accumulate=True)
                 if s.skip_extra and s.in_extra:
                     _gemm(2, g, xe, _off(GP[2 * i], s.in_pts), W, s.in_extra, M, accumulate=True)
                 _gemm(2, g, hp, _off(GP[2 * i], s.skip_in), W, W, M, accumulate=True)
                 if dpm is not None:
-                    _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True)
-                _gemm(1, g, _off(wi, s.skip_in), g_next, M, W, W, mask=hp, mask_act=act)
+                    _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True, tc=tc, a_scale_dev=sc)
+                _gemm(1, g, _off(wi, s.skip_in), g_next, M, W, W, mask=hp, mask_act=act, tc=tc, a_scale_dev=sc)
                 g, g_next = g_next, g
             else:
                 _gemm(2, g, hp, GP[2 * i], W, W, M, accumulate=True)
-                _gemm(1, g, wi, g_next, M, W, W, mask=hp, mask_act=act)
+                _gemm(1, g, wi, g_next, M, W, W, mask=hp, mask_act=act, tc=tc, a_scale_dev=sc)
                 g, g_next = g_next, g
         return (None, None, d_pts, None, None) + tuple(G)
 

@@ -64,11 +64,22 @@ class TNerfNetworkQuery:
     both encodings come from one kernel (no [N,S,3] points tensor, no expand of viewdirs) and the time encoding
     is one broadcast row."""
 
-    def __init__(self, embed_fn, embeddirs_fn, embedtime_fn, netchunk=1024 * 64, embd_time_discr=True):
+    def __init__(self, embed_fn, embeddirs_fn, embedtime_fn, netchunk=1024 * 64, embd_time_discr=True,
+                 precision=None):
         self.embed_fn, self.embeddirs_fn, self.embedtime_fn = embed_fn, embeddirs_fn, embedtime_fn
         self.netchunk, self.embd_time_discr = netchunk, embd_time_discr
+        # "tc": layers on the tcgen05 GEMM (fp16 operands, fp32 accumulate - the precision of the fused vanilla path);
+        # "fp32": the fp32 SIMT GEMM (the <= 1e-5 check mode)
+        self.precision = precision or os.environ.get("SWNERF_PRECISION", "tc")
+        if self.precision not in ("tc", "fp32"):
+            raise ValueError("precision must be 'tc' or 'fp32'")
+
+    def _arm(self, network_fn):
+        if hasattr(network_fn, "tc_gemm"):
+            network_fn.tc_gemm = self.precision == "tc"
 
     def __call__(self, inputs, viewdirs, ts, network_fn):
+        self._arm(network_fn)
         return run_network(inputs, viewdirs, ts, network_fn, embed_fn=self.embed_fn,
                            embeddirs_fn=self.embeddirs_fn, embedtime_fn=self.embedtime_fn,
                            netchunk=self.netchunk, embd_time_discr=self.embd_time_discr)
@@ -76,6 +87,7 @@ class TNerfNetworkQuery:
     def query_rays(self, ray_batch, z_vals, network_fn, view_col, cur_time: float):
         N, S = z_vals.shape
         dev = z_vals.device
+        self._arm(network_fn)
         if view_col < 0 or getattr(self.embed_fn, "L", None) is None or getattr(self.embeddirs_fn, "L", None) is None:
             rays_o, rays_d = ray_batch[:, 0:3], ray_batch[:, 3:6]
             pts = rays_o[..., None, :] + rays_d[..., None, :] * z_vals[..., :, None]
@@ -199,7 +211,8 @@ def create_nerf(args, device=None):
                   net_dim=128, skip_layer=4).to(device)
     grad_vars = list(model.parameters())
     network_query_fn = TNerfNetworkQuery(embed_fn, embeddirs_fn, embedtime_fn, netchunk=args.netchunk,
-                                         embd_time_discr=getattr(args, "nerf_type", "tnerf") != "temporal")
+                                         embd_time_discr=getattr(args, "nerf_type", "tnerf") != "temporal",
+                                         precision=getattr(args, "swnerf_precision", None))
     optimizer = torch.optim.Adam(params=grad_vars, lr=args.lrate, betas=(0.9, 0.999))
     if getattr(args, "do_half_precision", False):
         raise NotImplementedError("apex amp (run_tnerf.py:291-294) is not part of this path")

@@ -29,7 +29,7 @@ def _args(tmp):
                      netdepth=8, netwidth=256, netchunk=65536, lrate=5e-4, ft_path=None, basedir=str(tmp),
                      expname="e", no_reload=True, perturb=1.0, white_bkgd=True, raw_noise_std=0.0,
                      dataset_type="blender", no_ndc=False, lindisp=False, nerf_type="tnerf",
-                     do_half_precision=False)
+                     do_half_precision=False, swnerf_precision="fp32")
 
 
 def _model(seed):
@@ -154,3 +154,69 @@ def test_tnerf_render_frame_and_checkpoint_roundtrip(tmp_path):
     assert start == 1
     for (n, a), (_, b) in zip(model.state_dict().items(), kw2["network_fn"].state_dict().items()):
         assert torch.equal(a, b), n
+
+
+def test_hgemm_tc_vs_fp32_gemm():
+    """The layer-at-a-time tcgen05 GEMM against the fp32 SIMT GEMM: both operand orders, ragged M, N and K that are not
+    multiples of the tile, strided / unaligned / broadcast operands, bias + accumulate + ELU / ReLU, mask derivative.
+    Tolerance: fp16 operands (2^-11 relative each) over K <= 256 terms, fp32 accumulation."""
+    rs = np.random.RandomState(11)
+    for op, M, N, K, act, acc, mask_act in [(0, 1000, 128, 84, "elu", False, None), (0, 333, 256, 256, "relu", True, None),
+                                             (0, 129, 64, 155, "elu", False, None), (0, 5, 16, 3, False, False, None),
+                                             (1, 700, 63, 128, False, True, None), (1, 300, 256, 256, False, False, "relu"),
+                                             (1, 257, 128, 64, False, False, "elu"), (0, 4096, 128, 128, "elu", False, None)]:
+        wide = torch.from_numpy(rs.uniform(-1, 1, size=(M, K + 7)).astype(np.float32)).to(DEV)
+        A = wide[:, 3:3 + K]                                         # unaligned base, stride K + 7
+        Wm = torch.from_numpy(rs.uniform(-1, 1, size=((N, K) if op == 0 else (K, N))).astype(np.float32)).to(DEV) / np.sqrt(K)
+        bias = torch.from_numpy(rs.uniform(-1, 1, size=(N,)).astype(np.float32)).to(DEV) if op == 0 else None
+        C0 = torch.from_numpy(rs.uniform(-1, 1, size=(M, N)).astype(np.float32)).to(DEV)
+        mask = torch.from_numpy(rs.uniform(-1, 1, size=(M, N)).astype(np.float32)).to(DEV) if mask_act else None
+        outs = []
+        for tcflag in (False, True):
+            C = C0.clone()
+            ops._gemm(op, (A.data_ptr(), A.stride(0)), (Wm.data_ptr(), Wm.stride(0)), (C.data_ptr(), N), M, N, K,
+                      bias=None if bias is None else bias.data_ptr(), accumulate=acc, relu=act,
+                      mask=None if mask is None else (mask.data_ptr(), N), mask_act=mask_act or "relu", tc=tcflag,
+                      a_scale=4.0 if op == 1 else 1.0)
+            outs.append(C)
+        torch.cuda.synchronize()
+        err = float((outs[1] - outs[0]).abs().max())
+        assert err < 2e-3, (op, M, N, K, err)
+    # a broadcast row as A (the time encoding of one frame, stride 0)
+    row = torch.from_numpy(rs.uniform(-1, 1, size=(1, 21)).astype(np.float32)).to(DEV)
+    A = row.expand(200, -1)
+    Wm = torch.from_numpy(rs.uniform(-1, 1, size=(128, 21)).astype(np.float32)).to(DEV)
+    Cs = [torch.zeros(200, 128, device=DEV) for _ in range(2)]
+    for C, tcflag in zip(Cs, (False, True)):
+        ops._gemm(0, (A.data_ptr(), 0), (Wm.data_ptr(), 21), (C.data_ptr(), 128), 200, 128, 21, tc=tcflag)
+    assert float((Cs[0] - Cs[1]).abs().max()) < 2e-3
+
+
+@pytest.mark.parametrize("tag", ["det", "pert"])
+def test_render_rays_tnerf_tc_golden(golden, tag, tmp_path):
+    """precision='tc' (the default): the network's layers on the tcgen05 GEMM.  north_star: <= 1e-3 on the maps with
+    fp16 / TF32-class operands."""
+    g = golden("render_rays_tnerf")
+    args = _args(tmp_path); args.swnerf_precision = "tc"
+    kw_train, kw_test, _, _, _ = tnerf.create_nerf(args, device=torch.device(DEV))
+    model = kw_train["network_fn"]
+    model.load_state_dict({k: v.to(DEV) for k, v in O.make_params(O.tnerf_param_shapes(), int(g["seed"])).items()})
+    kw = dict(kw_test if tag == "det" else kw_train)
+    kw.pop("use_viewdirs"); kw.pop("ndc")
+    if tag == "pert":
+        kw["raw_noise_std"] = 0.5
+    rays, target = T(g[f"{tag}/rays"]), T(g[f"{tag}/target"])
+    before = _lib.launch_count()
+    ret = tnerf.render_rays(rays, retraw=True, pytest=True, **kw)
+    assert model.tc_gemm and _lib.launch_count() > before
+    for k in ["rgb_map", "acc_map"]:
+        assert float((ret[k].cpu() - torch.from_numpy(g[f"{tag}/{k}"])).abs().max()) < 1e-3, k
+    loss = torch.mean((ret["rgb_map"] - target) ** 2)
+    assert abs(loss.item() - float(g[f"{tag}/loss"])) < 1e-4
+    loss.backward()
+    num = den = 0.0
+    for n, p in model.named_parameters():
+        sub = p.grad.reshape(-1)[::251].cpu().double()
+        ref = torch.from_numpy(g[f"{tag}/gsub/{n}"]).double()
+        num += float((sub - ref).pow(2).sum()); den += float(ref.pow(2).sum())
+    assert (num / max(den, 1e-30)) ** 0.5 < 1e-2       # the tolerance of the fused vanilla path's gradients

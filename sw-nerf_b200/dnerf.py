@@ -78,7 +78,14 @@ class DNerfNetworkQuery:
                 and getattr(self.embed_fn, "L", None) == 10 and getattr(self.embedtime_fn, "L", None) == 10
                 and getattr(self.embeddirs_fn, "L", None) == 4)
 
+    def _arm(self, network_fn):
+        """Shapes without a fused kernel (MultiRes encoding widths, ...) run layer by layer: on the tcgen05 GEMM in 'tc'
+        precision, on the fp32 SIMT GEMM in 'fp32'."""
+        if hasattr(network_fn, "tc_gemm"):
+            network_fn.tc_gemm = self.precision == "tc"
+
     def __call__(self, inputs, viewdirs, ts, network_fn):
+        self._arm(network_fn)
         return run_network(inputs, viewdirs, ts, network_fn, embed_fn=self.embed_fn,
                            embeddirs_fn=self.embeddirs_fn, embedtime_fn=self.embedtime_fn,
                            netchunk=self.netchunk, embd_time_discr=self.embd_time_discr)
@@ -88,6 +95,7 @@ class DNerfNetworkQuery:
         dev = z_vals.device
         if self.uses_tc(network_fn, view_col >= 0):
             return tc.dnerf_query(network_fn, ray_batch, z_vals, view_col, float(cur_time))
+        self._arm(network_fn)
         L_pos = self.embed_fn.L
         L_dir = self.embeddirs_fn.L if view_col >= 0 else -1
         emb = ops.encode_points(ray_batch, z_vals, L_pos, L_dir, view_col)

@@ -15,6 +15,10 @@ from .ops import MLPSpec
 
 
 class _NerfBase(nn.Module):
+    # layer-at-a-time path on the tcgen05 GEMM (fp16 operands) instead of the fp32 SIMT GEMM: set by the network query
+    # objects from their `precision` when the shape has no fused kernel
+    tc_gemm = False
+
     def _build(self, D, W, input_ch, input_ch_views, output_ch, skips, use_viewdirs, output_color_ch=3):
         self.D, self.W = D, W
         self.input_ch, self.input_ch_views = input_ch, input_ch_views
@@ -35,7 +39,7 @@ class _NerfBase(nn.Module):
     def spec(self) -> MLPSpec:
         head = "viewdirs" if self.use_viewdirs else "output"
         return MLPSpec(self.D, self.W, self.input_ch, 0, self.input_ch_views, tuple(self.skips), head,
-                       self.output_ch)
+                       self.output_ch, tc=self.tc_gemm)
 
     def param_list(self):
         """Parameters in the order of include/swnerf_b200.h (trunk, views, feature, alpha, rgb)."""
@@ -109,6 +113,7 @@ class NeRFOriginal(_NerfBase):
 
 class DirectTemporalNeRF(nn.Module):
     """model.py:93-151: deformation network (x, t) -> dx, then the canonical NeRFOriginal at x + dx."""
+    tc_gemm = False           # as _NerfBase.tc_gemm; forwarded to the canonical network
 
     def __init__(self, D=8, W=256, input_ch=3, input_ch_views=3, input_ch_time=1, output_ch=4, skips=[4],
                  use_viewdirs=False, memory=[], embed_fn=None, zero_canonical=True):
@@ -133,7 +138,8 @@ class DirectTemporalNeRF(nn.Module):
 
     @property
     def time_spec(self) -> MLPSpec:
-        return MLPSpec(self.D, self.W, self.input_ch, self.input_ch_time, 0, tuple(self.skips), "linear", 3)
+        return MLPSpec(self.D, self.W, self.input_ch, self.input_ch_time, 0, tuple(self.skips), "linear", 3,
+                       tc=self.tc_gemm)
 
     def time_param_list(self):
         ps = []
@@ -161,6 +167,7 @@ class DirectTemporalNeRF(nn.Module):
             dx = self.query_time(input_pts, t)
             input_pts = self.embed_fn(input_pts[:, :3] + dx)                       # model.py:148-149
         occ = self._occ
+        occ.tc_gemm = self.tc_gemm
         out = ops.mlp_fp32(occ.spec, input_pts, None, input_views if occ.use_viewdirs else None, occ.param_list())
         return out, dx
 

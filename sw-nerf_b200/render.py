@@ -67,6 +67,7 @@ class NetworkQuery:
             training = torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in params))
             out = tc.TcOccPointsFn.apply(network_fn, vd, pts3.reshape(-1, 3).float(), s_, 0, 0.0, training, *params)
             return out.reshape(n, 4) if squeeze else out
+        self._arm(network_fn)
         if inputs.dim() == 2:                                  # load_model.py:57-58
             inputs = inputs[:, None]
             if viewdirs is not None and viewdirs.dim() == 3:
@@ -76,6 +77,11 @@ class NetworkQuery:
             return out
         return run_network(inputs, viewdirs, network_fn, embed_fn=self.embed_fn,
                            embeddirs_fn=self.embeddirs_fn, netchunk=self.netchunk)
+
+    def _arm(self, network_fn):
+        """Shapes without a fused kernel run layer by layer: on the tcgen05 GEMM in 'tc' precision, fp32 SIMT in 'fp32'."""
+        if hasattr(network_fn, "tc_gemm"):
+            network_fn.tc_gemm = self.precision == "tc"
 
     def uses_tc(self, network_fn, has_views):
         if torch.is_grad_enabled() and not tc.bwd_available() and \
@@ -89,6 +95,7 @@ class NetworkQuery:
         N, S = z_vals.shape
         if self.uses_tc(network_fn, view_col >= 0):
             return tc.mlp_query(network_fn, ray_batch, z_vals, view_col)
+        self._arm(network_fn)
         L_pos = getattr(self.embed_fn, "L", None)
         L_dir = getattr(self.embeddirs_fn, "L", -1) if view_col >= 0 else -1
         if L_pos is None:

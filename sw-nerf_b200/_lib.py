@@ -36,6 +36,7 @@ _SIG = {
     "swnerf_hgemm_tc": [_I32, _VP, _I64, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _VP, _I32, _I32, _VP, _I64, _F32, _VP,
                         _VP],
     "swnerf_pow2_scale": [_VP, _I64, _F32, _VP, _VP],
+    "swnerf_hgemm_tc_wgrad": [_VP, _I64, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _F32, _VP, _VP],
     "swnerf_act_bwd": [_VP, _I64, _VP, _I64, _I64, _I32, _I32, _VP, _I64, _VP],
     "swnerf_tc_packed_bytes": [],
     "swnerf_tc_packed_t_bytes": [],

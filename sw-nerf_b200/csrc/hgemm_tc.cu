@@ -32,6 +32,82 @@ struct HgArgs {
 
 constexpr int HG_A_CHUNK = 128 * 128;             // one [128 x 64] fp16 image
 
+// 128 rows m0 .. m0+127 of a row-major fp32 matrix (K columns, padded with zeros to kpad; rows beyond M are zero),
+// times `scale`, into fp16 operand images [128 x 64] (one per 64 columns) at dst.  NT threads, t = 0 .. NT-1.
+// When the column count divides the thread count a thread keeps its column and walks down the rows with eight
+// independent loads in flight (the loop is latency-bound otherwise).
+template <int NT>
+__device__ __forceinline__ void hg_load_tile(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int K,
+                                             int kpad, int vec, float scale, uint8_t* dst, int t) {
+  if (vec && (NT % (kpad >> 2)) == 0) {
+    const int units = kpad >> 2, rstep = NT / units, iters = 128 / rstep;
+    const int c = (t % units) << 2, r0 = t / units;
+    const bool c_ok = c < K;                               // K is a multiple of 4 on this path
+    const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
+    for (int j0 = 0; j0 < iters; j0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t m = m0 + r0 + (j0 + u) * rstep;
+        v[u] = (c_ok && m < M) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + (j0 + u) * rstep;
+        uint2 p;
+        p.x = pack_half2(v[u].x * scale, v[u].y * scale);
+        p.y = pack_half2(v[u].z * scale, v[u].w * scale);
+        *reinterpret_cast<uint2*>(dst + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
+      }
+    }
+  } else if (vec) {
+    const int units = kpad >> 2;
+    for (int idx = t; idx < 128 * units; idx += NT) {
+      const int r = idx / units, c = (idx - r * units) << 2;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int64_t m = m0 + r;
+      if (m < M && c < K) v = __ldg(reinterpret_cast<const float4*>(A + m * lda + c));
+      uint2 p; p.x = pack_half2(v.x * scale, v.y * scale); p.y = pack_half2(v.z * scale, v.w * scale);
+      *reinterpret_cast<uint2*>(dst + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
+    }
+  } else if ((NT % (kpad >> 1)) == 0) {
+    // unaligned / odd-width rows (first layers: encodings inside a wider row): same walk, two floats per step
+    const int pairs = kpad >> 1, rstep = NT / pairs, iters = 128 / rstep;
+    const int c = (t % pairs) << 1, r0 = t / pairs;
+    const bool x_ok = c < K, y_ok = c + 1 < K;
+    const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
+    for (int j0 = 0; j0 < iters; j0 += 8) {
+      float x[8], y[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t m = m0 + r0 + (j0 + u) * rstep;
+        const bool ok = m < M;
+        x[u] = (ok && x_ok) ? __ldg(A + m * lda + c) : 0.f;
+        y[u] = (ok && y_ok) ? __ldg(A + m * lda + c + 1) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + (j0 + u) * rstep;
+        *reinterpret_cast<uint32_t*>(dst + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
+            pack_half2(x[u] * scale, y[u] * scale);
+      }
+    }
+  } else {
+    const int pairs = kpad >> 1;
+    for (int idx = t; idx < 128 * pairs; idx += NT) {
+      const int r = idx / pairs, c = (idx - r * pairs) << 1;
+      const int64_t m = m0 + r;
+      float x = 0.f, y = 0.f;
+      if (m < M) {
+        if (c < K) x = __ldg(A + m * lda + c) * scale;
+        if (c + 1 < K) y = __ldg(A + m * lda + c + 1) * scale;
+      }
+      *reinterpret_cast<uint32_t*>(dst + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
+          pack_half2(x, y);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -76,78 +152,7 @@ __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t m0 = tile * 128;
       if (it > 0) mbar_wait(&a_free, (it - 1) & 1);        // the previous tile's MMAs have read the image
-      if (g.vec_a && (128 % (kpad >> 2)) == 0) {
-        // a thread keeps its column and walks down the rows, eight independent 16-byte loads in flight at a time
-        const int units = kpad >> 2, rstep = 128 / units;
-        const int c = (t % units) << 2, r0 = t / units;
-        const bool c_ok = c < g.K;
-        const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
-        for (int j0 = 0; j0 < units; j0 += 8) {
-          float4 v[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t m = m0 + r0 + (j0 + u) * rstep;
-            v[u] = (c_ok && m < g.M) ? __ldg(reinterpret_cast<const float4*>(g.A + m * g.lda + c))
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = r0 + (j0 + u) * rstep;
-            uint2 p;
-            p.x = pack_half2(v[u].x * a_scale_, v[u].y * a_scale_);
-            p.y = pack_half2(v[u].z * a_scale_, v[u].w * a_scale_);
-            *reinterpret_cast<uint2*>(sa + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
-          }
-        }
-      } else if (g.vec_a) {
-        const int units = kpad >> 2;                       // float4 per row (kpad is a multiple of 64)
-        for (int idx = t; idx < 128 * units; idx += 128) {
-          const int r = idx / units, c = (idx - r * units) << 2;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          const int64_t m = m0 + r;
-          if (m < g.M && c < g.K) {                        // K is a multiple of 4 on this path
-            v = __ldg(reinterpret_cast<const float4*>(g.A + m * g.lda + c));
-            v.x *= a_scale_; v.y *= a_scale_; v.z *= a_scale_; v.w *= a_scale_;
-          }
-          uint2 p; p.x = pack_half2(v.x, v.y); p.y = pack_half2(v.z, v.w);
-          *reinterpret_cast<uint2*>(sa + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
-        }
-      } else if ((128 % (kpad >> 1)) == 0) {
-        // unaligned / odd-width A (first layers: encodings inside a wider row): same walk, two floats per step
-        const int pairs = kpad >> 1, rstep = 128 / pairs;
-        const int c = (t % pairs) << 1, r0 = t / pairs;
-        const bool x_ok = c < g.K, y_ok = c + 1 < g.K;
-        const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
-        for (int j0 = 0; j0 < pairs; j0 += 8) {
-          float x[8], y[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int64_t m = m0 + r0 + (j0 + u) * rstep;
-            const bool ok = m < g.M;
-            x[u] = (ok && x_ok) ? __ldg(g.A + m * g.lda + c) : 0.f;
-            y[u] = (ok && y_ok) ? __ldg(g.A + m * g.lda + c + 1) : 0.f;
-          }
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const int r = r0 + (j0 + u) * rstep;
-            *reinterpret_cast<uint32_t*>(sa + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
-                pack_half2(x[u] * a_scale_, y[u] * a_scale_);
-          }
-        }
-      } else {
-        const int pairs = kpad >> 1;
-        for (int idx = t; idx < 128 * pairs; idx += 128) {
-          const int r = idx / pairs, c = (idx - r * pairs) << 1;
-          const int64_t m = m0 + r;
-          float x = 0.f, y = 0.f;
-          if (m < g.M) {
-            if (c < g.K) x = __ldg(g.A + m * g.lda + c) * a_scale_;
-            if (c + 1 < g.K) y = __ldg(g.A + m * g.lda + c + 1) * a_scale_;
-          }
-          *reinterpret_cast<uint32_t*>(sa + (uint32_t)(c >> 6) * HG_A_CHUNK + tile_off((uint32_t)r, (uint32_t)(c & 63))) =
-              pack_half2(x, y);
-        }
-      }
+      hg_load_tile<128>(g.A, g.lda, m0, g.M, g.K, kpad, g.vec_a, a_scale_, sa, t);
       fence_async_smem();
       named_bar_sync(1, 128);
       if (warp == 8) {
@@ -223,6 +228,83 @@ __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
+// Weight gradient G[N_out, K_in] += sum over samples of dY[m, :]^T X[m, :] (swnerf_sgemm op 2) on the tensor cores.
+// Both operands are read with K = the sample index, i.e. as MN-major operands over the same [128 samples x 64 columns]
+// images the forward builds (the saved-image trick of mlp_tc_bwd.cu): per 128-sample tile the CTA converts its dY tile
+// (times the gradient scale) and its X tile, issues 8 k-steps of M = 128 (one or two blocks of 128 output channels) x
+// N = K_in (padded to 64) MMAs, and keeps accumulating into tensor memory over ALL its tiles; one red.add flush at the end.
+struct HgWgArgs {
+  const float* dY; int64_t ldy;
+  const float* X; int64_t ldx;
+  float* G; int64_t ldg;
+  int64_t M; int n_out, k_in;
+  int m_blocks, n_pad;                            // blocks of 128 output channels (1 or 2); K_in rounded up to 64
+  float a_scale; const float* a_scale_dev;
+  int vec_y, vec_x;
+};
+
+__global__ void __launch_bounds__(256, 1) hgemm_tc_wgrad_kernel(const HgWgArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sy = smem;                                          // dY image: 2 m_blocks chunks of [128 x 64]
+  uint8_t* sx = smem + (size_t)g.m_blocks * 2 * HG_A_CHUNK;    // X image: n_pad / 64 chunks
+  __shared__ uint64_t mma_done;
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float a_scale_ = g.a_scale_dev ? __ldg(g.a_scale_dev) : g.a_scale, c_scale = 1.f / a_scale_;
+  if (threadIdx.x == 0) { mbar_init(&mma_done, 1); mbar_fence_init(); }
+  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const int64_t n_tiles = (g.M + 127) / 128;
+  const uint32_t idesc = umma_idesc_f16(128, g.n_pad, 1, 1);
+  uint32_t it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
+    if (it > 0) mbar_wait(&mma_done, (it - 1) & 1);            // the previous tile's MMAs have read both images
+    hg_load_tile<256>(g.dY, g.ldy, tile * 128, g.M, g.n_out, g.m_blocks * 128, g.vec_y, a_scale_, sy, threadIdx.x);
+    hg_load_tile<256>(g.X, g.ldx, tile * 128, g.M, g.k_in, g.n_pad, g.vec_x, 1.f, sx, threadIdx.x);
+    fence_async_smem();
+    __syncthreads();
+    if (warp == 0) {
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t y0 = smem_u32(sy), x0 = smem_u32(sx);
+        for (int ks = 0; ks < 8; ++ks) {                       // 16 samples per k-step = two 8-row atoms
+          const uint64_t bd = umma_desc_mnmajor(x0 + ks * 2048, HG_A_CHUNK);
+          for (int mb = 0; mb < g.m_blocks; ++mb)
+            umma_f16(tmem + mb * g.n_pad, umma_desc_mnmajor(y0 + mb * 2 * HG_A_CHUNK + ks * 2048, HG_A_CHUNK), bd, idesc,
+                     (it > 0 || ks > 0) ? 1u : 0u);
+        }
+        umma_commit(&mma_done);
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait(&mma_done, (it - 1) & 1);                          // it >= 1: every CTA owns at least one tile
+  tc_fence_after();
+  if (warp < 4) {
+    for (int mb = 0; mb < g.m_blocks; ++mb) {
+      const int row = mb * 128 + warp * 32 + lane;
+      for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mb * g.n_pad + c0, v);
+        tmem_ld_wait();
+        if (row < g.n_out) {
+          float* grow = g.G + (int64_t)row * g.ldg + c0;
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c0 + i < g.k_in) atomicAdd(grow + i, __uint_as_float(v[i]) * c_scale);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
 // out[0] = 2^floor(log2(target / max|x|)) (1 if x is all zero): the power of two that lifts a gradient tensor into
 // fp16's normal range with `target` as its largest magnitude (the fused backward does the same, mlp_tc_bwd.cu)
 __global__ void __launch_bounds__(1024) pow2_scale_kernel(const float* __restrict__ x, int64_t n, float target,
@@ -256,6 +338,32 @@ int swnerf_pow2_scale(const float* x, int64_t n, float target, float* out, void*
   SW_REQUIRE(x && out && n >= 0 && target > 0.f, "pow2_scale: bad argument");
   swnerf::pow2_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(x, n, target, out);
   return swnerf::check_launch("pow2_scale");
+}
+
+int swnerf_hgemm_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* G, int64_t ldg, int64_t M,
+                          int64_t n_out, int64_t k_in, float a_scale, const float* a_scale_dev, void* stream) {
+  SW_REQUIRE(dY && X && G, "hgemm_tc_wgrad: null pointer");
+  SW_REQUIRE(M >= 0 && n_out >= 32 && n_out <= 256 && k_in >= 1 && k_in <= 256,
+             "hgemm_tc_wgrad: needs 32 <= n_out <= 256 and 1 <= k_in <= 256");
+  SW_REQUIRE(a_scale > 0.f, "hgemm_tc_wgrad: a_scale must be positive");
+  if (M == 0) return SWNERF_OK;
+  HgWgArgs g;
+  g.dY = dY; g.ldy = ldy; g.X = X; g.ldx = ldx; g.G = G; g.ldg = ldg; g.M = M; g.n_out = (int)n_out; g.k_in = (int)k_in;
+  g.m_blocks = n_out > 128 ? 2 : 1;
+  g.n_pad = (int)((k_in + 63) / 64 * 64);
+  g.a_scale = a_scale; g.a_scale_dev = a_scale_dev;
+  g.vec_y = (aligned16(dY) && ldy % 4 == 0 && n_out % 4 == 0) ? 1 : 0;
+  g.vec_x = (aligned16(X) && ldx % 4 == 0 && k_in % 4 == 0) ? 1 : 0;
+  const size_t smem = (size_t)(g.m_blocks * 2 + g.n_pad / 64) * HG_A_CHUNK + 1024;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaFuncSetAttribute(hgemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
+    attr_done = true;
+  }
+  const int64_t tiles = (M + 127) / 128;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  hgemm_tc_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(g);
+  return check_launch("hgemm_tc_wgrad");
 }
 
 int swnerf_hgemm_tc_supported(int64_t N, int64_t K) { return (N >= 16 && N <= 256 && K >= 1 && K <= 256) ? 1 : 0; }

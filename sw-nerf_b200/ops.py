@@ -210,6 +210,10 @@ def _gemm(op, A, B, C, M, N, K, bias=None, accumulate=False, relu=False, mask=No
         call("swnerf_hgemm_tc", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), flags,
              None if mask is None else mask[0], 0 if mask is None else mask[1], float(a_scale), a_scale_dev, stream())
         return
+    if tc and op == 2 and accumulate and 32 <= M <= 256 and 1 <= N <= 256:
+        # C[M = out channels, N = in channels] += A[K = samples, M]^T . B[K, N]
+        call("swnerf_hgemm_tc_wgrad", A[0], A[1], B[0], B[1], C[0], C[1], K, M, N, float(a_scale), a_scale_dev, stream())
+        return
     call("swnerf_sgemm", op, A[0], A[1], B[0], B[1], C[0], C[1], M, N, K, bias, int(accumulate), flags,
          None if mask is None else mask[0], 0 if mask is None else mask[1], stream())
 
@@ -374,25 +378,25 @@ class MLPFp32Fn(torch.autograd.Function):
             d_hv = torch.empty((M, W // 2), dtype=F32, device=dev)
             dhm = (d_hv.data_ptr(), W // 2)
             d_alpha = _off(dm, 3)
-            _gemm(2, dm, hvm, GP[k + 6], 3, W // 2, M, accumulate=True)                # dW_rgb
+            _gemm(2, dm, hvm, GP[k + 6], 3, W // 2, M, accumulate=True, tc=tc, a_scale_dev=sc)                # dW_rgb
             _colsum(dm, M, 3, G[k + 7].data_ptr())
             _gemm(1, dm, wr, dhm, M, W // 2, 3, mask=hvm, mask_act=act, tc=tc, a_scale_dev=sc)               # d_hv (masked)
-            _gemm(2, dhm, fm, GP[k], W // 2, W, M, accumulate=True)                    # dW_v[:, :W]
+            _gemm(2, dhm, fm, GP[k], W // 2, W, M, accumulate=True, tc=tc, a_scale_dev=sc)                    # dW_v[:, :W]
             if xv is not None:
-                _gemm(2, dhm, xv, _off(GP[k], W), W // 2, s.in_views, M, accumulate=True)
+                _gemm(2, dhm, xv, _off(GP[k], W), W // 2, s.in_views, M, accumulate=True, tc=tc, a_scale_dev=sc)
             _colsum(dhm, M, W // 2, G[k + 1].data_ptr())
             d_feat = torch.empty((M, W), dtype=F32, device=dev)
             dfm = (d_feat.data_ptr(), W)
             _gemm(1, dhm, wv, dfm, M, W, W // 2, tc=tc, a_scale_dev=sc)                                       # d_feature
-            _gemm(2, dfm, hlast, GP[k + 2], W, W, M, accumulate=True)                  # dW_f
+            _gemm(2, dfm, hlast, GP[k + 2], W, W, M, accumulate=True, tc=tc, a_scale_dev=sc)                  # dW_f
             _colsum(dfm, M, W, G[k + 3].data_ptr())
-            _gemm(2, d_alpha, hlast, GP[k + 4], 1, W, M, accumulate=True)              # dW_a
+            _gemm(2, d_alpha, hlast, GP[k + 4], 1, W, M, accumulate=True, tc=tc, a_scale_dev=sc)              # dW_a
             _colsum(d_alpha, M, 1, G[k + 5].data_ptr())
             _gemm(1, dfm, wf, g, M, W, W, tc=tc, a_scale_dev=sc)
             _gemm(1, d_alpha, wa, g, M, W, 1, accumulate=True, mask=hlast, mask_act=act, tc=tc, a_scale_dev=sc)
         else:
             wo = P[k]
-            _gemm(2, dm, hlast, GP[k], s.out_dim, W, M, accumulate=True)
+            _gemm(2, dm, hlast, GP[k], s.out_dim, W, M, accumulate=True, tc=tc, a_scale_dev=sc)
             _colsum(dm, M, s.out_dim, G[k + 1].data_ptr())
             _gemm(1, dm, wo, g, M, W, s.out_dim, mask=hlast, mask_act=act, tc=tc, a_scale_dev=sc)
         d_pts = torch.zeros((M, s.in_pts), dtype=F32, device=dev) if ctx.pts_grad else None
@@ -402,22 +406,22 @@ class MLPFp32Fn(torch.autograd.Function):
             _colsum(g, M, W, G[2 * i + 1].data_ptr())
             hp = (hs[i - 1].data_ptr(), W) if i > 0 else None
             if i == 0:
-                _gemm(2, g, xp, GP[0], W, s.in_pts, M, accumulate=True)
+                _gemm(2, g, xp, GP[0], W, s.in_pts, M, accumulate=True, tc=tc, a_scale_dev=sc)
                 if s.in_extra:
-                    _gemm(2, g, xe, _off(GP[0], s.in_pts), W, s.in_extra, M, accumulate=True)
+                    _gemm(2, g, xe, _off(GP[0], s.in_pts), W, s.in_extra, M, accumulate=True, tc=tc, a_scale_dev=sc)
                 if dpm is not None:
                     _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True, tc=tc, a_scale_dev=sc)
             elif (i - 1) in s.skips:
-                _gemm(2, g, xp, GP[2 * i], W, s.in_pts, M, accumulate=True)
+                _gemm(2, g, xp, GP[2 * i], W, s.in_pts, M, accumulate=True, tc=tc, a_scale_dev=sc)
                 if s.skip_extra and s.in_extra:
-                    _gemm(2, g, xe, _off(GP[2 * i], s.in_pts), W, s.in_extra, M, accumulate=True)
-                _gemm(2, g, hp, _off(GP[2 * i], s.skip_in), W, W, M, accumulate=True)
+                    _gemm(2, g, xe, _off(GP[2 * i], s.in_pts), W, s.in_extra, M, accumulate=True, tc=tc, a_scale_dev=sc)
+                _gemm(2, g, hp, _off(GP[2 * i], s.skip_in), W, W, M, accumulate=True, tc=tc, a_scale_dev=sc)
                 if dpm is not None:
                     _gemm(1, g, wi, dpm, M, s.in_pts, W, accumulate=True, tc=tc, a_scale_dev=sc)
                 _gemm(1, g, _off(wi, s.skip_in), g_next, M, W, W, mask=hp, mask_act=act, tc=tc, a_scale_dev=sc)
                 g, g_next = g_next, g
             else:
-                _gemm(2, g, hp, GP[2 * i], W, W, M, accumulate=True)
+                _gemm(2, g, hp, GP[2 * i], W, W, M, accumulate=True, tc=tc, a_scale_dev=sc)
                 _gemm(1, g, wi, g_next, M, W, W, mask=hp, mask_act=act, tc=tc, a_scale_dev=sc)
                 g, g_next = g_next, g
         return (None, None, d_pts, None, None) + tuple(G)

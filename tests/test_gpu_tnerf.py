@@ -182,6 +182,20 @@ def test_hgemm_tc_vs_fp32_gemm():
         torch.cuda.synchronize()
         err = float((outs[1] - outs[0]).abs().max())
         assert err < 2e-3, (op, M, N, K, err)
+    # weight gradients: G[n_out, k_in] += dY^T X over ragged sample counts, gradient-sized dY lifted by a power of two
+    for n_out, k_in, M in [(128, 84, 1000), (256, 256, 700), (64, 155, 333), (128, 128, 20000), (256, 63, 129)]:
+        wide = torch.from_numpy(rs.uniform(-1, 1, size=(M, k_in + 5)).astype(np.float32)).to(DEV)
+        X = wide[:, 1:1 + k_in]
+        dY = torch.from_numpy(rs.normal(size=(M, n_out)).astype(np.float32)).to(DEV) * 1e-6
+        scale = torch.empty(1, device=DEV)
+        _lib.call("swnerf_pow2_scale", dY.data_ptr(), dY.numel(), 32.0, scale.data_ptr(), _lib.stream())
+        assert 16.0 <= float(scale.item() * dY.abs().max().item()) <= 32.0
+        Gs = [torch.zeros(n_out, k_in, device=DEV) for _ in range(2)]
+        for G, tcflag in zip(Gs, (False, True)):
+            ops._gemm(2, (dY.data_ptr(), n_out), (X.data_ptr(), X.stride(0)), (G.data_ptr(), k_in), n_out, k_in, M,
+                      accumulate=True, tc=tcflag, a_scale_dev=scale.data_ptr())
+        err = float((Gs[0] - Gs[1]).abs().max() / Gs[0].abs().max())
+        assert err < 2e-3, (n_out, k_in, M, err)
     # a broadcast row as A (the time encoding of one frame, stride 0)
     row = torch.from_numpy(rs.uniform(-1, 1, size=(1, 21)).astype(np.float32)).to(DEV)
     A = row.expand(200, -1)

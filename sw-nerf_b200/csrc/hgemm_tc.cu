@@ -5,7 +5,7 @@
 //     C[M,N] = act( A[M,K] . B^T + bias ) (+ C) (* act'(mask)),     B = W[N,K]  (forward)  or  W[K,N] read transposed (dgrad)
 // A and C stay fp32 row-major in HBM (any row stride, any alignment): the kernel converts a 128-row tile of A to the
 // fp16 operand image itself (tc_common.cuh: rows of 128 B, 8-row atoms, 16-B units XOR-swizzled), and builds the image
-// of the small weight matrix once per CTA.  Persistent CTAs, 384 threads: warps 8-11 load / convert the next A tile and
+// of the small weight matrix once per CTA.  Persistent CTAs, 512 threads: warps 8-15 load / convert the next A tile and
 // one of their lanes issues the K/16 `tcgen05.mma.cta_group::1.kind::f16` of the tile; warps 0-7 read the fp32
 // accumulator (two 256-column TMEM buffers alternate) and run the epilogue, so a tile's stores overlap the next tile's
 // loads and MMAs.  HBM-bound by construction (fp32 activations in and out: 4 (K + N) bytes per row).
@@ -36,6 +36,28 @@ constexpr int HG_A_CHUNK = 128 * 128;             // one [128 x 64] fp16 image
 // times `scale`, into fp16 operand images [128 x 64] (one per 64 columns) at dst.  NT threads, t = 0 .. NT-1.
 // When the column count divides the thread count a thread keeps its column and walks down the rows with eight
 // independent loads in flight (the loop is latency-bound otherwise).
+// a thread's column c of rows r0, r0 + rstep, ...: UN independent 16-byte loads in flight, then convert and store
+template <int UN>
+__device__ __forceinline__ void hg_walk_vec(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int c,
+                                            bool c_ok, int r0, int rstep, int iters, float scale, uint8_t* dst_chunk) {
+  for (int j0 = 0; j0 < iters; j0 += UN) {
+    float4 v[UN];
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int64_t m = m0 + r0 + (j0 + u) * rstep;
+      v[u] = (c_ok && m < M) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < UN; ++u) {
+      const int r = r0 + (j0 + u) * rstep;
+      uint2 p;
+      p.x = pack_half2(v[u].x * scale, v[u].y * scale);
+      p.y = pack_half2(v[u].z * scale, v[u].w * scale);
+      *reinterpret_cast<uint2*>(dst_chunk + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
+    }
+  }
+}
+
 template <int NT>
 __device__ __forceinline__ void hg_load_tile(const float* __restrict__ A, int64_t lda, int64_t m0, int64_t M, int K,
                                              int kpad, int vec, float scale, uint8_t* dst, int t) {
@@ -44,22 +66,8 @@ __device__ __forceinline__ void hg_load_tile(const float* __restrict__ A, int64_
     const int c = (t % units) << 2, r0 = t / units;
     const bool c_ok = c < K;                               // K is a multiple of 4 on this path
     const uint32_t cbase = (uint32_t)(c >> 6) * HG_A_CHUNK;
-    for (int j0 = 0; j0 < iters; j0 += 8) {
-      float4 v[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int64_t m = m0 + r0 + (j0 + u) * rstep;
-        v[u] = (c_ok && m < M) ? __ldg(reinterpret_cast<const float4*>(A + m * lda + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int r = r0 + (j0 + u) * rstep;
-        uint2 p;
-        p.x = pack_half2(v[u].x * scale, v[u].y * scale);
-        p.y = pack_half2(v[u].z * scale, v[u].w * scale);
-        *reinterpret_cast<uint2*>(dst + cbase + tile_off((uint32_t)r, (uint32_t)(c & 63))) = p;
-      }
-    }
+    if (iters % 16 == 0) hg_walk_vec<16>(A, lda, m0, M, c, c_ok, r0, rstep, iters, scale, dst + cbase);
+    else hg_walk_vec<8>(A, lda, m0, M, c, c_ok, r0, rstep, iters, scale, dst + cbase);
   } else if (vec) {
     const int units = kpad >> 2;
     for (int idx = t; idx < 128 * units; idx += NT) {
@@ -108,7 +116,7 @@ __device__ __forceinline__ void hg_load_tile(const float* __restrict__ A, int64_
   }
 }
 
-__global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
+__global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const uint32_t w_chunk = (uint32_t)g.n_pad * 128u;
@@ -116,8 +124,10 @@ __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
   uint8_t* sa = smem + (((uint32_t)g.k_chunks * w_chunk + 1023u) & ~1023u);
   __shared__ uint64_t a_free, acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
+  __shared__ __align__(16) float s_bias[256];               // bias padded with zeros: unconditional vector reads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kpad = g.k_chunks * 64;
+  if (threadIdx.x < 256) s_bias[threadIdx.x] = (g.bias && (int)threadIdx.x < g.N) ? __ldg(g.bias + threadIdx.x) : 0.f;
   const float a_scale_ = g.a_scale_dev ? __ldg(g.a_scale_dev) : g.a_scale, c_scale = 1.f / a_scale_;
 
   if (threadIdx.x == 0) {
@@ -145,16 +155,16 @@ __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
 
   if (warp >= 8) {
     // ===================== loaders (+ the MMA issuer) =====================
-    const int t = threadIdx.x - 256;                       // 0..127
+    const int t = threadIdx.x - 256;                       // 0..255
     const uint32_t idesc = umma_idesc_f16(128, g.n_pad, 0, 0);
     const int ksteps = (g.K + 15) / 16;
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t m0 = tile * 128;
       if (it > 0) mbar_wait(&a_free, (it - 1) & 1);        // the previous tile's MMAs have read the image
-      hg_load_tile<128>(g.A, g.lda, m0, g.M, g.K, kpad, g.vec_a, a_scale_, sa, t);
+      hg_load_tile<256>(g.A, g.lda, m0, g.M, g.K, kpad, g.vec_a, a_scale_, sa, t);
       fence_async_smem();
-      named_bar_sync(1, 128);
+      named_bar_sync(1, 256);
       if (warp == 8) {
         const uint32_t buf = it & 1;
         if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);      // the epilogue has drained this accumulator
@@ -196,11 +206,11 @@ __global__ void __launch_bounds__(384, 1) hgemm_tc_kernel(const HgArgs g) {
           for (int i = 0; i < 32; ++i) {
             const int n = c0 + i;
             float x = __uint_as_float(v[i]) * c_scale;
+            x += s_bias[n];
             if (n < g.N) {
-              if (g.bias) x += __ldg(g.bias + n);
               if (g.accumulate) x += crow[i];
               if (g.act == 1) x = fmaxf(x, 0.f);
-              else if (g.act == 2) x = x > 0.f ? x : expm1f(x);
+              else if (g.act == 2) x = x > 0.f ? x : __expf(x) - 1.f;      // abs. error 1e-7: below the fp16 operands' rounding
               if (mrow) {
                 const float y = __ldg(mrow + i);
                 x = (y > 0.f) ? x : (g.mask_kind == 1 ? x * (y + 1.f) : 0.f);
@@ -394,7 +404,7 @@ int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t
   }
   const int64_t tiles = (M + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  hgemm_tc_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(g);
+  hgemm_tc_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(g);
   return check_launch("hgemm_tc");
 }
 

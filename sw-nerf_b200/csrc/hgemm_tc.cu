@@ -28,9 +28,12 @@ struct HgArgs {
   float a_scale;                                  // A is multiplied by a_scale before rounding, the product by 1 / a_scale
   const float* a_scale_dev;                       // if set: the scale is read from device memory (swnerf_pow2_scale)
   int vec_a, vec_c;                               // float4 access allowed (alignment checked on the host)
+  int a_bufs;                                     // 2 when two A images fit next to the weight image, else 1
 };
 
 constexpr int HG_A_CHUNK = 128 * 128;             // one [128 x 64] fp16 image
+
+__device__ __forceinline__ bool aligned16_dev(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 // 128 rows m0 .. m0+127 of a row-major fp32 matrix (K columns, padded with zeros to kpad; rows beyond M are zero),
 // times `scale`, into fp16 operand images [128 x 64] (one per 64 columns) at dst.  NT threads, t = 0 .. NT-1.
@@ -122,7 +125,7 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
   const uint32_t w_chunk = (uint32_t)g.n_pad * 128u;
   uint8_t* sw = smem;
   uint8_t* sa = smem + (((uint32_t)g.k_chunks * w_chunk + 1023u) & ~1023u);
-  __shared__ uint64_t a_free, acc_full[2], acc_free[2];
+  __shared__ uint64_t a_free[2], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256];               // bias padded with zeros: unconditional vector reads
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -131,7 +134,7 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
   const float a_scale_ = g.a_scale_dev ? __ldg(g.a_scale_dev) : g.a_scale, c_scale = 1.f / a_scale_;
 
   if (threadIdx.x == 0) {
-    mbar_init(&a_free, 1);
+    mbar_init(&a_free[0], 1); mbar_init(&a_free[1], 1);
     mbar_init(&acc_full[0], 1); mbar_init(&acc_full[1], 1);
     mbar_init(&acc_free[0], 8); mbar_init(&acc_free[1], 8);
     mbar_fence_init();
@@ -161,8 +164,11 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
     uint32_t it = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
       const int64_t m0 = tile * 128;
-      if (it > 0) mbar_wait(&a_free, (it - 1) & 1);        // the previous tile's MMAs have read the image
-      hg_load_tile<256>(g.A, g.lda, m0, g.M, g.K, kpad, g.vec_a, a_scale_, sa, t);
+      // image buffer ab: with two buffers the load of tile it overlaps the MMAs of tile it-1
+      const uint32_t ab = (g.a_bufs == 2) ? (it & 1) : 0u, use = (g.a_bufs == 2) ? (it >> 1) : it;
+      if (use > 0) mbar_wait(&a_free[ab], (use - 1) & 1);  // the MMAs that read this buffer last have completed
+      uint8_t* sab = sa + (size_t)ab * g.k_chunks * HG_A_CHUNK;
+      hg_load_tile<256>(g.A, g.lda, m0, g.M, g.K, kpad, g.vec_a, a_scale_, sab, t);
       fence_async_smem();
       named_bar_sync(1, 256);
       if (warp == 8) {
@@ -170,13 +176,13 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
         if (it >= 2) mbar_wait(&acc_free[buf], ((it >> 1) - 1) & 1);      // the epilogue has drained this accumulator
         tc_fence_after();
         if (elect_one()) {
-          const uint32_t a0 = smem_u32(sa), b0 = smem_u32(sw);
+          const uint32_t a0 = smem_u32(sab), b0 = smem_u32(sw);
           for (int ks = 0; ks < ksteps; ++ks) {
             const uint32_t kb = ks >> 2, ko = (ks & 3) * 32;
             umma_f16(tmem + buf * 256, umma_desc_kmajor(a0 + kb * HG_A_CHUNK + ko),
                      umma_desc_kmajor(b0 + kb * w_chunk + ko), idesc, ks > 0 ? 1u : 0u);
           }
-          umma_commit(&a_free);
+          umma_commit(&a_free[ab]);
           umma_commit(&acc_full[buf]);
         }
         __syncwarp();
@@ -199,26 +205,55 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0, v);
         tmem_ld_wait();
         if (m < g.M) {
+          // every option is tested once per 32-column block; the element loops inside are branch-free
           float* crow = g.C + m * g.ldc + c0;
-          const float* mrow = g.mask ? g.mask + m * g.ldmask + c0 : nullptr;
+          const bool full = c0 + 32 <= g.N, vec = g.vec_c && full;
           float o[32];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const int n = c0 + i;
-            float x = __uint_as_float(v[i]) * c_scale;
-            x += s_bias[n];
-            if (n < g.N) {
-              if (g.accumulate) x += crow[i];
-              if (g.act == 1) x = fmaxf(x, 0.f);
-              else if (g.act == 2) x = x > 0.f ? x : __expf(x) - 1.f;      // abs. error 1e-7: below the fp16 operands' rounding
-              if (mrow) {
-                const float y = __ldg(mrow + i);
-                x = (y > 0.f) ? x : (g.mask_kind == 1 ? x * (y + 1.f) : 0.f);
+          for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(v[i]), c_scale, s_bias[c0 + i]);
+          if (g.accumulate) {
+            if (vec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 c4 = *reinterpret_cast<const float4*>(crow + i);
+                o[i] += c4.x; o[i + 1] += c4.y; o[i + 2] += c4.z; o[i + 3] += c4.w;
               }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (c0 + i < g.N) o[i] += crow[i];
             }
-            o[i] = x;
           }
-          if (g.vec_c && c0 + 32 <= g.N) {
+          if (g.act == 1) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = fmaxf(o[i], 0.f);
+          } else if (g.act == 2) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) o[i] = o[i] > 0.f ? o[i] : __expf(o[i]) - 1.f;   // abs. error 1e-7: below fp16 rounding
+          }
+          if (g.mask) {
+            const float* mrow = g.mask + m * g.ldmask + c0;
+            const bool mvec = full && aligned16_dev(mrow);
+            float y[32];
+            if (mvec) {
+#pragma unroll
+              for (int i = 0; i < 32; i += 4) {
+                const float4 m4 = __ldg(reinterpret_cast<const float4*>(mrow + i));
+                y[i] = m4.x; y[i + 1] = m4.y; y[i + 2] = m4.z; y[i + 3] = m4.w;
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) y[i] = (c0 + i < g.N) ? __ldg(mrow + i) : 1.f;
+            }
+            if (g.mask_kind == 1) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = y[i] > 0.f ? o[i] : o[i] * (y[i] + 1.f);
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) o[i] = y[i] > 0.f ? o[i] : 0.f;
+            }
+          }
+          if (vec) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(crow + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
           } else {
@@ -396,7 +431,9 @@ int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t
   g.a_scale = a_scale; g.a_scale_dev = a_scale_dev;
   g.vec_a = (aligned16(A) && lda % 4 == 0 && K % 4 == 0) ? 1 : 0;
   g.vec_c = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
-  const size_t smem = (((size_t)g.k_chunks * g.n_pad * 128 + 1023) & ~(size_t)1023) + (size_t)g.k_chunks * HG_A_CHUNK + 1024;
+  const size_t w_bytes = ((size_t)g.k_chunks * g.n_pad * 128 + 1023) & ~(size_t)1023, a_bytes = (size_t)g.k_chunks * HG_A_CHUNK;
+  g.a_bufs = (w_bytes + 2 * a_bytes + 1024 <= 200 * 1024) ? 2 : 1;
+  const size_t smem = w_bytes + g.a_bufs * a_bytes + 1024;
   static bool attr_done = false;
   if (!attr_done) {
     cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // W <= 128 KB, A <= 64 KB

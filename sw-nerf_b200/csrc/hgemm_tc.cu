@@ -288,7 +288,8 @@ struct HgWgArgs {
   int vec_y, vec_x;
 };
 
-__global__ void __launch_bounds__(256, 1) hgemm_tc_wgrad_kernel(const HgWgArgs g) {
+template <int TMEM_COLS>
+__global__ void __launch_bounds__(256, (TMEM_COLS <= 256) ? 2 : 1) hgemm_tc_wgrad_kernel(const HgWgArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sy = smem;                                          // dY image: 2 m_blocks chunks of [128 x 64]
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(256, 1) hgemm_tc_wgrad_kernel(const HgWgArgs g
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float a_scale_ = g.a_scale_dev ? __ldg(g.a_scale_dev) : g.a_scale, c_scale = 1.f / a_scale_;
   if (threadIdx.x == 0) { mbar_init(&mma_done, 1); mbar_fence_init(); }
-  if (warp == 0) tmem_alloc<512>(&tmem_slot);
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(256, 1) hgemm_tc_wgrad_kernel(const HgWgArgs g
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<512>(tmem);
+  if (warp == 0) tmem_dealloc<TMEM_COLS>(tmem);
 }
 
 // out[0] = 2^floor(log2(target / max|x|)) (1 if x is all zero): the power of two that lifts a gradient tensor into
@@ -402,12 +403,22 @@ int swnerf_hgemm_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t 
   const size_t smem = (size_t)(g.m_blocks * 2 + g.n_pad / 64) * HG_A_CHUNK + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(hgemm_tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
+    cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
+    cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
+    cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
     attr_done = true;
   }
+  // accumulator columns = m_blocks x n_pad: a CTA that needs at most half of tensor memory shares its SM with a second
+  // one (their loads and MMAs overlap; the kernel has no other latency hiding)
+  const int cols = g.m_blocks * g.n_pad;
   const int64_t tiles = (M + 127) / 128;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  hgemm_tc_wgrad_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(g);
+  const int per_sm = (cols <= 256 && smem <= 100 * 1024) ? 2 : 1;
+  const int64_t max_ctas = (int64_t)per_sm * sm_count();
+  const int grid = (int)(tiles < max_ctas ? tiles : max_ctas);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cols <= 128) hgemm_tc_wgrad_kernel<128><<<grid, 256, smem, st>>>(g);
+  else if (cols <= 256) hgemm_tc_wgrad_kernel<256><<<grid, 256, smem, st>>>(g);
+  else hgemm_tc_wgrad_kernel<512><<<grid, 256, smem, st>>>(g);
   return check_launch("hgemm_tc_wgrad");
 }
 

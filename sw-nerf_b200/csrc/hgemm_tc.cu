@@ -141,13 +141,24 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
   }
   if (warp == 0) tmem_alloc<512>(&tmem_slot);
   // weight image: B(n, k) for n < n_pad, k < kpad, zero outside [N x K]
-  for (int idx = threadIdx.x; idx < g.n_pad * kpad; idx += blockDim.x) {
-    int n, k;
-    if (g.trans_w) { n = idx % g.n_pad; k = idx / g.n_pad; } else { k = idx % kpad; n = idx / kpad; }
-    float v = 0.f;
-    if (n < g.N && k < g.K) v = g.trans_w ? __ldg(g.W + (int64_t)k * g.ldw + n) : __ldg(g.W + (int64_t)n * g.ldw + k);
-    *reinterpret_cast<__half*>(sw + (uint32_t)(k >> 6) * w_chunk + tile_off((uint32_t)n, (uint32_t)(k & 63))) =
-        __float2half_rn(v);
+  // (eight independent loads in flight per thread: every CTA rebuilds the image, a dependent load per element was a
+  // fifth of the kernel's time)
+  for (int base = threadIdx.x; base < g.n_pad * kpad; base += 8 * blockDim.x) {
+    float v[8];
+    uint32_t off[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int idx = base + u * blockDim.x;
+      int n, k;
+      if (g.trans_w) { n = idx % g.n_pad; k = idx / g.n_pad; } else { k = idx % kpad; n = idx / kpad; }
+      const bool in = idx < g.n_pad * kpad;
+      v[u] = 0.f;
+      if (in && n < g.N && k < g.K) v[u] = g.trans_w ? __ldg(g.W + (int64_t)k * g.ldw + n) : __ldg(g.W + (int64_t)n * g.ldw + k);
+      off[u] = in ? (uint32_t)(k >> 6) * w_chunk + tile_off((uint32_t)n, (uint32_t)(k & 63)) : 0xffffffffu;
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      if (off[u] != 0xffffffffu) *reinterpret_cast<__half*>(sw + off[u]) = __float2half_rn(v[u]);
   }
   fence_async_smem();
   tc_fence_before();
@@ -330,12 +341,16 @@ __global__ void __launch_bounds__(256, (TMEM_COLS <= 256) ? 2 : 1) hgemm_tc_wgra
   }
   mbar_wait(&mma_done, (it - 1) & 1);                          // it >= 1: every CTA owns at least one tile
   tc_fence_after();
-  if (warp < 4) {
+  {
+    // all eight warps flush: warp w reads TMEM lanes 32 (w & 3) .., warps 0-3 the lower half of the 32-column blocks,
+    // warps 4-7 the upper half
+    const int q = warp & 3, n_blk = g.n_pad / 32, blk_lo = (warp < 4) ? 0 : (n_blk + 1) / 2,
+              blk_hi = (warp < 4) ? (n_blk + 1) / 2 : n_blk;
     for (int mb = 0; mb < g.m_blocks; ++mb) {
-      const int row = mb * 128 + warp * 32 + lane;
-      for (int c0 = 0; c0 < g.n_pad; c0 += 32) {
+      const int row = mb * 128 + q * 32 + lane;
+      for (int c0 = 32 * blk_lo; c0 < 32 * blk_hi; c0 += 32) {
         uint32_t v[32];
-        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + mb * g.n_pad + c0, v);
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mb * g.n_pad + c0, v);
         tmem_ld_wait();
         if (row < g.n_out) {
           float* grow = g.G + (int64_t)row * g.ldg + c0;

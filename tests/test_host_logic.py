@@ -161,3 +161,25 @@ def test_tnerf_module_layout_and_signatures():
     assert sig(m.forward) == ["inp", "vdir", "dyn_t"]
     with pytest.raises((RuntimeError, TypeError)):                   # no CPU path
         m(torch.zeros(4, 90), torch.zeros(4, 27), torch.zeros(4, 21))
+
+
+def test_precision_switch_arms_layerwise_tc_gemm():
+    """'tc' precision routes shapes without a fused kernel to the layer-wise tcgen05 GEMMs (spec.tc), 'fp32' to the fp32
+    SIMT check path; the fused-kernel shape is untouched by the flag."""
+    from swnerf_b200 import tnerf
+    e3, e1 = S.get_embedder(10, 3, 0)[0], S.get_embedder(10, 1, 0)[0]
+    ev = S.get_embedder(4, 3, 0)[0]
+    m = S.TNeRF(8, 63, 27, 21)
+    assert m.spec.tc is False
+    for prec, want in (("tc", True), ("fp32", False)):
+        tnerf.TNerfNetworkQuery(e3, ev, e1, precision=prec)._arm(m)
+        assert m.tc_gemm is want and m.spec.tc is want
+        v = S.vallina_NeRF(8, 256, 63, 0, 4, [4], False)
+        S.NetworkQuery(e3, None, precision=prec)._arm(v)
+        assert v.spec.tc is want
+        d = S.DirectTemporalNeRF(D=8, W=256, input_ch=63, input_ch_views=63, input_ch_time=9, output_ch=5, skips=[4],
+                                 use_viewdirs=True, embed_fn=e3)
+        dnerf.DNerfNetworkQuery(e3, S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 1, 0)[0], precision=prec)._arm(d)
+        assert d.tc_gemm is want and d.time_spec.tc is want
+    with pytest.raises(ValueError):
+        tnerf.TNerfNetworkQuery(e3, ev, e1, precision="bf16")

@@ -29,6 +29,7 @@ struct HgArgs {
   const float* a_scale_dev;                       // if set: the scale is read from device memory (swnerf_pow2_scale)
   int vec_a, vec_c;                               // float4 access allowed (alignment checked on the host)
   int a_bufs;                                     // 2 when two A images fit next to the weight image, else 1
+  int stage;                                      // epilogue stores go through a per-warp staging slice (20 KB)
 };
 
 constexpr int HG_A_CHUNK = 128 * 128;             // one [128 x 64] fp16 image
@@ -125,6 +126,7 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
   const uint32_t w_chunk = (uint32_t)g.n_pad * 128u;
   uint8_t* sw = smem;
   uint8_t* sa = smem + (((uint32_t)g.k_chunks * w_chunk + 1023u) & ~1023u);
+  float* s_stage = reinterpret_cast<float*>(sa + (size_t)g.a_bufs * g.k_chunks * HG_A_CHUNK);   // 8 warps x 32 x 20 floats
   __shared__ uint64_t a_free[2], acc_full[2], acc_free[2];
   __shared__ uint32_t tmem_slot;
   __shared__ __align__(16) float s_bias[256];               // bias padded with zeros: unconditional vector reads
@@ -215,11 +217,12 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + buf * 256 + c0, v);
         tmem_ld_wait();
-        if (m < g.M) {
+        const bool row_ok = m < g.M;
+        float o[32];
+        const bool full = c0 + 32 <= g.N, vec = g.vec_c && full;
+        float* crow = g.C + m * g.ldc + c0;
+        if (row_ok) {
           // every option is tested once per 32-column block; the element loops inside are branch-free
-          float* crow = g.C + m * g.ldc + c0;
-          const bool full = c0 + 32 <= g.N, vec = g.vec_c && full;
-          float o[32];
 #pragma unroll
           for (int i = 0; i < 32; ++i) o[i] = fmaf(__uint_as_float(v[i]), c_scale, s_bias[c0 + i]);
           if (g.accumulate) {
@@ -264,6 +267,30 @@ __global__ void __launch_bounds__(512, 1) hgemm_tc_kernel(const HgArgs g) {
               for (int i = 0; i < 32; ++i) o[i] = y[i] > 0.f ? o[i] : 0.f;
             }
           }
+        }
+        if (vec && g.stage) {
+          // a lane owns a ROW of the accumulator, so its own stores would touch 32 different 128-byte lines per
+          // instruction.  The block goes through a 32 x 16 staging slice per warp (row stride 20 floats: conflict-free
+          // 16-byte accesses) and leaves as 64-byte runs, eight rows per instruction
+          float* stg = s_stage + warp * (32 * 20);
+          const int pr = lane >> 2, pc = (lane & 3) * 4;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4)
+              *reinterpret_cast<float4*>(stg + lane * 20 + i) =
+                  make_float4(o[16 * h + i], o[16 * h + i + 1], o[16 * h + i + 2], o[16 * h + i + 3]);
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int r = pr + 8 * j;
+              const int64_t mr = tile * 128 + q * 32 + r;
+              if (mr < g.M)
+                *reinterpret_cast<float4*>(g.C + mr * g.ldc + c0 + 16 * h + pc) = *reinterpret_cast<const float4*>(stg + r * 20 + pc);
+            }
+            __syncwarp();
+          }
+        } else if (row_ok) {
           if (vec) {
 #pragma unroll
             for (int i = 0; i < 32; i += 4) *reinterpret_cast<float4*>(crow + i) = make_float4(o[i], o[i + 1], o[i + 2], o[i + 3]);
@@ -458,11 +485,13 @@ int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t
   g.vec_a = (aligned16(A) && lda % 4 == 0 && K % 4 == 0) ? 1 : 0;
   g.vec_c = (aligned16(C) && ldc % 4 == 0) ? 1 : 0;
   const size_t w_bytes = ((size_t)g.k_chunks * g.n_pad * 128 + 1023) & ~(size_t)1023, a_bytes = (size_t)g.k_chunks * HG_A_CHUNK;
-  g.a_bufs = (w_bytes + 2 * a_bytes + 1024 <= 200 * 1024) ? 2 : 1;
-  const size_t smem = w_bytes + g.a_bufs * a_bytes + 1024;
+  const size_t stage_bytes = 8 * 32 * 20 * sizeof(float);
+  g.a_bufs = (w_bytes + 2 * a_bytes + stage_bytes + 1024 <= 220 * 1024) ? 2 : 1;
+  g.stage = (w_bytes + g.a_bufs * a_bytes + stage_bytes + 1024 <= 220 * 1024) ? 1 : 0;
+  const size_t smem = w_bytes + g.a_bufs * a_bytes + (g.stage ? stage_bytes : 0) + 1024;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);   // W <= 128 KB, A <= 64 KB
+    cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);   // W <= 128 KB, A <= 64 KB, staging 20 KB
     attr_done = true;
   }
   const int64_t tiles = (M + 127) / 128;

@@ -30,6 +30,30 @@ def test_library_exports_every_declared_symbol():
     assert L.swnerf_version() == 100
 
 
+def test_binding_table_matches_header_signatures():
+    """Every entry of the ctypes table has as many arguments as the header's prototype, pointer arguments are bound as
+    void pointers, floats as c_float and 64-bit sizes as c_int64 (a mismatch corrupts the call silently)."""
+    from swnerf_b200 import _lib
+    src = open(os.path.join(ROOT, "include", "swnerf_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    protos = dict(re.findall(r"\b(swnerf_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src))
+    checked = 0
+    for name, argtypes in _lib._SIG.items():
+        params = [p.strip() for p in protos[name].split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(argtypes), (name, len(params), len(argtypes))
+        for p_, t in zip(params, argtypes):
+            if "*" in p_:
+                assert t is ctypes.c_void_p, (name, p_)
+            elif p_.startswith("float"):
+                assert t is ctypes.c_float, (name, p_)
+            elif p_.startswith("int64_t"):
+                assert t is ctypes.c_int64, (name, p_)
+            elif p_.startswith("int ") or p_.startswith("unsigned"):
+                assert t is ctypes.c_int, (name, p_)
+        checked += 1
+    assert checked == len(_lib._SIG) >= 20
+
+
 def test_error_channel_without_gpu():
     from swnerf_b200 import _lib
     L = _lib.lib()

@@ -156,8 +156,7 @@ def main():
 
     import torch.distributed as dist
     import swnerf_b200 as S
-    from swnerf_b200 import _lib, tc, parallel
-    from oracle import nerf_oracle as O      # synthetic ray generator + cpu_baseline only
+    from swnerf_b200 import _lib, tc, parallel, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -167,9 +166,8 @@ def main():
     precision = args.precision or ("tc" if tc.available() else "fp32")
 
     torch.manual_seed(1234 + rank)
-    shapes = O.mlp_param_shapes()
-    mc = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mc.load_state_dict(O.make_params(shapes, 21)); mc.to(dev)
-    mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(O.make_params(shapes, 55)); mf.to(dev)
+    mc = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mc.load_state_dict(synth.scene_params(mc, 21)); mc.to(dev)
+    mf = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); mf.load_state_dict(synth.scene_params(mf, 55)); mf.to(dev)
     q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], precision=precision)
     params = list(mc.parameters()) + list(mf.parameters())
     # loss + optimizer of the step: parameters and gradients live in two flat buffers, the
@@ -180,7 +178,7 @@ def main():
     n_global = N_RAND * world
 
     nbatch = 4
-    host_rays = [torch.from_numpy(O.blender_rays(N_RAND, 100 + rank * 10 + i)).pin_memory() for i in range(nbatch)]
+    host_rays = [torch.from_numpy(synth.blender_rays(N_RAND, 100 + rank * 10 + i)).pin_memory() for i in range(nbatch)]
     host_tgt = [torch.from_numpy(np.random.RandomState(200 + rank * 10 + i).uniform(0, 1, (N_RAND, 3))
                                  .astype(np.float32)).pin_memory() for i in range(nbatch)]
     dev_rays = [r.to(dev) for r in host_rays]
@@ -336,7 +334,7 @@ def main():
         H = W = 800
         focal = 0.5 * W / np.tan(0.5 * 0.6911112)
         Kmat = np.array([[focal, 0, 0.5 * W], [0, focal, 0.5 * H], [0, 0, 1]], dtype=np.float32)
-        c2w = torch.from_numpy(O.pose_spherical(40.0, -30.0, 4.0)[:3, :4])
+        c2w = torch.from_numpy(synth.pose_spherical(40.0, -30.0, 4.0)[:3, :4])
         kwt = dict(kw); kwt["perturb"] = 0.0
         with torch.no_grad():
             def frame_fn():

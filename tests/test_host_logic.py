@@ -183,3 +183,21 @@ def test_precision_switch_arms_layerwise_tc_gemm():
         assert d.tc_gemm is want and d.time_spec.tc is want
     with pytest.raises(ValueError):
         tnerf.TNerfNetworkQuery(e3, ev, e1, precision="bf16")
+
+
+def test_synthetic_workload_matches_the_oracles_generators():
+    """bench.py and tools/ take their inputs from swnerf_b200.synth (the product never imports the oracle); the cpu_baseline
+    leg takes them from the oracle: both must be the same rays and the same scene, bit for bit."""
+    from swnerf_b200 import synth
+    assert np.array_equal(synth.blender_rays(257, 7), O.blender_rays(257, 7))
+    assert np.array_equal(synth.blender_rays(33, 3, frame_time=0.4), O.blender_rays(33, 3, frame_time=0.4))
+    assert np.array_equal(synth.pose_spherical(40.0, -30.0, 4.0), O.pose_spherical(40.0, -30.0, 4.0))
+    m = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True)
+    p, q = synth.scene_params(m, 21), O.make_params(O.mlp_param_shapes(), 21)
+    assert list(p) == list(q) and all(torch.equal(p[k], q[k]) for k in q)
+    t = S.TNeRF(8, 63, 27, 21)
+    p, q = synth.scene_params(t, 5), O.make_params(O.tnerf_param_shapes(), 5)
+    assert all(torch.equal(p[k], q[k]) for k in q)
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "bench.py")).read()
+    body = src.split("def main():")[1]
+    assert "oracle" not in body.split("cpu_reference_run(")[0].replace("oracle port", "")   # main arm: no oracle import

@@ -6,7 +6,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import swnerf_b200 as S
 from swnerf_b200 import dnerf
-from oracle import nerf_oracle as O
+from swnerf_b200 import synth
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 500
 dev = torch.device("cuda")
@@ -22,9 +22,9 @@ for prec in ("fp32", "tc"):
                      swnerf_precision=prec)
     kw, _, _, gv, opt = dnerf.create_nerf(args, device=dev)
     model = kw["network_fn"]
-    model.load_state_dict(O.make_params(O.dnerf_param_shapes(), 332)); model.to(dev)
+    model.load_state_dict(synth.scene_params(model, 332)); model.to(dev)
     kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
-    rays = torch.from_numpy(O.blender_rays(N, 31, frame_time=0.37)).to(dev)
+    rays = torch.from_numpy(synth.blender_rays(N, 31, frame_time=0.37)).to(dev)
     rays2 = rays.clone(); rays2[:, 8] = 0.38
     tgt = torch.rand(N, 3, device=dev)
 

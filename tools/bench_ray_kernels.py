@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import swnerf_b200 as S
 from swnerf_b200 import ops, _lib
-from oracle import nerf_oracle as O
+from swnerf_b200 import synth
 
 dev = "cuda"
 peak = 6525.2
@@ -29,7 +29,7 @@ def timeit(fn, reps=20):
 
 call, st = _lib.call, _lib.stream
 for N in (4096, 32768, 262144):
-    rays = torch.from_numpy(O.blender_rays(N, 1)).to(dev)
+    rays = torch.from_numpy(synth.blender_rays(N, 1)).to(dev)
     for Ssamp in (64, 192):
         raw = torch.randn(N, Ssamp, 4, device=dev)
         z = torch.sort(torch.rand(N, Ssamp, device=dev) * 4 + 2, -1)[0]

@@ -4,14 +4,14 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 import swnerf_b200 as S
 from swnerf_b200 import ops, tc, _lib
-from oracle import nerf_oracle as O
+from swnerf_b200 import synth
 
 dev = "cuda"
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
 Ssamp = int(sys.argv[2]) if len(sys.argv) > 2 else 192
 train = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-rays = torch.from_numpy(O.blender_rays(N, 1)).to(dev)
-m = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); m.load_state_dict(O.make_params(O.mlp_param_shapes(), 21)); m.to(dev)
+rays = torch.from_numpy(synth.blender_rays(N, 1)).to(dev)
+m = S.vallina_NeRF(8, 256, 63, 27, 5, [4], True); m.load_state_dict(synth.scene_params(m, 21)); m.to(dev)
 q = S.NetworkQuery(S.get_embedder(10, 3, 0)[0], S.get_embedder(4, 3, 0)[0], precision="tc")
 z = torch.sort(torch.rand(N, Ssamp, device=dev) * 4 + 2, -1)[0]
 st = tc.packed_weights(m)

@@ -55,13 +55,15 @@ int swnerf_embed_bwd(const float* x, const float* dy, float* dx, int64_t rows, i
 int swnerf_encode_points(const float* rays, int ray_stride, int view_col, const float* z_vals, float* out,
                          int64_t n_rays, int n_samples, int L_pos, int L_dir, int out_stride, void* stream);
 
-/* ---- a8: raw2outputs (ray.py:155-198).  raw[N,S,4], z_vals[N,S], rays_d = rays[:, d_col:d_col+3],
- * noise[N,S] (already scaled by raw_noise_std) or NULL. */
-int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+/* ---- a8: raw2outputs (ray.py:155-198).  raw[N,S,raw_ch] with raw_ch >= 4 (create_nerf builds output_ch = 5 networks
+ * when N_importance > 0, nerf/run.py:231; ray.py:175-186 reads channels 0..2 = rgb and 3 = sigma only), z_vals[N,S],
+ * rays_d = rays[:, d_col:d_col+3], noise[N,S] (already scaled by raw_noise_std) or NULL. */
+int swnerf_composite_fwd(const float* raw, int raw_ch, const float* z_vals, const float* rays, int ray_stride, int d_col,
                          const float* noise, int white_bkgd, int64_t n_rays, int n_samples, float* rgb_map,
                          float* disp_map, float* acc_map, float* weights, float* depth_map, void* stream);
-/* autograd of the above: any of g_* may be NULL (= zero); g_disp needs the saved acc/depth maps. */
-int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+/* autograd of the above: any of g_* may be NULL (= zero); g_disp needs the saved acc/depth maps.  d_raw[N,S,raw_ch]:
+ * channels >= 4 receive zeros.  Same n_samples limit as the forward (<= 1024). */
+int swnerf_composite_bwd(const float* raw, int raw_ch, const float* z_vals, const float* rays, int ray_stride, int d_col,
                          const float* noise, int white_bkgd, int64_t n_rays, int n_samples, const float* g_rgb,
                          const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
                          const float* acc_map, const float* depth_map, float* d_raw, void* stream);
@@ -77,6 +79,19 @@ int swnerf_sample_pdf(const float* bins, const float* weights, const float* cdf,
  * z_samples is returned in ASCENDING order (the reference only uses it through std and the sort). */
 int swnerf_resample(const float* z_vals, const float* weights, const float* u, int det, int64_t n_rays,
                     int n_samples, int n_importance, float* z_samples, float* z_fine, float* z_std, void* stream);
+/* Check-mode / test entry of the same stage (same outputs), with
+ *  - cdf_in[N, n_samples-1] (optional): sample from THIS cdf instead of building one from the weights - the
+ *    north_star's "bin indices bit-exact given identical CDFs" test, on the production kernel;
+ *  - inds_out[N, n_importance] int64 (optional): torch.searchsorted(cdf, u, right=True) (ray.py:136) per sample, in
+ *    ascending-u order (the kernels sort the uniforms first); cdf_out[N, n_samples-1] (optional): the cdf used;
+ *  - variant 0: the production kernel of the shape (64+128: the eight-lanes-per-ray kernel); variant 1: the
+ *    reference-order routine - pdf sum in the order of torch.sum on the reference's CPU path (`ref_lanes` = SIMD lanes of
+ *    the host that produced the comparison data: 16 for AVX512, 8 for AVX2), IEEE divisions, cdf accumulated
+ *    sequentially in double like torch.cumsum on CPU (ray.py:111-114): z_fine is bit-identical to the reference's given
+ *    identical weights.  render_rays uses variant 1 in precision='fp32' (the <= 1e-5 check mode). */
+int swnerf_resample_check(const float* z_vals, const float* weights, const float* cdf_in, const float* u, int det,
+                          int64_t n_rays, int n_samples, int n_importance, int variant, int ref_lanes, float* z_samples,
+                          float* z_fine, float* z_std, int64_t* inds_out, float* cdf_out, void* stream);
 /* Kernel used for the 64 + 128 shape of the reference configs: 1 (default) = eight lanes per ray, four rays per
  * warp; 0 = the first specialisation, one warp per ray.  Both are verified per ray and fall back to the generic
  * routine, so the results are identical; the switch exists for A/B timing (tools/bench_ray_kernels.py). */

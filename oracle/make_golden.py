@@ -159,6 +159,47 @@ def gen_sample_pdf(ref):
     np.savez_compressed(os.path.join(OUT, "sample_pdf.npz"), **d)
 
 
+def gen_resample(ref):
+    """Hierarchical resampling exactly as nerf/run.py:396-400, :416 drives it: z_mid bins, the reference's sample_pdf on
+    weights[..., 1:-1] (deterministic and with the pytest uniforms), sort(cat(z_vals, z_samples)), z_std; plus the cdf
+    and the searchsorted indices the reference's formulas give (ray.py:111-114, :136)."""
+    rs = np.random.RandomState(31)
+    d = {}
+    N = 37                                          # not a multiple of the 4 rays per warp / 16 rays per block
+    near, far = 2.0, 6.0
+    t = np.linspace(0.0, 1.0, 64, dtype=np.float32)
+    z = (near * (1 - t) + far * t)[None, :].repeat(N, 0).astype(np.float32)
+    mids = 0.5 * (z[:, 1:] + z[:, :-1])
+    upper = np.concatenate([mids, z[:, -1:]], -1); lower = np.concatenate([z[:, :1], mids], -1)
+    z = (lower + (upper - lower) * rs.uniform(0, 1, size=z.shape).astype(np.float32)).astype(np.float32)   # run.py:369-383
+    z[5] = (near * (1 - t) + far * t)               # an unperturbed ray
+    w = (rs.uniform(0, 1, size=(N, 64)).astype(np.float32) ** 6).astype(np.float32)
+    w[0] = 0.0                                      # empty ray: uniform pdf
+    w[1, 10:50] = 0.0                               # flat cdf stretch (denom < 1e-5, ray.py:149)
+    w[2, :] = 0.0; w[2, 31] = 1.0                   # one dominant bin
+    w[3, :] = 0.0; w[3, 62] = 5.0                   # all mass in the last bin the pdf sees
+    w[4, :] = 0.0; w[4, 1] = 3.0                    # ... in the first
+    d["z_vals"], d["weights"] = z, w
+    zt, wt = torch.from_numpy(z), torch.from_numpy(w)
+    z_mid = .5 * (zt[..., 1:] + zt[..., :-1])                                   # run.py:396
+    for tag, det in (("det", True), ("rand", False)):
+        zs = ref.ray.sample_pdf(z_mid, wt[..., 1:-1], 128, det=det, pytest=not det).detach()   # run.py:397-398
+        zf, _ = torch.sort(torch.cat([zt, zs], -1), -1)                         # run.py:400
+        d[f"{tag}/z_samples"], d[f"{tag}/z_fine"] = zs.numpy(), zf.numpy()
+        d[f"{tag}/z_std"] = torch.std(zs, dim=-1, unbiased=False).numpy()       # run.py:416
+    np.random.seed(0)
+    d["u_rand"] = np.random.rand(N, 128).astype(np.float32)                     # ray.py:124-132 (pytest hook)
+    wp = wt[..., 1:-1] + 1e-5                                                   # ray.py:111-114
+    pdf = wp / torch.sum(wp, -1, keepdim=True)
+    cdf = torch.cumsum(pdf, -1)
+    cdf = torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)
+    d["cdf"] = cdf.numpy()
+    u = torch.linspace(0., 1., steps=128).expand(N, 128).contiguous()
+    d["det/inds"] = torch.searchsorted(cdf, u, right=True).numpy()              # ray.py:136
+    d["rand/inds"] = torch.searchsorted(cdf, torch.from_numpy(d["u_rand"]).contiguous(), right=True).numpy()
+    np.savez_compressed(os.path.join(OUT, "resample.npz"), **d)
+
+
 def gen_searchsorted():
     f = ref_import.load_reference_searchsorted_numpy()
     rs = np.random.RandomState(15)
@@ -327,6 +368,7 @@ def main():
     gen_mlp(ref)
     gen_raw2outputs(ref)
     gen_sample_pdf(ref)
+    gen_resample(ref)
     gen_searchsorted()
     gen_render_rays(ref)
     gen_render_rays_dnerf(ref)

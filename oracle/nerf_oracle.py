@@ -194,6 +194,30 @@ def pdf_to_cdf(weights: torch.Tensor) -> torch.Tensor:
     return torch.cat([torch.zeros_like(cdf[..., :1]), cdf], -1)        # ray.py:114
 
 
+def torch_cpu_sum_order(w: np.ndarray, lanes: int = 8) -> np.float32:
+    """The order in which torch.sum reduces ONE contiguous fp32 row on the reference's CPU path (ray.py:112), restated
+    from ATen's vectorised inner sum (aten/src/ATen/native/cpu/SumKernel.cpp: `lanes`-wide vector partial sums, four
+    interleaved accumulators when the row holds >= 4 vectors, scalar tail first, then the lanes of the partial sum in
+    order).  ATen registers this kernel for AVX2 (8 lanes) on AVX512 hosts too.  Valid below 16 * 4 * lanes elements
+    (no cascade level).  The CUDA check mode follows this order (ray_kernels.cu: warp_build_cdf_ref); the test
+    test_cpu_sum_order_is_the_one_the_check_mode_follows pins it to torch.sum on the host at hand."""
+    f = np.float32
+    n = len(w)
+    nvec, nilp = n // lanes, (n // lanes) // 4
+    tot = f(0)
+    for k in range(nvec * lanes, n):
+        tot = f(tot + w[k])
+    for l in range(lanes):
+        p = [f(0)] * 4
+        for i in range(nilp):
+            for k in range(4):
+                p[k] = f(p[k] + w[(4 * i + k) * lanes + l])
+        for i in range(nilp * 4, nvec):
+            p[0] = f(p[0] + w[i * lanes + l])
+        tot = f(tot + f(f(f(p[0] + p[1]) + p[2]) + p[3]))
+    return tot
+
+
 def searchsorted_rows(a: np.ndarray, v: np.ndarray, side: str = "left") -> np.ndarray:
     """Row-wise np.searchsorted with row broadcasting, int64 result.
     d_nerf/torchsearchsorted/src/torchsearchsorted/utils.py:4-14 and

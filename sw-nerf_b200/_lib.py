@@ -25,11 +25,12 @@ _SIG = {
     "swnerf_embed_fwd": [_VP, _VP, _I64, _I32, _I32, _VP],
     "swnerf_embed_bwd": [_VP, _VP, _VP, _I64, _I32, _I32, _VP],
     "swnerf_encode_points": [_VP, _I32, _I32, _VP, _VP, _I64, _I32, _I32, _I32, _I32, _VP],
-    "swnerf_composite_fwd": [_VP, _VP, _VP, _I32, _I32, _VP, _I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP],
-    "swnerf_composite_bwd": [_VP, _VP, _VP, _I32, _I32, _VP, _I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
+    "swnerf_composite_fwd": [_VP, _I32, _VP, _VP, _I32, _I32, _VP, _I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP],
+    "swnerf_composite_bwd": [_VP, _I32, _VP, _VP, _I32, _I32, _VP, _I32, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _VP,
                              _VP, _VP],
     "swnerf_sample_pdf": [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _VP, _VP, _VP],
     "swnerf_resample": [_VP, _VP, _VP, _I32, _I64, _I32, _I32, _VP, _VP, _VP, _VP],
+    "swnerf_resample_check": [_VP, _VP, _VP, _VP, _I32, _I64, _I32, _I32, _I32, _I32, _VP, _VP, _VP, _VP, _VP, _VP],
     "swnerf_sgemm": [_I32, _VP, _I64, _VP, _I64, _VP, _I64, _I64, _I64, _I64, _VP, _I32, _I32, _VP, _I64, _VP],
     "swnerf_colsum": [_VP, _I64, _I64, _I32, _VP, _I32, _VP],
     "swnerf_hgemm_tc_supported": [_I64, _I64],

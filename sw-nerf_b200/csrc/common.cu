@@ -3,6 +3,7 @@
 #include "../../include/swnerf_b200.h"
 #include <stdarg.h>
 #include <cuda.h>
+#include <mutex>
 
 namespace swnerf {
 
@@ -49,6 +50,18 @@ int encode_u8_tensor_map(void* map, const void* base, int ndim, const unsigned l
                       CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return set_err(SWNERF_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return SWNERF_OK;
+}
+
+bool once_per_device(int id) {
+  constexpr int kMaxDev = 64;
+  static std::mutex mu;
+  static bool done[ONCE_COUNT][kMaxDev] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev || id < 0 || id >= ONCE_COUNT) return true;
+  std::lock_guard<std::mutex> lock(mu);
+  if (done[id][dev]) return false;
+  done[id][dev] = true;
+  return true;
 }
 
 int sm_count() {

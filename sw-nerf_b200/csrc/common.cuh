@@ -19,6 +19,14 @@ int set_err(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
 
+// One-time, PER-DEVICE setup (cudaFuncSetAttribute opt-ins, __constant__ uploads): true exactly once for each
+// (id, current device) pair, whatever thread asks; callers run their setup when it returns true.  Ids below.
+bool once_per_device(int id);
+enum OnceId {
+  ONCE_FWD4 = 0, ONCE_FWD1_TRAIN, ONCE_FWD1_INFER, ONCE_BWD_BASE, ONCE_BWD_DATA_PAIR, ONCE_BWD_WEIGHT_PAIR,
+  ONCE_HGEMM, ONCE_HGEMM_WGRAD, ONCE_RESAMPLE64Q, ONCE_RESAMPLE64Q_CHECK, ONCE_FWDX, ONCE_BWDX, ONCE_COUNT
+};
+
 // u8 tensor map (1..3 dims, no swizzle / interleave) through the driver entry point fetched at run time, so the
 // library does not link libcuda.  `map` points to a 128-byte CUtensorMap.  strides[] has ndim - 1 entries (bytes).
 int encode_u8_tensor_map(void* map, const void* base, int ndim, const unsigned long long* dims,

@@ -443,12 +443,10 @@ int swnerf_hgemm_tc_wgrad(const float* dY, int64_t ldy, const float* X, int64_t 
   g.vec_y = (aligned16(dY) && ldy % 4 == 0 && n_out % 4 == 0) ? 1 : 0;
   g.vec_x = (aligned16(X) && ldx % 4 == 0 && k_in % 4 == 0) ? 1 : 0;
   const size_t smem = (size_t)(g.m_blocks * 2 + g.n_pad / 64) * HG_A_CHUNK + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (once_per_device(ONCE_HGEMM_WGRAD)) {
     cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
     cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
     cudaFuncSetAttribute(hgemm_tc_wgrad_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * HG_A_CHUNK + 1024);
-    attr_done = true;
   }
   // accumulator columns = m_blocks x n_pad: a CTA that needs at most half of tensor memory shares its SM with a second
   // one (their loads and MMAs overlap; the kernel has no other latency hiding)
@@ -489,11 +487,8 @@ int swnerf_hgemm_tc(int op, const float* A, int64_t lda, const float* W, int64_t
   g.a_bufs = (w_bytes + 2 * a_bytes + stage_bytes + 1024 <= 220 * 1024) ? 2 : 1;
   g.stage = (w_bytes + g.a_bufs * a_bytes + stage_bytes + 1024 <= 220 * 1024) ? 1 : 0;
   const size_t smem = w_bytes + g.a_bufs * a_bytes + (g.stage ? stage_bytes : 0) + 1024;
-  static bool attr_done = false;
-  if (!attr_done) {
+  if (once_per_device(ONCE_HGEMM))
     cudaFuncSetAttribute(hgemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);   // W <= 128 KB, A <= 64 KB, staging 20 KB
-    attr_done = true;
-  }
   const int64_t tiles = (M + 127) / 128;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   hgemm_tc_kernel<<<grid, 512, smem, (cudaStream_t)stream>>>(g);

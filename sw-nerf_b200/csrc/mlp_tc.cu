@@ -140,8 +140,17 @@ struct FwdArgs {
   const uint8_t* packed; float* raw;          // kind 0: raw[P,4];  kind 1: dx[P,3]
   uint8_t* ws; int64_t num_tiles;
   int kind;
-  int ko;                                     // experiment knock-outs (tools only; 0 in production)
+  int f32_slot;                               // CTA-pair kernel: which copy of the bias block in constant memory
+#ifdef SWNERF_EXPERIMENTS
+  int ko;                                     // knock-out experiments (profiles/r1_knockout_experiments.md): bench builds only
+#endif
 };
+// The knock-out branches exist only in builds made with -DSWNERF_EXPERIMENTS; the shipped library compiles them out.
+#ifdef SWNERF_EXPERIMENTS
+#define SW_KO(g, bit) ((g).ko & (bit))
+#else
+#define SW_KO(g, bit) 0
+#endif
 
 __device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
   // angle = 2*pi*frac((th + tl) * scale): th*scale and the rounding to nearest integer are exact in fp32
@@ -514,7 +523,11 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
 // fp32 block of the packed weights (trunk biases, folded head bias, rgb_linear) for the CTA-pair kernel: staged per
 // call with a device-to-device copy on the launching stream.  Every access is warp-uniform, so constant-cache reads
 // cost the same as the shared-memory broadcast they replace, and the 10 KB of shared memory buy a 4th ring stage.
-__constant__ float c_f32[F32_COUNT];
+// There are F32_SLOTS copies: a stream keeps the slot it used last, another stream takes another slot, so the coarse
+// and the fine network (or two callers) can run concurrently on different streams without sharing a bias block.
+constexpr int F32_SLOTS = 4;
+constexpr int F32_PAD = (F32_COUNT + 3) & ~3;
+__constant__ float c_f32s[F32_SLOTS][F32_PAD];
 
 // ======================================================================================================
 // Forward kernel on CTA pairs (cta_group::2), two tile slots per CTA.
@@ -555,6 +568,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
+  const float* c_f32 = c_f32s[g.f32_slot];
   const int64_t num_quads = (g.num_tiles + 3) >> 2;          // a pair iteration covers 4 tiles: tile = 4 q + 2 slot + rank
   const int64_t quad0 = blockIdx.x >> 1, quad_step = gridDim.x >> 1;
 
@@ -584,7 +598,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
     // ===================== weight producer: this CTA's half of every chunk, once per slot =====================
     // Tensor-map loads with .cta_group::2 report their bytes to the LEADER's barrier, which expects both halves: no
     // relay hop between the peer's copy landing and the leader issuing.
-    if (lane == 0 && !(g.ko & 32)) {
+    if (lane == 0 && !SW_KO(g, 32)) {
       const uint32_t w_full_l = mapa_u32(smem_u32(w_full), 0);
       uint32_t cnt = 0;
       for (int64_t quad = quad0; quad < num_quads; quad += quad_step) {
@@ -632,9 +646,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             if (li == 0) aj = -1;
             const uint32_t a_base = aj < 0 ? enc_u32 + t * ACT_BLK : act_u32 + t * ACT_BYTES + aj * ACT_BLK;
             const uint32_t stage = cnt % NST4, wph = (cnt / NST4) & 1;
-            if (!(g.ko & 32)) {
-              mbar_wait(&w_full[stage], wph);
-            }
+            if (!SW_KO(g, 32)) mbar_wait(&w_full[stage], wph);
             tc_fence_after();
             const uint32_t b_base = ring_u32 + stage * STG4_B;
             if (elect_one()) {
@@ -671,7 +683,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
           uint8_t* img = s_act + t * ACT_BYTES;
           mbar_wait(&d_full[t], dcnt & 1);
           tc_fence_after();
-          if (li < 8 && (g.ko & 16)) {     // experiment: synchronisation only
+          if (li < 8 && SW_KO(g, 16)) {     // experiment: synchronisation only
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(act_full_l + t * 8);
@@ -736,7 +748,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             }
             // the sign masks go out AFTER the hand-off: in front of it the proxy fence and the release-arrive would
             // wait for these global stores (ncu: 15 % of the kernel's stall samples sat on that ERRBAR / arrive)
-            if (TRAIN && tvalid && !(g.ko & 2)) {
+            if (TRAIN && tvalid && !SW_KO(g, 2)) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) ws_mask[(li * 8 + j * 2 + hh) * 128 + row] = masks[j];
             }
@@ -902,7 +914,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
             const int nblk = (li < 8) ? 4 : 2;                                 // h9 sits in blocks 0,1
             uint8_t* dst = ws_tile + (li < 8 ? WS_H_OFF + li * ACT_BYTES : WS_H9_OFF);
             for (int j = 0; j < nblk; ++j) {
-              if (tile < g.num_tiles && !(g.ko & 8)) bulk_s2g(dst + j * ACT_BLK, img + j * ACT_BLK, ACT_BLK);
+              if (tile < g.num_tiles && !SW_KO(g, 8)) bulk_s2g(dst + j * ACT_BLK, img + j * ACT_BLK, ACT_BLK);
               bulk_commit();
               bulk_wait_read0();
             }
@@ -978,27 +990,43 @@ static int weight_tensor_maps(const void* packed, CUtensorMap* trunk, CUtensorMa
   return SWNERF_OK;
 }
 
-// Copies a network's fp32 block into c_f32 on the launching stream.  The buffer is process-wide: a call on a different
-// stream than the previous one first waits for that one's kernel (event), so concurrent streams serialise instead of
-// racing.  (While a stream is being captured into a CUDA graph only same-stream use is supported.)
-static int stage_f32_block(const uint8_t* src, cudaStream_t s) {
+// Copies a network's fp32 block into one of the constant-memory slots on the launching stream and returns the slot.
+// A stream reuses the slot it used last (stream order makes that safe); a stream without one takes the least recently
+// assigned slot and first waits (event) for the work of the stream that owned it.  Bookkeeping is per device.
+// (While a stream is being captured into a CUDA graph no cross-stream wait is inserted: captures use one stream.)
+static int stage_f32_block(const uint8_t* src, cudaStream_t s, int* slot_out) {
+  constexpr int kMaxDev = 64;
+  struct Slot { cudaStream_t owner; bool used; unsigned long long stamp; };
   static std::mutex mu;
-  static cudaStream_t last = nullptr;
-  static bool have_last = false;
-  static cudaEvent_t ev = nullptr;
+  static Slot slots[kMaxDev][F32_SLOTS] = {};
+  static cudaEvent_t ev[kMaxDev] = {};
+  static unsigned long long clock_ = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: no current device");
   std::lock_guard<std::mutex> lock(mu);
-  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-  cudaStreamIsCapturing(s, &cap);
-  if (cap == cudaStreamCaptureStatusNone) {
-    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    if (have_last && last != s) {
-      cudaEventRecord(ev, last);
-      cudaStreamWaitEvent(s, ev, 0);
+  Slot* sl = slots[dev];
+  int k = -1;
+  for (int i = 0; i < F32_SLOTS; ++i) if (sl[i].used && sl[i].owner == s) k = i;
+  if (k < 0) {
+    for (int i = 0; i < F32_SLOTS; ++i) if (!sl[i].used) { k = i; break; }
+    if (k < 0) {
+      k = 0;
+      for (int i = 1; i < F32_SLOTS; ++i) if (sl[i].stamp < sl[k].stamp) k = i;
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cap);
+      if (cap == cudaStreamCaptureStatusNone) {
+        if (!ev[dev]) cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming);
+        cudaEventRecord(ev[dev], sl[k].owner);
+        cudaStreamWaitEvent(s, ev[dev], 0);
+      }
     }
-    last = s; have_last = true;
+    sl[k].owner = s; sl[k].used = true;
   }
-  cudaError_t e = cudaMemcpyToSymbolAsync(c_f32, src, F32_COUNT * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+  sl[k].stamp = ++clock_;
+  cudaError_t e = cudaMemcpyToSymbolAsync(c_f32s, src, F32_COUNT * sizeof(float), (size_t)k * F32_PAD * sizeof(float),
+                                          cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: staging the bias block failed: %s", cudaGetErrorString(e));
+  *slot_out = k;
   return SWNERF_OK;
 }
 
@@ -1020,37 +1048,38 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   FwdArgs g;
   g.rays = rays; g.ray_stride = ray_stride; g.view_col = view_col; g.z = z_vals; g.S = n_samples;
   g.P = n_rays * n_samples; g.pts = pts; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = out;
-  g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE; g.kind = kind;
+  g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE; g.kind = kind; g.f32_slot = 0;
+#ifdef SWNERF_EXPERIMENTS
   { static const char* ko = getenv("SWNERF_KO"); g.ko = ko ? atoi(ko) : 0; }
+#endif
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
   const int variant = g_fwd_variant.load();
   // automatic: a launch that does not fill the GPU twice over runs one tile per CTA (a pair CTA works through its two
   // slots back to back: 0.055 vs 0.033 ms at 128 tiles; equal from ~500 tiles; 17 % faster at 6144)
   if (variant == 1 || (variant < 0 && g.num_tiles > 2 * (int64_t)sm_count())) {        // CTA-pair kernel
-    static std::once_flag once;
-    std::call_once(once, [] {
+    if (once_per_device(ONCE_FWD4)) {
       cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
       cudaFuncSetAttribute(mlp_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
-    });
+    }
     const int64_t num_quads = (g.num_tiles + 3) / 4;
     const int grid4 = 2 * (int)(num_quads < sm_count() / 2 ? num_quads : sm_count() / 2);
     CUtensorMap tm_trunk, tm_head;
     int rc = weight_tensor_maps(packed, &tm_trunk, &tm_head);
     if (rc) return rc;
-    rc = stage_f32_block(reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF, s);
+    rc = stage_f32_block(reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF, s, &g.f32_slot);
     if (rc) return rc;
     if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
     else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
     return check_launch("tc_mlp_fwd");
   }
   if (training) {
-    static thread_local bool attr_t = false;
-    if (!attr_t) { cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL); attr_t = true; }
+    if (once_per_device(ONCE_FWD1_TRAIN))
+      cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     mlp_fwd_kernel<true><<<grid, 512, SM_TOTAL, s>>>(g);
   } else {
-    static thread_local bool attr_i = false;
-    if (!attr_i) { cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL); attr_i = true; }
+    if (once_per_device(ONCE_FWD1_INFER))
+      cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
     mlp_fwd_kernel<false><<<grid, 512, SM_TOTAL, s>>>(g);
   }
   return check_launch("tc_mlp_fwd");

@@ -1229,12 +1229,11 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   b.packed = reinterpret_cast<const uint8_t*>(packed); b.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
   b.ws = ws; b.unfold = unfold; b.absmax = absmax; b.fixed_scale = grad_scale;
   for (int i = 0; i < 24; ++i) b.grads[i] = i < np ? grads[i] : nullptr;
-  static thread_local bool attr = false;
-  static thread_local int wg_smem = 0;
-  const int dpe_smem = 8 * DPE_CHUNK_B + 2 * ACT_BYTES + 1024;
-  if (!attr) {
-    cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
-    WgJob jobs[2][WG_JOBS];
+  // job table: built once per process (host), uploaded once per DEVICE together with the shared-memory opt-ins
+  static WgJob jobs[2][WG_JOBS];
+  static int wg_smem = 0;
+  static std::once_flag jobs_once;
+  std::call_once(jobs_once, [] {
     build_jobs(jobs[0], 0);
     build_jobs(jobs[1], 1);
     for (int k = 0; k < 2; ++k)
@@ -1242,20 +1241,21 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
         int need = jobs[k][j].stage_bytes * jobs[k][j].nstage + 1024;
         if (need > wg_smem) wg_smem = need;
       }
+  });
+  const int dpe_smem = 8 * DPE_CHUNK_B + 2 * ACT_BYTES + 1024;
+  if (once_per_device(ONCE_BWD_BASE)) {
+    cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
     cudaMemcpyToSymbol(c_jobs, jobs, sizeof(jobs));
     cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem);
     cudaFuncSetAttribute(mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dpe_smem);
-    attr = true;
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (g_prof) cudaEventRecord(g_ev[0], s);
   int rc = SWNERF_OK;
   static const int dg_variant = [] { const char* e = getenv("SWNERF_BWD_PAIR"); return e ? atoi(e) : -1; }();
   if (dg_variant == 1 || (dg_variant < 0 && tiles > 2 * (int64_t)sm_count())) {
-    static std::once_flag once_dg;
-    std::call_once(once_dg, [] {
+    if (once_per_device(ONCE_BWD_DATA_PAIR))
       cudaFuncSetAttribute(mlp_bwd_data_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, S5_TOTAL);
-    });
     CUtensorMap tm_wt;
     const unsigned long long dims[2] = {128, (unsigned long long)NT_CHUNKS * 256};
     const unsigned long long strides[1] = {128};
@@ -1290,10 +1290,8 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   if (g_prof) cudaEventRecord(g_ev[1], s);
   if (wg_pair) {
     // trunk layers: CTA pairs
-    static std::once_flag once;
-    std::call_once(once, [] {
+    if (once_per_device(ONCE_BWD_WEIGHT_PAIR))
       cudaFuncSetAttribute(mlp_bwd_weight_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WGP_SMEM);
-    });
     WgPairArgs pw;
     pw.num_tiles = tiles; pw.absmax = absmax; pw.fixed_scale = grad_scale; pw.kind = kind;
     for (int i = 0; i < 24; ++i) pw.grads[i] = i < np ? grads[i] : nullptr;

@@ -156,15 +156,23 @@ __device__ __forceinline__ float sigmoidf_(float x) { return __frcp_rn(1.f + __e
 // All loads of a ray are issued before any arithmetic (NC = compile-time number of 32-sample chunks, registers
 // hold the whole ray: 6 x (float4 + z + noise) for S = 192), so every warp keeps ~5 KB in flight instead of
 // 0.6 KB and the kernel is HBM- rather than latency-bound.  z[i+1] comes from the neighbouring lane.
+// raw_ch = channels per sample in `raw` (4: one float4 per sample; > 4: the reference's output_ch = 5 networks,
+// nerf/run.py:231 - ray.py:175-186 reads channels 0..3 only, so do we, with scalar loads).
 template <int NC>
-__device__ __forceinline__ void load_ray(const float4* __restrict__ raw4, const float* __restrict__ zr,
+__device__ __forceinline__ void load_ray(const float* __restrict__ rawr, int raw_ch, const float* __restrict__ zr,
                                          const float* __restrict__ nr, int S, int lane, float4 (&q)[NC], float (&zi)[NC],
                                          float (&nz)[NC]) {
+  const float4* raw4 = reinterpret_cast<const float4*>(rawr);
 #pragma unroll
   for (int c = 0; c < NC; ++c) {
     int i = c * 32 + lane;
     bool valid = i < S;
-    q[c] = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (raw_ch == 4) {
+      q[c] = valid ? __ldg(raw4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+      const float* p = rawr + (size_t)i * raw_ch;
+      q[c] = valid ? make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     zi[c] = valid ? __ldg(zr + i) : 0.f;
     nz[c] = (valid && nr) ? __ldg(nr + i) : 0.f;
   }
@@ -179,18 +187,18 @@ __device__ __forceinline__ float z_next(const float (&zi)[NC], int c, int lane) 
 
 template <int NC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_fwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
+composite_fwd_kernel(const float* __restrict__ raw, int raw_ch, const float* __restrict__ z, const float* __restrict__ rays,
                      int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
                      float* __restrict__ rgb_map, float* __restrict__ disp_map, float* __restrict__ acc_map,
                      float* __restrict__ weights, float* __restrict__ depth_map) {
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= N) return;
-  const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
+  const float* rawr = raw + r * S * raw_ch;
   const float* zr = z + r * S;
   const float* nr = noise ? noise + r * S : nullptr;
   float4 q[NC]; float zi[NC], nz[NC];
-  load_ray<NC>(raw4, zr, nr, S, lane, q, zi, nz);
+  load_ray<NC>(rawr, raw_ch, zr, nr, S, lane, q, zi, nz);
   float norm = ray_norm(rays, r, ray_stride, d_col);
   float carry = 1.f;
   float sr = 0.f, sg = 0.f, sb = 0.f, sd = 0.f, sa = 0.f;
@@ -250,7 +258,7 @@ __device__ __forceinline__ float warp_rscan_add(float v, int lane) {   // inclus
 
 template <int NC>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
-composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z, const float* __restrict__ rays,
+composite_bwd_kernel(const float* __restrict__ raw, int raw_ch, const float* __restrict__ z, const float* __restrict__ rays,
                      int ray_stride, int d_col, const float* __restrict__ noise, int white_bkgd, int64_t N, int S,
                      const float* __restrict__ g_rgb, const float* __restrict__ g_disp, const float* __restrict__ g_acc,
                      const float* __restrict__ g_w, const float* __restrict__ g_depth,
@@ -259,13 +267,13 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
   int lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (r >= N) return;
-  const float4* raw4 = reinterpret_cast<const float4*>(raw) + r * S;
-  float4* out4 = reinterpret_cast<float4*>(d_raw) + r * S;
+  const float* rawr = raw + r * S * raw_ch;
+  float* outr = d_raw + r * S * raw_ch;
   const float* zr = z + r * S;
   const float* nr = noise ? noise + r * S : nullptr;
   const float* gw = g_w ? g_w + r * S : nullptr;
   float4 q[NC]; float zi[NC], nz[NC], gwv[NC];
-  load_ray<NC>(raw4, zr, nr, S, lane, q, zi, nz);
+  load_ray<NC>(rawr, raw_ch, zr, nr, S, lane, q, zi, nz);
 #pragma unroll
   for (int c = 0; c < NC; ++c) gwv[c] = (gw && c * 32 + lane < S) ? __ldg(gw + c * 32 + lane) : 0.f;
   float norm = ray_norm(rays, r, ray_stride, d_col);
@@ -325,7 +333,13 @@ composite_bwd_kernel(const float* __restrict__ raw, const float* __restrict__ z,
       o.y = wv[c] * gg * q[c].y * (1.f - q[c].y);
       o.z = wv[c] * gb * q[c].z * (1.f - q[c].z);
       o.w = dsig;
-      out4[i] = o;
+      if (raw_ch == 4) {
+        reinterpret_cast<float4*>(outr)[i] = o;
+      } else {                                   // channels the reference never reads get a zero gradient
+        float* p = outr + (size_t)i * raw_ch;
+        p[0] = o.x; p[1] = o.y; p[2] = o.z; p[3] = o.w;
+        for (int k = 4; k < raw_ch; ++k) p[k] = 0.f;
+      }
     }
   }
 }
@@ -374,6 +388,35 @@ __device__ void warp_build_cdf(const float* __restrict__ w, int M, float* cdf, i
     float inc = warp_scan_add(p, lane);
     if (i < M - 1) cdf[i + 1] = carry + inc;
     carry += __shfl_sync(0xffffffffu, inc, 31);
+  }
+  __syncwarp();
+}
+
+// The same cdf in the order the reference's CPU ops use, for the check mode and the "given identical weights" parity
+// test (tests/test_gpu_kernels.py): ray.py:112 torch.sum over the last dim = ATen's vectorised inner sum (SumKernel.cpp:
+// `lanes`-wide vector partial sums, four interleaved accumulators when there are >= 4 vectors, scalar tail first, then
+// the lanes of the partial sum in order; lanes = 16 on AVX512 hosts, 8 on AVX2), IEEE division, and ray.py:113
+// torch.cumsum = sequential accumulation in double rounded to float at every step.  One lane does the work.
+__device__ void warp_build_cdf_ref(const float* __restrict__ w, int M, float* cdf, int lane, int lanes) {
+  if (lane == 0) {
+    const int n = M - 1;
+    const int nvec = n / lanes, nilp = nvec / 4;
+    float tot = 0.f;
+    for (int k = nvec * lanes; k < n; ++k) tot = __fadd_rn(tot, __fadd_rn(w[k], 1e-5f));       // scalar tail
+    for (int l = 0; l < lanes; ++l) {
+      float p[4] = {0.f, 0.f, 0.f, 0.f};
+      for (int i = 0; i < nilp; ++i)
+        for (int k = 0; k < 4; ++k) p[k] = __fadd_rn(p[k], __fadd_rn(w[(4 * i + k) * lanes + l], 1e-5f));
+      for (int i = nilp * 4; i < nvec; ++i) p[0] = __fadd_rn(p[0], __fadd_rn(w[i * lanes + l], 1e-5f));
+      p[0] = __fadd_rn(__fadd_rn(__fadd_rn(p[0], p[1]), p[2]), p[3]);
+      tot = __fadd_rn(tot, p[0]);
+    }
+    double acc = 0.0;
+    cdf[0] = 0.f;
+    for (int i = 0; i < n; ++i) {
+      acc += (double)div_rn_z(__fadd_rn(w[i], 1e-5f), tot);
+      cdf[i + 1] = (float)acc;
+    }
   }
   __syncwarp();
 }
@@ -450,10 +493,17 @@ __device__ __forceinline__ void smem_cswap(float* a, int i, int l) {
 
 // One ray on one warp, any S / Ni (the exact algorithm; also the fallback of the specialised kernel below).
 // row_smem: cdf[M] | bins[M] | z[S] | samples[NiP] | merged[S+Ni]
+struct ResampleCheck {      // test / check-mode extras (all optional; the production launches pass an all-zero struct)
+  const float* cdf_in;      // [N, S-1]: use this cdf instead of building it
+  int64_t* inds_out;        // [N, Ni]: torch.searchsorted(cdf, u, right=True) per sample, in ascending-u order
+  float* cdf_out;           // [N, S-1]: the cdf the samples were drawn from
+  int ref_lanes;            // 0: warp-scan cdf; 8 / 16: the reference's CPU summation order (warp_build_cdf_ref)
+};
+
 __device__ void resample_row_generic(const float* __restrict__ z_vals, const float* __restrict__ weights,
                                      const float* __restrict__ u_in, int64_t r, int S, int Ni, int NiP,
                                      float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std,
-                                     float* row_smem, int lane) {
+                                     float* row_smem, int lane, const ResampleCheck ck = ResampleCheck{nullptr, nullptr, nullptr, 0}) {
   const int M = S - 1;                               // bins = z_mid (S-1), weights[1:-1] (S-2)
   float* cdf = row_smem;
   float* bs = cdf + M;
@@ -472,8 +522,16 @@ __device__ void resample_row_generic(const float* __restrict__ z_vals, const flo
   } else {
     for (int j = Ni + lane; j < NiP; j += 32) sm[j] = inf;
   }
-  warp_build_cdf(weights + r * S + 1, M, cdf, lane);
+  if (ck.cdf_in) {
+    for (int i = lane; i < M; i += 32) cdf[i] = __ldg(ck.cdf_in + r * M + i);
+  } else if (ck.ref_lanes) {
+    warp_build_cdf_ref(weights + r * S + 1, M, cdf, lane, ck.ref_lanes);
+  } else {
+    warp_build_cdf(weights + r * S + 1, M, cdf, lane);
+  }
   __syncwarp();
+  if (ck.cdf_out)
+    for (int i = lane; i < M; i += 32) ck.cdf_out[r * M + i] = cdf[i];
   if (u_in) warp_bitonic_sort(sm, NiP, lane);        // ascending uniforms -> ascending samples
   float s1 = 0.f;
   for (int j = lane; j < Ni; j += 32) {
@@ -482,6 +540,7 @@ __device__ void resample_row_generic(const float* __restrict__ z_vals, const flo
     float sv = invert_cdf(cdf, bs, M, u, &ind);
     sm[j] = sv;
     s1 += sv;
+    if (ck.inds_out) ck.inds_out[r * Ni + j] = (int64_t)ind;
   }
   __syncwarp();
   // repair one-ulp inversions between neighbours, then verify
@@ -515,13 +574,13 @@ __device__ void resample_row_generic(const float* __restrict__ z_vals, const flo
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 resample_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
                 int64_t N, int S, int Ni, int NiP, float* __restrict__ z_samples, float* __restrict__ z_fine,
-                float* __restrict__ z_std) {
+                float* __restrict__ z_std, const ResampleCheck ck) {
   extern __shared__ float smem[];
   int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int64_t r = (int64_t)blockIdx.x * kWarpsPerBlock + warp;
   if (r >= N) return;
   resample_row_generic(z_vals, weights, u_in, r, S, Ni, NiP, z_samples, z_fine, z_std,
-                       smem + (size_t)warp * (2 * (S - 1) + S + NiP + S + Ni), lane);
+                       smem + (size_t)warp * (2 * (S - 1) + S + NiP + S + Ni), lane, ck);
 }
 
 // Specialisation for the reference configs' shape (64 coarse samples, 128 importance samples): everything a lane owns
@@ -739,10 +798,13 @@ __device__ unsigned long long g_resample_fallbacks = 0ull;
 constexpr int kQRow = 456;
 constexpr int kQWarps = 4;                 // warps per block (16 rays): 29 KB of shared memory; 5-6 blocks per SM (registers)
 
-template <bool RANDOM>
+// CHECK adds the test entry's cdf-in / inds-out / cdf-out (swnerf_resample_check); the production instances
+// (CHECK = false) carry none of it.
+template <bool RANDOM, bool CHECK = false>
 __global__ void __launch_bounds__(kQWarps * 32, 5)
 resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
-                   int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std) {
+                   int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std,
+                   const ResampleCheck ck = ResampleCheck{nullptr, nullptr, nullptr, 0}) {
   constexpr int S = 64, Ni = 128;
   extern __shared__ __align__(16) float smem[];
   const unsigned full = 0xffffffffu;
@@ -867,6 +929,16 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   if (g == 0) ex = 0.f;
 #pragma unroll
   for (int i = 0; i < 8; ++i) q[i] = __fadd_rn(ex, q[i]);
+  if (CHECK) {
+    if (ck.cdf_in) {                                           // given cdf[0..62]; entry 63 repeats entry 62 (w[63] adds 0)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) q[i] = __ldg(ck.cdf_in + rr * 63 + min(8 * g + i, 62));
+    }
+    if (ck.cdf_out && valid) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) if (8 * g + i < 63) ck.cdf_out[r * 63 + 8 * g + i] = q[i];
+    }
+  }
   // the cdf is stored in search order, one small table per probe level (the three upper levels live in registers):
   // lv4[m] = cdf[8m+3], lv2[m] = cdf[4m+1], lv1[m] = cdf[2m].  Rays that probe neighbouring entries of a level are then
   // a few banks apart, never a multiple of the 8-bank row skew (the linear array made two rays of a warp collide
@@ -918,6 +990,9 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
     pc += (lds_f32(cdf_sa + (pc >> 1)) <= uu) ? 4u : 0u;       // lv4[pc / 8]      = cdf[pc + 3]
     pc += (lds_f32(cdf_sa + 32 + pc) <= uu) ? 2u : 0u;         // lv2[pc / 4]      = cdf[pc + 1]
     pc += (lds_f32(cdf_sa + 96 + 2 * pc) <= uu) ? 1u : 0u;     // lv1[pc / 2]      = cdf[pc]
+    if (CHECK) {                                               // ray.py:136 over the 63 real entries
+      if (ck.inds_out && valid) ck.inds_out[r * Ni + g + 8 * i] = (int64_t)min(pc, 63u);
+    }
     const unsigned pb = 4 * pc;
     ok = ok && (pb != 0);                                      // u >= cdf[0] = 0
     const unsigned x = max(pb, 4u) - 4u;                       // 4 x below (ray.py:137)
@@ -1011,7 +1086,7 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
     if (((okmask >> (8 * sb)) & 0xffu) == 0xffu || r0 + sb >= N) continue;
     if (lane == 0) atomicAdd(&g_resample_fallbacks, 1ull);
     resample_row_generic(z_vals, weights, RANDOM ? u_in : nullptr, r0 + sb, S, Ni, Ni, z_samples, z_fine, z_std,
-                         wbase, lane);
+                         wbase, lane, ck);
     __syncwarp();
   }
 }
@@ -1090,12 +1165,13 @@ int swnerf_encode_points(const float* rays, int ray_stride, int view_col, const 
   return check_launch("encode_points");
 }
 
-int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+int swnerf_composite_fwd(const float* raw, int raw_ch, const float* z_vals, const float* rays, int ray_stride, int d_col,
                          const float* noise, int white_bkgd, int64_t n_rays, int n_samples, float* rgb_map,
                          float* disp_map, float* acc_map, float* weights, float* depth_map, void* stream) {
   SW_REQUIRE(raw && z_vals && rays && rgb_map && disp_map && acc_map && weights && depth_map,
              "composite_fwd: null pointer");
-  SW_REQUIRE(aligned16(raw), "composite_fwd: raw must be 16-byte aligned");
+  SW_REQUIRE(raw_ch >= 4, "composite_fwd: raw needs at least 4 channels per sample (rgb, sigma), got %d", raw_ch);
+  SW_REQUIRE(raw_ch != 4 || aligned16(raw), "composite_fwd: raw must be 16-byte aligned");
   SW_REQUIRE(n_samples >= 1, "composite_fwd: n_samples < 1");
   if (n_rays == 0) return SWNERF_OK;
   SW_REQUIRE(n_samples <= 1024, "composite_fwd: n_samples > 1024");
@@ -1103,7 +1179,7 @@ int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* ray
   const int nc = (n_samples + 31) / 32;
 #define SW_FWD(NC)                                                                                              \
   composite_fwd_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(                            \
-      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, rgb_map, disp_map, acc_map,    \
+      raw, raw_ch, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, rgb_map, disp_map, acc_map, \
       weights, depth_map)
   if (nc <= 2) SW_FWD(2); else if (nc <= 4) SW_FWD(4); else if (nc <= 6) SW_FWD(6); else if (nc <= 8) SW_FWD(8);
   else if (nc <= 16) SW_FWD(16); else SW_FWD(32);
@@ -1111,23 +1187,24 @@ int swnerf_composite_fwd(const float* raw, const float* z_vals, const float* ray
   return check_launch("composite_fwd");
 }
 
-int swnerf_composite_bwd(const float* raw, const float* z_vals, const float* rays, int ray_stride, int d_col,
+int swnerf_composite_bwd(const float* raw, int raw_ch, const float* z_vals, const float* rays, int ray_stride, int d_col,
                          const float* noise, int white_bkgd, int64_t n_rays, int n_samples, const float* g_rgb,
                          const float* g_disp, const float* g_acc, const float* g_weights, const float* g_depth,
                          const float* acc_map, const float* depth_map, float* d_raw, void* stream) {
   SW_REQUIRE(raw && z_vals && rays && d_raw, "composite_bwd: null pointer");
-  SW_REQUIRE(aligned16(raw) && aligned16(d_raw), "composite_bwd: raw/d_raw must be 16-byte aligned");
+  SW_REQUIRE(raw_ch >= 4, "composite_bwd: raw needs at least 4 channels per sample (rgb, sigma), got %d", raw_ch);
+  SW_REQUIRE(raw_ch != 4 || (aligned16(raw) && aligned16(d_raw)), "composite_bwd: raw/d_raw must be 16-byte aligned");
   SW_REQUIRE(!g_disp || (acc_map && depth_map), "composite_bwd: g_disp needs saved acc/depth maps");
-  SW_REQUIRE(n_samples <= 512, "composite_bwd: n_samples > 512");
+  SW_REQUIRE(n_samples >= 1 && n_samples <= 1024, "composite_bwd: n_samples must be in 1..1024 (as the forward)");
   if (n_rays == 0) return SWNERF_OK;
   unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
   const int nc = (n_samples + 31) / 32;
 #define SW_BWD(NC)                                                                                              \
   composite_bwd_kernel<NC><<<blocks, kWarpsPerBlock * 32, 0, (cudaStream_t)stream>>>(                            \
-      raw, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, g_rgb, g_disp, g_acc, g_weights, \
+      raw, raw_ch, z_vals, rays, ray_stride, d_col, noise, white_bkgd, n_rays, n_samples, g_rgb, g_disp, g_acc, g_weights, \
       g_depth, acc_map, depth_map, d_raw)
   if (nc <= 2) SW_BWD(2); else if (nc <= 4) SW_BWD(4); else if (nc <= 6) SW_BWD(6); else if (nc <= 8) SW_BWD(8);
-  else SW_BWD(16);
+  else if (nc <= 16) SW_BWD(16); else SW_BWD(32);
 #undef SW_BWD
   return check_launch("composite_bwd");
 }
@@ -1183,11 +1260,9 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
   if (n_samples == 64 && n_importance == 128 && al && aligned16(z_fine) && g_resample_variant != 0) {
     // eight lanes per ray, four rays per warp
     const size_t qsmem = (size_t)kQWarps * 4 * kQRow * sizeof(float);
-    static bool attr_done = false;
-    if (!attr_done) {
+    if (once_per_device(ONCE_RESAMPLE64Q)) {
       cudaFuncSetAttribute(resample64q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
       cudaFuncSetAttribute(resample64q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
-      attr_done = true;
     }
     const unsigned qblocks = (unsigned)((n_rays + 4 * kQWarps - 1) / (4 * kQWarps));
     if (det) resample64q_kernel<false><<<qblocks, kQWarps * 32, qsmem, (cudaStream_t)stream>>>(
@@ -1204,8 +1279,46 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
     return check_launch("resample");
   }
   resample_kernel<<<blocks, kWarpsPerBlock * 32, smem, (cudaStream_t)stream>>>(
-      z_vals, weights, det ? nullptr : u, n_rays, n_samples, n_importance, P, z_samples, z_fine, z_std);
+      z_vals, weights, det ? nullptr : u, n_rays, n_samples, n_importance, P, z_samples, z_fine, z_std,
+      ResampleCheck{nullptr, nullptr, nullptr, 0});
   return check_launch("resample");
+}
+
+int swnerf_resample_check(const float* z_vals, const float* weights, const float* cdf_in, const float* u, int det,
+                          int64_t n_rays, int n_samples, int n_importance, int variant, int ref_lanes, float* z_samples,
+                          float* z_fine, float* z_std, int64_t* inds_out, float* cdf_out, void* stream) {
+  SW_REQUIRE(z_vals && weights && z_fine, "resample_check: null pointer");
+  SW_REQUIRE(det || u, "resample_check: random mode needs caller-supplied u");
+  SW_REQUIRE(n_samples >= 3 && n_importance >= 1, "resample_check: need n_samples >= 3 and n_importance >= 1");
+  SW_REQUIRE(variant == 0 || variant == 1, "resample_check: variant 0 (production kernel of the shape) or 1 (reference order)");
+  SW_REQUIRE(variant == 0 || ref_lanes == 8 || ref_lanes == 16, "resample_check: ref_lanes must be 8 (AVX2 host) or 16 (AVX512)");
+  int P = next_pow2(n_importance);
+  SW_REQUIRE(P <= 1024 && n_samples <= 1024, "resample_check: n_samples / n_importance > 1024");
+  if (n_rays == 0) return SWNERF_OK;
+  const ResampleCheck ck{cdf_in, inds_out, cdf_out, variant == 1 ? ref_lanes : 0};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (variant == 0 && n_samples == 64 && n_importance == 128) {
+    SW_REQUIRE(aligned16(z_vals) && aligned16(weights) && (det || aligned16(u)) && (!z_samples || aligned16(z_samples)) &&
+               aligned16(z_fine), "resample_check: the 64+128 kernel needs 16-byte aligned buffers");
+    const size_t qsmem = (size_t)kQWarps * 4 * kQRow * sizeof(float);
+    if (once_per_device(ONCE_RESAMPLE64Q_CHECK)) {
+      cudaFuncSetAttribute(resample64q_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      cudaFuncSetAttribute(resample64q_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+    }
+    const unsigned qblocks = (unsigned)((n_rays + 4 * kQWarps - 1) / (4 * kQWarps));
+    if (det) resample64q_kernel<false, true><<<qblocks, kQWarps * 32, qsmem, s>>>(z_vals, weights, nullptr, n_rays,
+                                                                                 z_samples, z_fine, z_std, ck);
+    else resample64q_kernel<true, true><<<qblocks, kQWarps * 32, qsmem, s>>>(z_vals, weights, u, n_rays, z_samples,
+                                                                            z_fine, z_std, ck);
+    return check_launch("resample_check");
+  }
+  size_t smem = (size_t)kWarpsPerBlock * (2 * (n_samples - 1) + n_samples + P + n_samples + n_importance) * sizeof(float);
+  unsigned blocks = (unsigned)((n_rays + kWarpsPerBlock - 1) / kWarpsPerBlock);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  resample_kernel<<<blocks, kWarpsPerBlock * 32, smem, s>>>(z_vals, weights, det ? nullptr : u, n_rays, n_samples,
+                                                           n_importance, P, z_samples, z_fine, z_std, ck);
+  return check_launch("resample_check");
 }
 
 int swnerf_searchsorted(const float* a, const float* v, int64_t* out, int64_t nrow_a, int64_t nrow_v,

@@ -217,7 +217,8 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
                     _, _, _, weights, _ = ops.composite(raw, z_vals, ray_batch, 3, noise, white_bkgd)
             det = (perturb == 0.)
             u = pytest_uniform([N_rays, N_importance], dev) if (pytest and not det) else None
-            _, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u, want_samples=False)
+            _, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u, want_samples=False,
+                                            exact=getattr(network_query_fn, "precision", None) == "fp32")
     else:
         z_vals = z_vals.contiguous().float()
 

@@ -100,6 +100,9 @@ class CompositeFn(torch.autograd.Function):
     def forward(ctx, raw, z_vals, rays, d_col, noise, white_bkgd):
         N, S = z_vals.shape
         dev = raw.device
+        if raw.dim() != 3 or tuple(raw.shape[:2]) != (N, S) or raw.shape[-1] < 4:
+            raise ValueError("raw must be [N, S, C >= 4] matching z_vals [N, S] (ray.py:175-186 reads channels 0..3); "
+                             "got %s for z_vals %s" % (tuple(raw.shape), tuple(z_vals.shape)))
         raw = raw if raw.is_contiguous() else raw.contiguous()
         rgb = torch.empty((N, 3), dtype=F32, device=dev)
         disp = torch.empty((N,), dtype=F32, device=dev)
@@ -107,7 +110,7 @@ class CompositeFn(torch.autograd.Function):
         depth = torch.empty((N,), dtype=F32, device=dev)
         weights = torch.empty((N, S), dtype=F32, device=dev)
         rp, stride = _rays(rays)
-        call("swnerf_composite_fwd", ptr(raw, F32, "raw"), ptr(z_vals, F32, "z_vals"), rp, stride, d_col,
+        call("swnerf_composite_fwd", ptr(raw, F32, "raw"), raw.shape[-1], ptr(z_vals, F32, "z_vals"), rp, stride, d_col,
              ptr(noise, F32, "noise", allow_none=True), int(bool(white_bkgd)), N, S, rgb.data_ptr(),
              disp.data_ptr(), acc.data_ptr(), weights.data_ptr(), depth.data_ptr(), stream())
         ctx.save_for_backward(raw, z_vals, rays, noise, acc, depth)
@@ -130,7 +133,7 @@ class CompositeFn(torch.autograd.Function):
             return None, None, None, None, None, None
         d_raw = torch.empty_like(raw)
         rp, stride = _rays(rays)
-        call("swnerf_composite_bwd", raw.data_ptr(), z_vals.data_ptr(), rp, stride, ctx.d_col,
+        call("swnerf_composite_bwd", raw.data_ptr(), raw.shape[-1], z_vals.data_ptr(), rp, stride, ctx.d_col,
              None if noise is None else noise.data_ptr(), int(ctx.white), N, S,
              *[None if g is None else g.data_ptr() for g in keep],
              acc.data_ptr(), depth.data_ptr(), d_raw.data_ptr(), stream())
@@ -158,10 +161,17 @@ def sample_pdf(bins, weights, n_samples: int, det=False, u=None, cdf=None, retur
     return (samples, inds) if return_inds else samples
 
 
-def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples=True):
+# SIMD lanes of the ATen CPU sum kernel behind the reference's torch.sum (ray.py:112): ATen registers its sum kernel
+# for AVX2 only (8 fp32 lanes), AVX512 hosts included (pinned against torch.sum on the host by the CPU tests)
+REF_SUM_LANES = 8
+
+
+def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples=True, exact=False):
     """Returns (z_samples, z_fine, z_std): nerf/run.py:396-400 and :416.  z_samples comes back in ascending
     order (the reference uses it only through std() and the sort, both order-free); render_rays passes
-    want_samples=False - it only needs z_std, which the kernel computes itself - and gets None for it."""
+    want_samples=False - it only needs z_std, which the kernel computes itself - and gets None for it.
+    exact=True (the precision='fp32' check mode): the reference-order routine (swnerf_resample_check variant 1),
+    whose z_fine is bit-identical to the reference's for identical weights."""
     N, S = z_vals.shape
     dev = z_vals.device
     if not det and u is None:
@@ -169,10 +179,32 @@ def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples
     z_samples = torch.empty((N, n_importance), dtype=F32, device=dev) if want_samples else None
     z_fine = torch.empty((N, S + n_importance), dtype=F32, device=dev)
     z_std = torch.empty((N,), dtype=F32, device=dev)
+    if exact and S <= 512:
+        call("swnerf_resample_check", ptr(z_vals, F32, "z_vals"), ptr(weights, F32, "weights"), None,
+             None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance, 1, REF_SUM_LANES,
+             z_samples.data_ptr() if want_samples else None, z_fine.data_ptr(), z_std.data_ptr(), None, None, stream())
+        return z_samples, z_fine, z_std
     call("swnerf_resample", ptr(z_vals, F32, "z_vals"), ptr(weights, F32, "weights"),
          None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance,
          z_samples.data_ptr() if want_samples else None, z_fine.data_ptr(), z_std.data_ptr(), stream())
     return z_samples, z_fine, z_std
+
+
+def resample_check(z_vals, weights, n_importance: int, det=False, u=None, cdf=None, variant=0, ref_lanes=REF_SUM_LANES):
+    """Test entry (swnerf_resample_check): returns dict(z_samples, z_fine, z_std, inds, cdf).  `cdf` [N, S-1]
+    replaces the cdf built from the weights; `inds` are torch.searchsorted(cdf, sort(u), right=True)."""
+    N, S = z_vals.shape
+    dev = z_vals.device
+    out = dict(z_samples=torch.empty((N, n_importance), dtype=F32, device=dev),
+               z_fine=torch.empty((N, S + n_importance), dtype=F32, device=dev),
+               z_std=torch.empty((N,), dtype=F32, device=dev),
+               inds=torch.empty((N, n_importance), dtype=torch.int64, device=dev),
+               cdf=torch.empty((N, S - 1), dtype=F32, device=dev))
+    call("swnerf_resample_check", ptr(z_vals, F32, "z_vals"), ptr(weights, F32, "weights"),
+         ptr(cdf, F32, "cdf", allow_none=True), None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance,
+         int(variant), int(ref_lanes), out["z_samples"].data_ptr(), out["z_fine"].data_ptr(), out["z_std"].data_ptr(),
+         out["inds"].data_ptr(), out["cdf"].data_ptr(), stream())
+    return out
 
 
 def searchsorted(a, v, out=None, side="left"):

@@ -32,9 +32,20 @@ class FlatGrads:
         dev = self.params[0].device
         self.flat = torch.zeros(n, dtype=torch.float32, device=dev)
         off = 0
+        self.offsets = {}
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            self.offsets[id(p)] = (off, off + p.numel())
             off += p.numel()
+        tc.direct_grads(self.params, True)     # the fused backward accumulates straight into these views
+
+    def span(self, params):
+        """(lo, hi) of the contiguous slice of the flat buffer that holds `params` (e.g. one network)."""
+        spans = sorted(self.offsets[id(p)] for p in params if id(p) in self.offsets)
+        lo, hi = spans[0][0], spans[-1][1]
+        if sum(b - a for a, b in spans) != hi - lo:
+            raise ValueError("these parameters are not contiguous in the flat buffer")
+        return lo, hi
 
     def zero_(self):
         self.flat.zero_()

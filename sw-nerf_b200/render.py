@@ -193,7 +193,9 @@ def render_rays(ray_batch, network_fn, network_query_fn, N_samples, retraw=False
         rgb_map_0, disp_map_0, acc_map_0 = rgb_map, disp_map, acc_map
         det = (perturb == 0.)
         u = pytest_uniform([N_rays, N_importance], dev) if (pytest and not det) else None
-        _, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u, want_samples=False)
+        exact = getattr(network_query_fn, "precision", None) == "fp32"      # check mode: the reference's summation order
+        _, z_vals, z_std = ops.resample(z_vals, weights.detach(), N_importance, det=det, u=u, want_samples=False,
+                                        exact=exact)
         run_fn = network_fn if network_fine is None else network_fine
         raw = _query(network_query_fn, ray_batch, z_vals, run_fn, view_col)
         noise = raw_noise((N_rays, N_samples + N_importance), raw_noise_std, dev, pytest)

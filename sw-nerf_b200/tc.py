@@ -4,6 +4,8 @@ The kernels live in csrc/mlp_tc*.cu behind swnerf_tc_* (include/swnerf_b200.h). 
 packed fp16 image of each network's weights, re-packed whenever a parameter changed (the optimizer
 bumps the tensors' version counters); the fp32 nn.Parameters stay the master copy.
 """
+import weakref
+
 import torch
 
 from . import _lib
@@ -20,22 +22,92 @@ def bwd_available() -> bool:
     return int(_lib.lib().swnerf_tc_packed_t_bytes()) > 0
 
 
+class _Token:
+    """Held by the autograd ctx of a training forward until its backward has run (or the graph is dropped)."""
+    __slots__ = ("__weakref__",)
+
+
 class _Packed:
-    __slots__ = ("versions", "fwd", "bwd", "bwd_versions")
+    """Per-network derived state: packed fp16 weight images and the training workspace.  A forward that will be
+    differentiated takes a lease on both; while a lease is alive a re-pack (parameters changed, another frame time)
+    or another training forward gets FRESH buffers instead of overwriting the ones the pending backward will read."""
+    __slots__ = ("versions", "fwd", "bwd", "bwd_versions", "leases", "ws", "ws_leases")
 
     def __init__(self):
         self.versions = None
         self.fwd = None
         self.bwd = None
         self.bwd_versions = None
+        self.leases = []
+        self.ws = None
+        self.ws_leases = []
+
+    @staticmethod
+    def _alive(leases):
+        leases[:] = [r for r in leases if r() is not None]
+        return bool(leases)
+
+    def lease(self):
+        tok = _Token()
+        self.leases.append(weakref.ref(tok))
+        return tok
+
+    def release_if_leased(self):
+        """Before overwriting the packed images: drop them (the pending backward keeps its own references)."""
+        if self._alive(self.leases):
+            self.fwd = self.bwd = None
+            self.bwd_versions = None
+            self.leases = []
+
+    def workspace(self, nbytes, dev):
+        """A workspace of at least nbytes that no pending backward reads: the cached one when it is free (the steady
+        state of a training loop: one allocation for the whole run), otherwise a fresh one."""
+        if self.ws is None or self.ws.numel() < nbytes or self.ws.device != dev or self._alive(self.ws_leases):
+            self.ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            self.ws_leases = []
+        tok = _Token()
+        self.ws_leases.append(weakref.ref(tok))
+        return self.ws, tok
 
 
-# bumped by optimizers that update the parameters behind autograd's back (parallel.FlatAdam)
+# bumped whenever parameters change behind autograd's back: parallel.FlatAdam.step(), and invalidate() below
 GENERATION = 0
+
+
+def invalidate(network=None):
+    """Mark the packed fp16 images stale.  Needed only after edits the tensors' version counters do not see:
+    `p.data.copy_ / mul_` (EMA updates), `p.data = ...` (load_weights_from_keras).  optimizer.step(), load_state_dict
+    and every in-place op on the parameter itself are detected without it."""
+    global GENERATION
+    GENERATION += 1
 
 
 def _versions(params):
     return (GENERATION,) + tuple((p.data_ptr(), p._version) for p in params)
+
+
+def direct_grads(params, on=True):
+    """Opt in (parallel.FlatGrads does) to the backward kernels accumulating straight into the dense fp32 `.grad` of
+    these parameters instead of returning gradients to autograd: no zero-fill + AccumulateGrad per tensor, and the
+    flat all-reduce buffer is written in place.  Autograd hooks on these parameters do NOT fire in this mode and
+    torch.autograd.grad() sees None for them, which is why it is never inferred."""
+    for p in params:
+        p._swnerf_direct_grad = bool(on)
+
+
+def _grad_targets(params):
+    direct = all(getattr(p, "_swnerf_direct_grad", False) and p.grad is not None and p.grad.dtype == F32
+                 and p.grad.is_contiguous() and p.grad.device == p.device for p in params)
+    return direct, ([p.grad for p in params] if direct else [torch.zeros_like(p) for p in params])
+
+
+def _take_ws(ctx):
+    ws = ctx.ws
+    if ws is None:
+        raise RuntimeError("swnerf_b200: backward through this network query ran twice (retain_graph=True?) - the "
+                           "saved activations were released after the first pass; call the forward again")
+    ctx.ws = ctx.ws_lease = ctx.lease = None
+    return ws
 
 
 def packed_weights(network, need_bwd=False):
@@ -49,6 +121,7 @@ def packed_weights(network, need_bwd=False):
     if st.versions != v or st.fwd is None:
         for p in params:
             ptr(p, F32, "parameter")
+        st.release_if_leased()
         if st.fwd is None or st.fwd.device != dev:
             st.fwd = torch.empty(int(_lib.lib().swnerf_tc_packed_bytes()), dtype=torch.uint8, device=dev)
         call("swnerf_tc_pack_weights", ptr_array([p.detach() for p in params]), st.fwd.data_ptr(), stream())
@@ -71,14 +144,13 @@ class TcMlpFn(torch.autograd.Function):
         raw = torch.empty((N, S, 4), dtype=F32, device=dev)
         ws = None
         if training:
-            nbytes = int(_lib.lib().swnerf_tc_workspace_bytes(N * S, 1))
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws, ctx.ws_lease = st.workspace(int(_lib.lib().swnerf_tc_workspace_bytes(N * S, 1)), dev)
         call("swnerf_tc_mlp_fwd", ptr(ray_batch, F32, "ray_batch"), ray_batch.shape[1], view_col,
              ptr(z_vals, F32, "z_vals"), N, S, st.fwd.data_ptr(), raw.data_ptr(),
              None if ws is None else ws.data_ptr(), int(training), stream())
         if training:
             ctx.network, ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = network, ws, (N, S), params, grad_scale
-            ctx.packed = (st.fwd, st.bwd)
+            ctx.packed, ctx.lease = (st.fwd, st.bwd), st.lease()
         return raw
 
     @staticmethod
@@ -86,18 +158,17 @@ class TcMlpFn(torch.autograd.Function):
         N, S = ctx.shape
         params = ctx.params
         d_raw = d_raw.contiguous()
-        # The kernels ACCUMULATE into the buffers they are given.  When every parameter already owns a
-        # dense .grad (optimizer.zero_grad(set_to_none=False), or parallel.FlatGrads' views into the flat
-        # all-reduce buffer) the gradients go straight there - the same result loss.backward() leaves in
-        # .grad, without 24 zero-fills and 24 AccumulateGrad adds per network.
-        direct = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous()
-                     and p.grad.device == p.device for p in params) and not torch.is_grad_enabled()
-        grads = [p.grad for p in params] if direct else [torch.zeros_like(p) for p in params]
+        # The kernels ACCUMULATE into the buffers they are given.  For parameters that opted in (direct_grads():
+        # parallel.FlatGrads' views into the flat all-reduce buffer) the gradients go straight into .grad - the same
+        # result loss.backward() leaves there, without 24 zero-fills and 24 AccumulateGrad adds per network.
+        direct, grads = _grad_targets(params)
+        if direct and torch.is_grad_enabled():                   # create_graph=True: autograd needs real outputs
+            direct, grads = False, [torch.zeros_like(p) for p in params]
         fwd, bwd = ctx.packed
+        ws = _take_ws(ctx)
         call("swnerf_tc_mlp_bwd", ptr(d_raw, F32, "d_raw"), N, S, fwd.data_ptr(), bwd.data_ptr(),
-             ptr_array([p.detach() for p in params]), ctx.ws.data_ptr(), ptr_array(grads),
+             ptr_array([p.detach() for p in params]), ws.data_ptr(), ptr_array(grads),
              float(ctx.grad_scale), stream())
-        ctx.ws = None
         if direct:
             return (None,) * (6 + len(params))
         return (None, None, None, None, None, None) + tuple(grads)
@@ -144,6 +215,7 @@ def packed_time_weights(model, t: float, need_bwd=False):
     if st.versions != v or st.fwd is None:
         for p in params:
             ptr(p, F32, "parameter")
+        st.release_if_leased()          # e.g. the tv-loss render at a neighbouring time before the backward
         if st.fwd is None or st.fwd.device != dev:
             st.fwd = torch.empty(int(_lib.lib().swnerf_tc_packed_bytes()), dtype=torch.uint8, device=dev)
         tpe = time_embedding(t)
@@ -159,12 +231,6 @@ def packed_time_weights(model, t: float, need_bwd=False):
     return st
 
 
-def _grad_targets(params):
-    direct = all(p.grad is not None and p.grad.dtype == F32 and p.grad.is_contiguous() and p.grad.device == p.device
-                 for p in params) and not torch.is_grad_enabled()
-    return direct, ([p.grad for p in params] if direct else [torch.zeros_like(p) for p in params])
-
-
 class TcTimeFn(torch.autograd.Function):
     """dx[N,S,3] = deformation network at (o + d z, t)  (model.py:128-136) on the fused forward kernel."""
 
@@ -174,14 +240,15 @@ class TcTimeFn(torch.autograd.Function):
         dev = z_vals.device
         st = packed_time_weights(model, t, need_bwd=training)
         dx = torch.empty((N, S, 3), dtype=F32, device=dev)
-        ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(N * S, 1)), dtype=torch.uint8, device=dev) \
-            if training else None
+        ws = None
+        if training:
+            ws, ctx.ws_lease = st.workspace(int(_lib.lib().swnerf_tc_workspace_bytes(N * S, 1)), dev)
         call("swnerf_tc_time_fwd", ptr(ray_batch, F32, "ray_batch"), ray_batch.shape[1], view_col,
              ptr(z_vals, F32, "z_vals"), N, S, st.fwd.data_ptr(), dx.data_ptr(),
              None if ws is None else ws.data_ptr(), int(training), stream())
         if training:
             ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = ws, (N, S), params, grad_scale
-            ctx.packed = (st.fwd, st.bwd)
+            ctx.packed, ctx.lease = (st.fwd, st.bwd), st.lease()
             ctx.tpe = torch.tensor(time_embedding(t), dtype=F32, device=dev)
         return dx
 
@@ -192,10 +259,10 @@ class TcTimeFn(torch.autograd.Function):
         d_dx = d_dx.contiguous()
         direct, grads = _grad_targets(params)
         fwd, bwd = ctx.packed
+        ws = _take_ws(ctx)
         call("swnerf_tc_time_bwd", ptr(d_dx, F32, "d_dx"), N, S, fwd.data_ptr(), bwd.data_ptr(),
-             ptr_array([p.detach() for p in params]), ctx.tpe.data_ptr(), ctx.ws.data_ptr(), ptr_array(grads),
+             ptr_array([p.detach() for p in params]), ctx.tpe.data_ptr(), ws.data_ptr(), ptr_array(grads),
              float(ctx.grad_scale), stream())
-        ctx.ws = None
         return (None,) * 7 + ((None,) * len(params) if direct else tuple(grads))
 
 
@@ -210,14 +277,15 @@ class TcOccPointsFn(torch.autograd.Function):
         pts = pts.contiguous()
         st = packed_weights(network, need_bwd=training)
         raw = torch.empty((N, n_samples, 4), dtype=F32, device=dev)
-        ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(P, 1)), dtype=torch.uint8, device=dev) \
-            if training else None
+        ws = None
+        if training:
+            ws, ctx.ws_lease = st.workspace(int(_lib.lib().swnerf_tc_workspace_bytes(P, 1)), dev)
         call("swnerf_tc_mlp_fwd_points", ptr(ray_batch, F32, "ray_batch"), ray_batch.shape[1], view_col,
              ptr(pts, F32, "pts"), N, n_samples, st.fwd.data_ptr(), raw.data_ptr(),
              None if ws is None else ws.data_ptr(), int(training), stream())
         if training:
             ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = ws, (N, n_samples), params, grad_scale
-            ctx.packed = (st.fwd, st.bwd)
+            ctx.packed, ctx.lease = (st.fwd, st.bwd), st.lease()
             ctx.pts = pts
             ctx.pts_grad = ctx.needs_input_grad[2]
         return raw
@@ -230,10 +298,10 @@ class TcOccPointsFn(torch.autograd.Function):
         direct, grads = _grad_targets(params)
         fwd, bwd = ctx.packed
         d_pts = torch.empty_like(ctx.pts) if ctx.pts_grad else None
+        ws = _take_ws(ctx)
         call("swnerf_tc_mlp_bwd_points", ptr(d_raw, F32, "d_raw"), N, S, fwd.data_ptr(), bwd.data_ptr(),
-             ptr_array([p.detach() for p in params]), ctx.ws.data_ptr(), ptr_array(grads), float(ctx.grad_scale),
+             ptr_array([p.detach() for p in params]), ws.data_ptr(), ptr_array(grads), float(ctx.grad_scale),
              ctx.pts.data_ptr() if ctx.pts_grad else None, None if d_pts is None else d_pts.data_ptr(), stream())
-        ctx.ws = None
         return (None, None, d_pts, None, None, None, None) + ((None,) * len(params) if direct else tuple(grads))
 
 

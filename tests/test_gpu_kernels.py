@@ -210,6 +210,70 @@ def test_resample(N, S_, Ni, det, variant):
     close(zstd, torch.std(zs_c, dim=-1, unbiased=False), rtol=1e-4, atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", ["det", "rand"])
+def test_resample64q_indices_bit_exact_given_cdf(golden, mode):
+    """The north_star's index bar on the PRODUCTION kernel of the 64+128 shape (resample64q_kernel, the one
+    render_rays launches): fed the reference's cdf, its branchless 6-probe search returns exactly
+    torch.searchsorted(cdf, u, right=True) (ray.py:136) for every sample of every ray - degenerate rows included."""
+    from swnerf_b200 import _lib
+    g = golden("resample")
+    z, w, cdf = T(g["z_vals"]), T(g["weights"]), T(g["cdf"])
+    det = mode == "det"
+    u = None if det else T(g["u_rand"])
+    _lib.resample_fallbacks(reset=True)
+    out = ops.resample_check(z, w, 128, det=det, u=u, cdf=cdf, variant=0)
+    inds_ref = g[f"{mode}/inds"]
+    if not det:      # the kernel draws the samples in ascending-u order
+        order = np.argsort(g["u_rand"], axis=-1, kind="stable")
+        inds_ref = np.take_along_axis(inds_ref, order, -1)
+    np.testing.assert_array_equal(out["inds"].cpu().numpy(), inds_ref)
+    np.testing.assert_array_equal(out["cdf"].cpu().numpy(), g["cdf"])
+    # samples from the reference's cdf: equal up to the kernel's reciprocal (1 / denom, MUFU: <= 2 ulp of t, a 0.06-wide
+    # bin) - except where denom ~ 1e-5 amplifies it (the flat-cdf rows), as in test_sample_pdf_indices_bit_exact_given_cdf
+    zs_ref = np.sort(g[f"{mode}/z_samples"], -1)
+    close(out["z_samples"], zs_ref, rtol=1e-6, atol=2e-5)
+    assert float((out["z_samples"].cpu() - torch.from_numpy(zs_ref)).abs().median()) < 5e-7
+    zf = out["z_fine"].cpu()
+    assert torch.equal(zf, torch.sort(torch.cat([torch.from_numpy(g["z_vals"]), out["z_samples"].cpu()], -1), -1)[0])
+    assert _lib.resample_fallbacks() <= 8          # the degenerate rows may take the exact routine; the rest must not
+
+
+@pytest.mark.parametrize("mode", ["det", "rand"])
+def test_resample_reference_order_is_bit_identical(golden, mode):
+    """Check mode (what precision='fp32' runs): given the reference's coarse weights, the whole stage - pdf, cdf,
+    searchsorted, the inverse-cdf arithmetic, the merge with z_vals - reproduces the reference's tensors BIT FOR BIT
+    (ray.py:96-153 + nerf/run.py:396-400 run unmodified by oracle/make_golden.py)."""
+    g = golden("resample")
+    z, w = T(g["z_vals"]), T(g["weights"])
+    det = mode == "det"
+    out = ops.resample_check(z, w, 128, det=det, u=None if det else T(g["u_rand"]), variant=1)
+    np.testing.assert_array_equal(out["cdf"].cpu().numpy(), g["cdf"])
+    inds_ref = g[f"{mode}/inds"]
+    if not det:
+        inds_ref = np.take_along_axis(inds_ref, np.argsort(g["u_rand"], axis=-1, kind="stable"), -1)
+    np.testing.assert_array_equal(out["inds"].cpu().numpy(), inds_ref)
+    np.testing.assert_array_equal(out["z_samples"].cpu().numpy(), np.sort(g[f"{mode}/z_samples"], -1))
+    np.testing.assert_array_equal(out["z_fine"].cpu().numpy(), g[f"{mode}/z_fine"])
+    close(out["z_std"], g[f"{mode}/z_std"], rtol=1e-5, atol=1e-7)
+    # and through the public op render_rays uses in the check mode
+    _, zf, _ = ops.resample(z, w, 128, det=det, u=None if det else T(g["u_rand"]), want_samples=False, exact=True)
+    np.testing.assert_array_equal(zf.cpu().numpy(), g[f"{mode}/z_fine"])
+
+
+def test_resample_reference_order_other_shapes():
+    """Variant 1 on shapes the 64+128 kernels do not cover, against the live oracle (its torch.sum / cumsum order)."""
+    for N, S_, Ni in ((19, 16, 7), (9, 128, 64), (5, 33, 130)):
+        rs = np.random.RandomState(N)
+        z = np.sort(rs.uniform(2, 6, size=(N, S_)).astype(np.float32), -1)
+        w = (rs.uniform(0, 1, size=(N, S_)).astype(np.float32)) ** 5
+        zt, wt = torch.from_numpy(z), torch.from_numpy(w)
+        zs_ref = O.sample_pdf(0.5 * (zt[:, 1:] + zt[:, :-1]), wt[:, 1:-1], Ni, det=True)
+        zf_ref = torch.sort(torch.cat([zt, zs_ref], -1), -1)[0]
+        out = ops.resample_check(T(z), T(w), Ni, det=True, variant=1)
+        np.testing.assert_array_equal(out["cdf"].cpu().numpy(), O.pdf_to_cdf(wt[:, 1:-1]).numpy())
+        np.testing.assert_array_equal(out["z_fine"].cpu().numpy(), zf_ref.numpy())
+
+
 def test_resample_variants_agree_at_render_size():
     """The two kernels of the 64+128 shape on a 32,768-ray render chunk (+3 so the last warp is ragged): identical
     merged rows up to the samples' own rounding (the pdf is normalised by a reciprocal in one and a division in the

@@ -75,6 +75,47 @@ def test_sample_pdf(golden):
     np.testing.assert_array_equal(inds.numpy(), g["inds_rand128"])
 
 
+@pytest.mark.parametrize("mode", ["det", "rand"])
+def test_resample(golden, mode):
+    """nerf/run.py:396-400, :416 as the reference ran it: the oracle reproduces cdf, indices, samples and the merged
+    z_fine bit for bit on this host (same torch ops)."""
+    g = golden("resample")
+    z, w = T(g["z_vals"]), T(g["weights"])
+    z_mid = 0.5 * (z[:, 1:] + z[:, :-1])
+    cdf = O.pdf_to_cdf(w[:, 1:-1])
+    np.testing.assert_array_equal(cdf.numpy(), g["cdf"])
+    det = mode == "det"
+    u = T(g["u_rand"]) if not det else torch.linspace(0.0, 1.0, 128).expand(z.shape[0], 128).contiguous()
+    zs, inds = O.sample_from_cdf(z_mid, cdf, u)
+    np.testing.assert_array_equal(inds.numpy(), g[f"{mode}/inds"])
+    np.testing.assert_array_equal(zs.numpy(), g[f"{mode}/z_samples"])
+    zf = torch.sort(torch.cat([z, zs], -1), -1)[0]
+    np.testing.assert_array_equal(zf.numpy(), g[f"{mode}/z_fine"])
+    close(torch.std(zs, dim=-1, unbiased=False).numpy(), g[f"{mode}/z_std"])
+
+
+def test_cpu_sum_order_is_the_one_the_check_mode_follows(golden):
+    """ray.py:112's torch.sum on this host == the 8-lane order restated in O.torch_cpu_sum_order (and implemented by
+    the CUDA check mode, ops.REF_SUM_LANES): on the golden weights and on random rows of several lengths."""
+    g = golden("resample")
+    w = (g["weights"][:, 1:-1] + np.float32(1e-5)).astype(np.float32)
+    ref = T(w).sum(-1).numpy()
+    mine = np.array([O.torch_cpu_sum_order(r) for r in w], dtype=np.float32)
+    np.testing.assert_array_equal(mine, ref)
+    rs = np.random.RandomState(3)
+    for n in (3, 14, 30, 62, 126, 190, 254, 510):
+        x = (rs.rand(40, n).astype(np.float32) ** 3).astype(np.float32)
+        np.testing.assert_array_equal(np.array([O.torch_cpu_sum_order(r) for r in x], dtype=np.float32), T(x).sum(-1).numpy())
+    # torch.cumsum on CPU: sequential accumulation in double, rounded to float at every step
+    p = T(w / ref[:, None])
+    acc = np.zeros(p.shape[0], dtype=np.float64)
+    seq = []
+    for i in range(p.shape[1]):
+        acc = acc + p[:, i].numpy().astype(np.float64)
+        seq.append(acc.astype(np.float32))
+    np.testing.assert_array_equal(np.stack(seq, -1), torch.cumsum(p, -1).numpy())
+
+
 def test_searchsorted(golden):
     g = golden("searchsorted")
     for k in range(int(g["n"])):

@@ -36,9 +36,9 @@ for N in (4096, 32768, 262144):
         rgb = torch.empty(N, 3, device=dev); disp = torch.empty(N, device=dev); acc = torch.empty(N, device=dev)
         dep = torch.empty(N, device=dev); w = torch.empty(N, Ssamp, device=dev); d_raw = torch.empty_like(raw)
         g = torch.randn(N, 3, device=dev)
-        fwd = lambda: call("swnerf_composite_fwd", raw.data_ptr(), z.data_ptr(), rays.data_ptr(), 11, 3, None, 1, N, Ssamp,
+        fwd = lambda: call("swnerf_composite_fwd", raw.data_ptr(), 4, z.data_ptr(), rays.data_ptr(), 11, 3, None, 1, N, Ssamp,
                            rgb.data_ptr(), disp.data_ptr(), acc.data_ptr(), w.data_ptr(), dep.data_ptr(), st())
-        bwd = lambda: call("swnerf_composite_bwd", raw.data_ptr(), z.data_ptr(), rays.data_ptr(), 11, 3, None, 1, N, Ssamp,
+        bwd = lambda: call("swnerf_composite_bwd", raw.data_ptr(), 4, z.data_ptr(), rays.data_ptr(), 11, 3, None, 1, N, Ssamp,
                            g.data_ptr(), None, None, None, None, acc.data_ptr(), dep.data_ptr(), d_raw.data_ptr(), st())
         ms = timeit(fwd)
         b = N * (24 * Ssamp + 36)

@@ -205,10 +205,24 @@ int swnerf_tc_time_bwd(const float* d_dx, int64_t n_rays, int n_samples, const v
 /* ---- next rows, one step either side of the path ------------------------------------------
  * f1: ray assembly (ray.py:10-38 get_rays, nerf/run.py:137-158): pixel p = j*W + i ->
  *     rays[k] = [o(3), d(3), near, far, (frame_time), (unit viewdir(3))].  pixels == NULL: all H*W pixels in
- *     row-major order.  c2w_host12: HOST pointer to the 3x4 camera-to-world matrix, row-major. */
+ *     row-major order.  c2w_host12: HOST pointer to the 3x4 camera-to-world matrix, row-major.  ndc != 0 applies
+ *     ndc_rays(H, W, ndc_focal, ndc_near, o, d) (ray.py:75-92) to origin and direction after the unit viewdir was taken
+ *     from the camera-space direction, as render() does for the LLFF configs (nerf/run.py:137-147; ndc_near = 1);
+ *     ndc_focal is K[0][0] in double precision (the reference forms -1/(W/(2 focal)) in Python doubles). */
 int swnerf_make_rays(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host12,
                      const int64_t* pixels, int64_t n_rays, float nearv, float farv, float frame_time, int has_time,
-                     int with_viewdirs, float* rays, int ray_stride, void* stream);
+                     int with_viewdirs, int ndc, float ndc_near, double ndc_focal, float* rays, int ray_stride,
+                     void* stream);
+/* f1: the per-step training batch of nerf/run.py:652-681 in one kernel: n_rand DISTINCT pixels drawn from the crop
+ *     [crop_y0, crop_y0+crop_h) x [crop_x0, crop_x0+crop_w) of the H x W image (the whole image, or the centre crop of the
+ *     first precrop_iters iterations), their ray rows (as swnerf_make_rays) and their target colours gathered from
+ *     image[H*W, 3] (device; optional together with `target`).  The draw is pixel k = perm_seed(k), a keyed bijection of
+ *     the crop (Feistel network, cycle-walked): without replacement by construction like np.random.choice(...,
+ *     replace=False), stateless, no host round trip.  pixels_out (optional) receives the flat ids y*W + x. */
+int swnerf_pick_batch(int H, int W, float fx, float fy, float cx, float cy, const float* c2w_host12, const float* image,
+                      int crop_y0, int crop_x0, int crop_h, int crop_w, uint64_t seed, int64_t n_rand, float nearv,
+                      float farv, float frame_time, int has_time, int with_viewdirs, int ndc, float ndc_near,
+                      double ndc_focal, float* rays, int ray_stride, float* target, int64_t* pixels_out, void* stream);
 /* f3: torch.optim.Adam (nerf/run.py:254; no weight decay, no amsgrad) on ONE flat buffer; `step` counts from 1. */
 int swnerf_adam_flat(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
                      float beta1, float beta2, float eps, int64_t step, void* stream);

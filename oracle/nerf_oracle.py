@@ -4,7 +4,8 @@ TEST INFRASTRUCTURE ONLY.  Nothing in the product path (sw-nerf_b200/) imports
 this file; only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
 --impl reference leg may use it, and only as the checker.
 
-It is a plain fp32 PyTorch-on-CPU restatement of the reference algorithm (the
+It is a plain fp32 PyTorch restatement of the reference algorithm, run on the CPU by the tests (device-agnostic, like
+the reference: bench.py's `gpu_eager_baseline` leg times it unchanged on the B200 - the reference's own deployment) (the
 reference itself is fp32 eager PyTorch; its arithmetic lives in torch, which is
 un-pinned by the reference - requirements.txt:9).  Each function cites the
 reference file:line it restates.  Gradients come from autograd over these
@@ -252,10 +253,10 @@ def sample_pdf(bins, weights, N_samples, det=False, u=None):
     cdf = pdf_to_cdf(weights)
     if u is None:
         if det:
-            u = torch.linspace(0.0, 1.0, N_samples, dtype=F32)         # ray.py:118
+            u = torch.linspace(0.0, 1.0, N_samples, dtype=F32, device=cdf.device)   # ray.py:118
             u = u.expand(list(cdf.shape[:-1]) + [N_samples])
         else:
-            u = torch.rand(list(cdf.shape[:-1]) + [N_samples], dtype=F32)   # ray.py:121
+            u = torch.rand(list(cdf.shape[:-1]) + [N_samples], dtype=F32, device=cdf.device)   # ray.py:121
     samples, _ = sample_from_cdf(bins, cdf, u)
     return samples
 
@@ -264,7 +265,7 @@ def sample_pdf(bins, weights, N_samples, det=False, u=None):
 # a2 / a3  stratified sampling and point generation  reference: nerf/run.py:361-385
 # ----------------------------------------------------------------------------
 def stratified_z(near, far, N_samples, lindisp=False, perturb=0.0, t_rand=None):
-    t = torch.linspace(0.0, 1.0, N_samples, dtype=F32)                 # run.py:361
+    t = torch.linspace(0.0, 1.0, N_samples, dtype=F32, device=near.device)   # run.py:361
     if not lindisp:
         z = near * (1.0 - t) + far * t                                 # run.py:363
     else:
@@ -275,7 +276,7 @@ def stratified_z(near, far, N_samples, lindisp=False, perturb=0.0, t_rand=None):
         upper = torch.cat([mids, z[..., -1:]], -1)
         lower = torch.cat([z[..., :1], mids], -1)
         if t_rand is None:
-            t_rand = torch.rand(z.shape, dtype=F32)                    # run.py:375
+            t_rand = torch.rand(z.shape, dtype=F32, device=z.device)   # run.py:375
         z = lower + (upper - lower) * t_rand                           # run.py:383
     return z
 
@@ -343,7 +344,7 @@ def run_network_dnerf(p, pts, viewdirs, frame_time: float, L_pos, L_time, L_dir,
                       zero_canonical=True, **kw):
     flat = pts.reshape(-1, 3)
     emb = embed(flat, L_pos)                                            # run_dnerf.py:57-58
-    t = torch.full((flat.shape[0], 1), float(frame_time), dtype=F32)    # run_dnerf.py:62-64
+    t = torch.full((flat.shape[0], 1), float(frame_time), dtype=F32, device=flat.device)    # run_dnerf.py:62-64
     emb_t = embed(t, L_time)                                            # run_dnerf.py:65
     ch, chv = emb.shape[-1], 0
     if viewdirs is not None:
@@ -435,7 +436,7 @@ def run_network_tnerf(p, pts, viewdirs, frame_time: float, L_pos=10, L_time=10, 
     """run_tnerf.py:45-86."""
     flat = pts.reshape(-1, 3)
     emb = embed(flat, L_pos)                                            # :56-57
-    t = torch.full((flat.shape[0], 1), float(frame_time), dtype=F32)    # :61-63
+    t = torch.full((flat.shape[0], 1), float(frame_time), dtype=F32, device=flat.device)    # :61-63
     emb_t = embed(t, L_time)                                            # :64
     dirs = viewdirs[:, None].expand(pts.shape).reshape(-1, 3)
     ed = embed(dirs, L_dir)                                             # :70-73

@@ -11,7 +11,7 @@ from . import ops, embedder, model, ray, render, tc  # noqa: F401
 from .embedder import get_embedder, Embedder  # noqa: F401
 from .model import vallina_NeRF, NeRFOriginal, DirectTemporalNeRF, NeRF, TNeRF  # noqa: F401
 from .ray import sample_pdf, raw2outputs, get_rays, get_rays_np, ndc_rays  # noqa: F401
-from .render import batchify, run_network, batchify_rays, render_rays, create_nerf, render, NetworkQuery  # noqa: F401
+from .render import batchify, run_network, batchify_rays, render_rays, create_nerf, render, render_path, NetworkQuery  # noqa: F401
 from .ops import searchsorted  # noqa: F401
 
 __version__ = "0.1.0"

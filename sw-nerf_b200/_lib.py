@@ -51,7 +51,10 @@ _SIG = {
     "swnerf_tc_pack_weights_time_t": [_VP, _VP, _VP, _VP],
     "swnerf_tc_time_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
     "swnerf_tc_time_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
-    "swnerf_make_rays": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I64, _F32, _F32, _F32, _I32, _I32, _VP, _I32, _VP],
+    "swnerf_make_rays": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I64, _F32, _F32, _F32, _I32, _I32, _I32, _F32,
+                         ctypes.c_double, _VP, _I32, _VP],
+    "swnerf_pick_batch": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I32, _I32, _I32, _I32, ctypes.c_uint64, _I64, _F32,
+                          _F32, _F32, _I32, _I32, _I32, _F32, ctypes.c_double, _VP, _I32, _VP, _VP, _VP],
     "swnerf_adam_flat": [_VP, _VP, _VP, _VP, _I64, _F32, _F32, _F32, _F32, _I64, _VP],
     "swnerf_mse2": [_VP, _VP, _VP, _I64, _F32, _VP, _VP, _VP, _VP],
     "swnerf_tc_set_profiling": [_I32],

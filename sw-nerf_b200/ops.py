@@ -180,6 +180,8 @@ def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples
     z_fine = torch.empty((N, S + n_importance), dtype=F32, device=dev)
     z_std = torch.empty((N,), dtype=F32, device=dev)
     if exact and S <= 512:
+        if det:     # the reference's u on its CPU path: torch.linspace's vectorised kernel (ray.py:118), not the closed form
+            u, det = _ref_linspace(n_importance, dev).expand(N, n_importance).contiguous(), False
         call("swnerf_resample_check", ptr(z_vals, F32, "z_vals"), ptr(weights, F32, "weights"), None,
              None if det else ptr(u, F32, "u"), int(bool(det)), N, S, n_importance, 1, REF_SUM_LANES,
              z_samples.data_ptr() if want_samples else None, z_fine.data_ptr(), z_std.data_ptr(), None, None, stream())
@@ -190,11 +192,25 @@ def resample(z_vals, weights, n_importance: int, det=False, u=None, want_samples
     return z_samples, z_fine, z_std
 
 
+_LINSPACE = {}
+
+
+def _ref_linspace(n, dev):
+    """torch.linspace(0, 1, n) as the reference's CPU path produces it (ray.py:118): ATen's vectorised kernel evaluates
+    base + k * step per SIMD block, one ulp off the closed form the device kernels (and torch's CUDA linspace) use."""
+    key = (n, str(dev))
+    if key not in _LINSPACE:
+        _LINSPACE[key] = torch.linspace(0.0, 1.0, n, dtype=F32).to(dev)
+    return _LINSPACE[key]
+
+
 def resample_check(z_vals, weights, n_importance: int, det=False, u=None, cdf=None, variant=0, ref_lanes=REF_SUM_LANES):
     """Test entry (swnerf_resample_check): returns dict(z_samples, z_fine, z_std, inds, cdf).  `cdf` [N, S-1]
     replaces the cdf built from the weights; `inds` are torch.searchsorted(cdf, sort(u), right=True)."""
     N, S = z_vals.shape
     dev = z_vals.device
+    if det and variant == 1:
+        u, det = _ref_linspace(n_importance, dev).expand(N, n_importance).contiguous(), False
     out = dict(z_samples=torch.empty((N, n_importance), dtype=F32, device=dev),
                z_fine=torch.empty((N, S + n_importance), dtype=F32, device=dev),
                z_std=torch.empty((N,), dtype=F32, device=dev),

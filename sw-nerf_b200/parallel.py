@@ -159,6 +159,22 @@ class _TwoLossMSE(torch.autograd.Function):
         return da, db, None, None
 
 
+def two_loss_mse_grads(rgb, rgb0, target, n_global=None):
+    """The same kernel without the autograd wrapper: (loss, d loss / d rgb, d loss / d rgb0).  For callers that run the
+    two losses' backward passes separately - torch.autograd.backward([rgb], [da]) then ([rgb0], [db]) - e.g. to
+    all-reduce the fine network's gradients while the coarse network's backward is still running (bench.py)."""
+    if n_global is None:
+        n_global = rgb.shape[0]
+    a, t = rgb.detach().contiguous(), target.contiguous()
+    b = None if rgb0 is None else rgb0.detach().contiguous()
+    da = torch.empty_like(a)
+    db = None if b is None else torch.empty_like(b)
+    loss = torch.empty((), dtype=torch.float32, device=a.device)
+    call("swnerf_mse2", _lib.ptr(a), None if b is None else _lib.ptr(b), _lib.ptr(t), a.numel(),
+         1.0 / float(n_global * a.shape[-1]), da.data_ptr(), None if db is None else db.data_ptr(), loss.data_ptr(), stream())
+    return loss, da, db
+
+
 def two_loss_mse(rgb, rgb0, target, n_global=None):
     """img2mse(rgb, target) + img2mse(rgb0, target) (nerf/run.py:689-697) in one kernel; n_global = number of
     rays of the WHOLE step when the batch is sharded over ranks (defaults to the local count)."""
@@ -195,3 +211,95 @@ def render_frame_sharded(H, W, K, c2w, near, far, chunk, render_rays_fn, group=N
         maps.append(gather_rows(local, n, group))
     rgb, disp, acc = maps
     return rgb.reshape(H, W, 3), disp.reshape(H, W), acc.reshape(H, W)
+
+
+class _HostFrames:
+    """Double-buffered device->host copies of rendered frames: frame i is copied on a side stream into one of two
+    pinned buffers while frame i+1 renders; the host only waits for a buffer when it needs it again (the reference
+    synchronises on every frame: rgb.cpu().numpy(), nerf/run.py:199-200)."""
+
+    def __init__(self, shapes, device):
+        self.stream = torch.cuda.Stream(device=device)
+        self.bufs = [[torch.empty(s, dtype=torch.float32).pin_memory() for s in shapes] for _ in range(2)]
+        self.events = [None, None]
+        self.pending = [None, None]          # (frame index, callback) waiting in buffer k
+        self.i = 0
+
+    def _drain(self, k, sink):
+        if self.pending[k] is not None:
+            self.events[k].synchronize()
+            sink(self.pending[k], [b.numpy().copy() for b in self.bufs[k]])
+            self.pending[k] = None
+
+    def push(self, idx, tensors, sink):
+        k = self.i & 1
+        self._drain(k, sink)
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            for b, t in zip(self.bufs[k], tensors):
+                b.copy_(t, non_blocking=True)
+                t.record_stream(self.stream)
+            ev = torch.cuda.Event()
+            ev.record(self.stream)
+        self.events[k], self.pending[k] = ev, idx
+        self.i += 1
+
+    def finish(self, sink):
+        for k in ((self.i & 1), (self.i & 1) ^ 1):
+            self._drain(k, sink)
+
+
+def render_path(render_poses, hwf, K, chunk, render_kwargs, gt_imgs=None, savedir=None, render_factor=0, near=None,
+                far=None, group=None, on_frame=None):
+    """nerf/run.py:172-219 -> (rgbs [F,H,W,3], disps [F,H,W]) as numpy arrays.
+
+    Same arguments and return value as the reference; near / far come from render_kwargs like there (train() puts them
+    in, nerf/run.py:577-579) or from the keywords.  What differs is how: every frame's rays are built by the ray assembly
+    kernel and rendered in `chunk`-ray slabs, the rays of a frame are SHARDED over the ranks of `group` and the maps
+    all-gathered (every rank returns the full frames; only rank 0 copies them to the host unless on_frame is given),
+    and the device->host copies are double-buffered on a side stream instead of a blocking .cpu() per frame.
+    `on_frame(i, rgb_np, disp_np)` is called as soon as frame i has landed in host memory (the reference writes its PNG
+    there); savedir needs imageio, which the caller's environment must provide."""
+    from .render import render_rays
+    import numpy as np
+    H, W, focal = hwf
+    if render_factor != 0:                                   # nerf/run.py:185-189
+        H, W, focal = H // render_factor, W // render_factor, focal / render_factor
+    kw = {k: v for k, v in render_kwargs.items() if k not in ("near", "far", "use_viewdirs", "ndc")}
+    near = render_kwargs.get("near", near)
+    far = render_kwargs.get("far", far)
+    if near is None or far is None:
+        raise ValueError("render_path: near / far must be in render_kwargs (nerf/run.py:577-579) or passed as keywords")
+    if render_kwargs.get("ndc", False):
+        raise NotImplementedError("render_path: the sharded frame loop renders non-NDC rays; use render() for LLFF/NDC")
+    world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    rank = dist.get_rank(group) if world > 1 else 0
+    dev = torch.device("cuda", torch.cuda.current_device())
+    writer = None
+    if savedir is not None:
+        import imageio                                           # noqa: F401  (I/O dependency of the caller, as in the reference)
+        import os
+        from .ray import to8b
+        writer = lambda i, rgb: imageio.imwrite(os.path.join(savedir, "{:03d}.png".format(i)), to8b(rgb))
+    to_host = rank == 0 or on_frame is not None
+    frames = {}
+
+    def sink(i, arrays):
+        frames[i] = arrays
+        if on_frame is not None:
+            on_frame(i, arrays[0], arrays[1])
+        if writer is not None and rank == 0:
+            writer(i, arrays[0])
+    host = _HostFrames([(H, W, 3), (H, W)], dev) if to_host else None
+    n = 0
+    with torch.no_grad():
+        for i, c2w in enumerate(render_poses):
+            c2w = torch.as_tensor(c2w)[:3, :4]
+            rgb, disp, acc = render_frame_sharded(H, W, K, c2w, float(near), float(far), chunk, render_rays, group=group, **kw)
+            if host is not None:
+                host.push(i, [rgb, disp], sink)
+            n += 1
+    if host is not None:
+        host.finish(sink)
+        return np.stack([frames[i][0] for i in range(n)], 0), np.stack([frames[i][1] for i in range(n)], 0)
+    return None, None

@@ -30,21 +30,27 @@ def get_rays(H, W, focal_or_K, c2w):
     return rays_o, rays_d
 
 
-def make_ray_batch(H, W, focal_or_K, c2w, near, far, pixels=None, frame_time=None, use_viewdirs=True, device=None):
-    """Flat ray batch straight from the camera (SURVEY.md 8f row f1): what get_rays (ray.py:10-38) plus the
-    viewdir normalisation / near-far / concatenation of render() (nerf/run.py:137-158) build with a dozen
-    eager ops, as ONE kernel.  `pixels`: int64 tensor of flat pixel ids j*W + i (None = the whole frame)."""
-    if device is None:
-        device = pixels.device if pixels is not None else (c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda
-                                                           else torch.device("cuda"))
-    if isinstance(focal_or_K, float):
+def _camera(H, W, focal_or_K, c2w):
+    import ctypes
+    if isinstance(focal_or_K, (float, int)):
         fx = fy = float(focal_or_K); cx, cy = W * 0.5, H * 0.5
     else:
         K = focal_or_K
         fx, fy, cx, cy = float(K[0][0]), float(K[1][1]), float(K[0][2]), float(K[1][2])
-    import ctypes
     m = torch.as_tensor(c2w, dtype=torch.float32).detach().cpu()[:3, :4].contiguous()
-    c2w12 = (ctypes.c_float * 12)(*m.reshape(-1).tolist())
+    return fx, fy, cx, cy, (ctypes.c_float * 12)(*m.reshape(-1).tolist())
+
+
+def make_ray_batch(H, W, focal_or_K, c2w, near, far, pixels=None, frame_time=None, use_viewdirs=True, device=None,
+                   ndc=False, ndc_near=1.):
+    """Flat ray batch straight from the camera (SURVEY.md 8f row f1): what get_rays (ray.py:10-38) plus the
+    viewdir normalisation / NDC warp / near-far / concatenation of render() (nerf/run.py:137-158) build with a dozen
+    eager ops, as ONE kernel.  `pixels`: int64 tensor of flat pixel ids j*W + i (None = the whole frame).
+    ndc=True applies ndc_rays(H, W, K[0][0], ndc_near, o, d) (ray.py:75-92) like render() does for the LLFF configs."""
+    if device is None:
+        device = pixels.device if pixels is not None else (c2w.device if isinstance(c2w, torch.Tensor) and c2w.is_cuda
+                                                           else torch.device("cuda"))
+    fx, fy, cx, cy, c2w12 = _camera(H, W, focal_or_K, c2w)
     n = H * W if pixels is None else pixels.numel()
     stride = 8 + (1 if frame_time is not None else 0) + (3 if use_viewdirs else 0)
     rays = torch.empty((n, stride), dtype=torch.float32, device=device)
@@ -52,8 +58,36 @@ def make_ray_batch(H, W, focal_or_K, c2w, near, far, pixels=None, frame_time=Non
     call("swnerf_make_rays", H, W, fx, fy, cx, cy, c2w12,
          None if pixels is None else ptr(pixels.reshape(-1), torch.int64, "pixels"), n, float(near), float(far),
          0.0 if frame_time is None else float(frame_time), int(frame_time is not None), int(use_viewdirs),
-         rays.data_ptr(), stride, stream())
+         int(bool(ndc)), float(ndc_near), float(fx), rays.data_ptr(), stride, stream())
     return rays
+
+
+def pick_batch(H, W, focal_or_K, c2w, image, N_rand, seed, near, far, precrop_frac=None, frame_time=None,
+               use_viewdirs=True, ndc=False, ndc_near=1., return_pixels=False):
+    """The per-step training batch of nerf/run.py:652-681 in ONE kernel: N_rand distinct random
+    pixels of `image` [H, W, 3] (a CUDA tensor) - inside the centre crop of half-size H//2 * precrop_frac when
+    `precrop_frac` is given (run.py:660-668) - as (ray_batch [N_rand, 8|9|11|12], target_s [N_rand, 3]).
+    `seed`: any integer, e.g. the global step; equal seeds give equal batches (the reference uses numpy's global RNG)."""
+    if not (isinstance(image, torch.Tensor) and image.is_cuda):
+        raise RuntimeError("swnerf_b200: pick_batch needs the target image on the GPU - this library has no CPU path")
+    if precrop_frac is not None:
+        dH, dW = int(H // 2 * precrop_frac), int(W // 2 * precrop_frac)
+        y0, x0, ch, cw = H // 2 - dH, W // 2 - dW, 2 * dH, 2 * dW
+    else:
+        y0, x0, ch, cw = 0, 0, H, W
+    fx, fy, cx, cy, c2w12 = _camera(H, W, focal_or_K, c2w)
+    img = image.reshape(H * W, -1)[:, :3].float().contiguous()
+    stride = 8 + (1 if frame_time is not None else 0) + (3 if use_viewdirs else 0)
+    rays = torch.empty((N_rand, stride), dtype=torch.float32, device=image.device)
+    target = torch.empty((N_rand, 3), dtype=torch.float32, device=image.device)
+    pix = torch.empty((N_rand,), dtype=torch.int64, device=image.device) if return_pixels else None
+    from ._lib import call, stream
+    call("swnerf_pick_batch", H, W, fx, fy, cx, cy, c2w12, img.data_ptr(), y0, x0, ch, cw,
+         int(seed) & 0xFFFFFFFFFFFFFFFF, N_rand, float(near), float(far),
+         0.0 if frame_time is None else float(frame_time), int(frame_time is not None), int(use_viewdirs),
+         int(bool(ndc)), float(ndc_near), float(fx), rays.data_ptr(), stride, target.data_ptr(),
+         None if pix is None else pix.data_ptr(), stream())
+    return (rays, target, pix) if return_pixels else (rays, target)
 
 
 def get_rays_np(H, W, focal_or_K, c2w):
@@ -113,7 +147,7 @@ def raw_noise(shape, raw_noise_std, device, pytest=False):
 
 def raw2outputs(raw, z_vals, rays_d, raw_noise_std=0, white_bkgd=False, pytest=False):
     """ray.py:155-198 -> (rgb_map, disp_map, acc_map, weights, depth_map)."""
-    noise = raw_noise(raw[..., 3].shape, raw_noise_std, raw.device, pytest)
+    noise = raw_noise(tuple(raw.shape[:-1]), raw_noise_std, raw.device, pytest)
     rd = rays_d if rays_d.is_contiguous() else rays_d.contiguous()
     z = z_vals if z_vals.is_contiguous() else z_vals.contiguous()
     return ops.composite(raw, z, rd, 0, noise, white_bkgd)

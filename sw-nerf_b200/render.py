@@ -13,6 +13,7 @@ from . import ops, tc
 from .embedder import get_embedder
 from .model import vallina_NeRF as NeRF
 from .ray import get_rays, ndc_rays, raw_noise, pytest_uniform, make_ray_batch
+from .parallel import render_path  # noqa: F401  (nerf/run.py:172-219, ray-sharded; defined next to the other DP code)
 
 DEBUG = False
 
@@ -120,10 +121,11 @@ def batchify_rays(rays_flat, chunk=1024 * 32, **kwargs):
 def render(H, W, K, chunk=1024 * 32, rays=None, c2w=None, ndc=True, near=0., far=1., use_viewdirs=False,
            c2w_staticcam=None, **kwargs):
     """nerf/run.py:105-170."""
-    if (c2w is not None and not ndc and c2w_staticcam is None and use_viewdirs and torch.cuda.is_available()
+    if (c2w is not None and c2w_staticcam is None and torch.cuda.is_available()
             and not torch.is_tensor(near) and not torch.is_tensor(far)):
-        # full-frame fast path: the whole ray assembly below is one kernel (same values, tests/test_gpu_next_rows.py)
-        rays = make_ray_batch(H, W, K, c2w, near, far, use_viewdirs=True)
+        # full-frame fast path: the whole ray assembly below (NDC warp included) is one kernel (same values,
+        # tests/test_gpu_next_rows.py)
+        rays = make_ray_batch(H, W, K, c2w, near, far, use_viewdirs=bool(use_viewdirs), ndc=bool(ndc))
         all_ret = batchify_rays(rays, chunk, **kwargs)
         for k in all_ret:
             all_ret[k] = torch.reshape(all_ret[k], [H, W] + list(all_ret[k].shape[1:]))

@@ -236,6 +236,14 @@ int swnerf_mse2(const float* a, const float* b, const float* target, int64_t n, 
  * bit-identical outputs (tests/test_gpu_render.py::test_cta_pair_forward_variant_matches_default). */
 int swnerf_tc_set_fwd_variant(int variant);
 
+/* Selects the backward of swnerf_tc_mlp_bwd (process-wide): -1 / 0 (default) = the two-kernel backward (data gradients,
+ * then weight gradients over the dy images in HBM); 1 = the layer-pipelined kernel for launches of more than two tiles
+ * per SM: one persistent kernel whose CTAs each own one layer's data- or weight-gradient role, the dy images travelling
+ * between them through an L2-resident ring, so only the saved activations are read from HBM (3x less DRAM traffic;
+ * not yet faster: profiles/r2_lw_backward.md).  Both produce the same gradients up to the accumulation order
+ * (tests/test_gpu_render.py::test_layer_pipelined_backward_matches_two_kernel_backward). */
+int swnerf_tc_set_bwd_variant(int variant);
+
 /* Per-kernel device timing of the last swnerf_tc_mlp_bwd on this thread (bench.py's roofline): when
  * profiling is on, CUDA events are recorded on the launching stream around the data-gradient and the
  * weight-gradient kernels; swnerf_tc_last_bwd_ms synchronises on them. */

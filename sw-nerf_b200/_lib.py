@@ -62,6 +62,7 @@ _SIG = {
     "swnerf_tc_selftest": [_I32, _VP, _VP, _VP, _I32, _I32, _VP, _VP],
     "swnerf_tc_probe": [_I32, _I32, _I32, _VP, _VP],
     "swnerf_tc_set_fwd_variant": [_I32],
+    "swnerf_tc_set_bwd_variant": [_I32],
     "swnerf_set_resample_variant": [_I32],
     "swnerf_resample_fallbacks": [_VP, _I32, _VP],
     "swnerf_tc_selftest_pair": [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP],

@@ -41,7 +41,8 @@ def _deps_mtime():
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+    extra = os.environ.get("SWNERF_NVCC_EXTRA", "").split()        # e.g. -DSWNERF_LW_DEBUG / -DSWNERF_EXPERIMENTS (tools only)
+    cmd = [NVCC] + FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

@@ -52,6 +52,38 @@ int encode_u8_tensor_map(void* map, const void* base, int ndim, const unsigned l
   return SWNERF_OK;
 }
 
+int const_slot_acquire(int family, int nslots, cudaStream_t s) {
+  constexpr int kMaxDev = 64, kFam = 2, kSlots = 8;
+  struct Slot { cudaStream_t owner; bool used; unsigned long long stamp; };
+  static std::mutex mu;
+  static Slot slots[kFam][kMaxDev][kSlots] = {};
+  static cudaEvent_t ev[kMaxDev] = {};
+  static unsigned long long clock_ = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev || family < 0 || family >= kFam || nslots > kSlots) return -1;
+  std::lock_guard<std::mutex> lock(mu);
+  Slot* sl = slots[family][dev];
+  int k = -1;
+  for (int i = 0; i < nslots; ++i) if (sl[i].used && sl[i].owner == s) k = i;
+  if (k < 0) {
+    for (int i = 0; i < nslots; ++i) if (!sl[i].used) { k = i; break; }
+    if (k < 0) {
+      k = 0;
+      for (int i = 1; i < nslots; ++i) if (sl[i].stamp < sl[k].stamp) k = i;
+      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+      cudaStreamIsCapturing(s, &cap);
+      if (cap == cudaStreamCaptureStatusNone) {
+        if (!ev[dev]) cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming);
+        cudaEventRecord(ev[dev], sl[k].owner);
+        cudaStreamWaitEvent(s, ev[dev], 0);
+      }
+    }
+    sl[k].owner = s; sl[k].used = true;
+  }
+  sl[k].stamp = ++clock_;
+  return k;
+}
+
 bool once_per_device(int id) {
   constexpr int kMaxDev = 64;
   static std::mutex mu;

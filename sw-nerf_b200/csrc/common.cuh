@@ -19,12 +19,20 @@ int set_err(int code, const char* fmt, ...);
 int check_launch(const char* what);
 int sm_count();
 
+// Rotating copies of a per-network parameter block in constant memory (per device and per `family` of kernels).  A
+// stream keeps the slot it used last (stream order makes re-staging safe); a stream without one takes the least
+// recently assigned slot and first waits (event) for the work of the stream that owned it, so launches on different
+// streams (coarse and fine network, or two callers) never share a block.  Returns the slot, or -1 without a device.
+// (While a stream is being captured into a CUDA graph no cross-stream wait is inserted: captures use one stream.)
+int const_slot_acquire(int family, int nslots, cudaStream_t s);
+constexpr int CONST_FAMILY_FWD_F32 = 0, CONST_FAMILY_BWD_WRGB = 1;
+
 // One-time, PER-DEVICE setup (cudaFuncSetAttribute opt-ins, __constant__ uploads): true exactly once for each
 // (id, current device) pair, whatever thread asks; callers run their setup when it returns true.  Ids below.
 bool once_per_device(int id);
 enum OnceId {
   ONCE_FWD4 = 0, ONCE_FWD1_TRAIN, ONCE_FWD1_INFER, ONCE_BWD_BASE, ONCE_BWD_DATA_PAIR, ONCE_BWD_WEIGHT_PAIR,
-  ONCE_HGEMM, ONCE_HGEMM_WGRAD, ONCE_RESAMPLE64Q, ONCE_RESAMPLE64Q_CHECK, ONCE_FWDX, ONCE_BWDX, ONCE_COUNT
+  ONCE_HGEMM, ONCE_HGEMM_WGRAD, ONCE_RESAMPLE64Q, ONCE_RESAMPLE64Q_CHECK, ONCE_FWDX, ONCE_BWDX, ONCE_BWD_LW, ONCE_COUNT
 };
 
 // u8 tensor map (1..3 dims, no swizzle / interleave) through the driver entry point fetched at run time, so the

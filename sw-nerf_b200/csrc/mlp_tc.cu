@@ -990,39 +990,10 @@ static int weight_tensor_maps(const void* packed, CUtensorMap* trunk, CUtensorMa
   return SWNERF_OK;
 }
 
-// Copies a network's fp32 block into one of the constant-memory slots on the launching stream and returns the slot.
-// A stream reuses the slot it used last (stream order makes that safe); a stream without one takes the least recently
-// assigned slot and first waits (event) for the work of the stream that owned it.  Bookkeeping is per device.
-// (While a stream is being captured into a CUDA graph no cross-stream wait is inserted: captures use one stream.)
+// Copies a network's fp32 block into one of the constant-memory slots on the launching stream (const_slot_acquire).
 static int stage_f32_block(const uint8_t* src, cudaStream_t s, int* slot_out) {
-  constexpr int kMaxDev = 64;
-  struct Slot { cudaStream_t owner; bool used; unsigned long long stamp; };
-  static std::mutex mu;
-  static Slot slots[kMaxDev][F32_SLOTS] = {};
-  static cudaEvent_t ev[kMaxDev] = {};
-  static unsigned long long clock_ = 0;
-  int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: no current device");
-  std::lock_guard<std::mutex> lock(mu);
-  Slot* sl = slots[dev];
-  int k = -1;
-  for (int i = 0; i < F32_SLOTS; ++i) if (sl[i].used && sl[i].owner == s) k = i;
-  if (k < 0) {
-    for (int i = 0; i < F32_SLOTS; ++i) if (!sl[i].used) { k = i; break; }
-    if (k < 0) {
-      k = 0;
-      for (int i = 1; i < F32_SLOTS; ++i) if (sl[i].stamp < sl[k].stamp) k = i;
-      cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-      cudaStreamIsCapturing(s, &cap);
-      if (cap == cudaStreamCaptureStatusNone) {
-        if (!ev[dev]) cudaEventCreateWithFlags(&ev[dev], cudaEventDisableTiming);
-        cudaEventRecord(ev[dev], sl[k].owner);
-        cudaStreamWaitEvent(s, ev[dev], 0);
-      }
-    }
-    sl[k].owner = s; sl[k].used = true;
-  }
-  sl[k].stamp = ++clock_;
+  const int k = const_slot_acquire(CONST_FAMILY_FWD_F32, F32_SLOTS, s);
+  if (k < 0) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: no current device");
   cudaError_t e = cudaMemcpyToSymbolAsync(c_f32s, src, F32_COUNT * sizeof(float), (size_t)k * F32_PAD * sizeof(float),
                                           cudaMemcpyDeviceToDevice, s);
   if (e != cudaSuccess) return set_err(SWNERF_ERR_CUDA, "tc_mlp_fwd: staging the bias block failed: %s", cudaGetErrorString(e));

@@ -16,6 +16,8 @@
 // unscaled in the fp32 flush.
 #include <cuda.h>
 #include <mutex>
+#include <cstdlib>
+#include <atomic>
 #include "common.cuh"
 #include "tc_common.cuh"
 #include "mlp_tc_layout.cuh"
@@ -624,7 +626,8 @@ struct WgArgs {
   int job_first_cta[WG_JOBS + 1];
   int kind;
 };
-__constant__ WgJob c_jobs[2][WG_JOBS];       // [kind]
+constexpr int WG_JOBS_ALL = WG_JOBS + 2;     // + the two halves of job 0 as separate jobs (layer-pipelined kernel)
+__constant__ WgJob c_jobs[2][WG_JOBS_ALL];   // [kind]
 
 constexpr int HALF_BLK = 64 * 128;     // 64 samples of one 64-column block
 
@@ -1070,6 +1073,584 @@ __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
   if (warp == 5) tmem_dealloc<64>(tmem);
 }
 
+// ------------------------------------------------------------------------------------------------
+// 5. Layer-pipelined backward ("LW"): dy never reaches HBM
+//
+// The two-kernel backward above is HBM-bound by construction: the data-gradient kernel writes every dy_l image
+// (4.5 KB / sample) and the weight-gradient kernels read them back next to the saved activations (9.7 KB / sample).
+// Here ONE persistent kernel runs both as a pipeline of layer workers.  Every CTA owns one role for its whole life:
+//     D(H), D(7) .. D(1)   data gradient through ONE layer: dy_l -> dy_{l-1} = (dy_l W_l) * relu'(layer l-1), with
+//                          the layer's transposed weights RESIDENT in shared memory (no weight streaming at all)
+//     W(H), W(7) .. W(0)   weight / bias gradient of ONE layer group, accumulated in tensor memory over ALL of the
+//                          role's tiles (the jobs of mlp_bwd_weight_kernel), one red.add flush at the end
+// A tile's dy_l image travels from D(l+1) to its two consumers D(l) and W(l) through a small ring of 64-KB slots in
+// global memory (9 rings x 32 slots = 19 MB, rewritten continuously, so it lives in the 126 MB L2) guarded by two
+// words per slot: `ready` (tile index + 1, st.release by the producer after its stores) and `done` (a running count
+// of consumers that have pulled the slot into shared memory).  Only the saved forward activations are read from HBM
+// (4.7 KB / sample).  CTAs of a role take tiles round-robin (tile = j, j + P, ...), every role walks its tiles in
+// increasing order and all CTAs are co-resident (grid <= SM count), so the pipeline cannot deadlock: the smallest
+// unproduced tile of any ring always has a free slot once its predecessors were consumed, and the last stage (the W
+// roles) has no output ring.
+// ------------------------------------------------------------------------------------------------
+constexpr int LW_ROLES = 18;         // 0: D(H) | 1..7: D(7)..D(1) | 8: W(H) (job 8) | 9..15: W(7)..W(1) (jobs 7..1) | 16: W(0) (job 9) | 17: W(5,PE) (job 10)
+constexpr int LW_RINGS = 9;          // 0: dyH | 1 + (7 - l): dy_l, l = 7..0
+constexpr int LW_R = 32;             // slots per ring
+constexpr int LW_IN_BLKS = 6;        // D roles: input ring of 16-KB blocks in shared memory
+constexpr int64_t LW_RING_BYTES = (int64_t)LW_RINGS * LW_R * ACT_BYTES;
+constexpr int LW_FLAG_WORDS = 2 * LW_RINGS * LW_R;
+constexpr int LW_FLAGS_OFF = 200 * 1024;            // inside the workspace tail (WS_TAIL_BYTES = 256 KB)
+static_assert(256 + UNFOLD_FLOATS * 4 <= LW_FLAGS_OFF && LW_FLAGS_OFF + LW_FLAG_WORDS * 4 <= WS_TAIL_BYTES, "workspace tail layout");
+
+struct LwArgs {
+  const float* d_raw; int64_t P; int64_t num_tiles;
+  const uint8_t* packed; const uint8_t* packed_t;
+  uint8_t* ws;                 // forward workspace: saved activation images and sign masks
+  uint8_t* ring;               // [LW_RINGS][LW_R] slots of 64 KB (lives in the dy region of the workspace)
+  uint32_t* flags;             // ready[LW_RINGS][LW_R] | done[LW_RINGS][LW_R], zeroed before the launch
+  float* grads[24]; float* unfold;
+  const uint32_t* absmax; float fixed_scale;
+  int role_first[LW_ROLES + 1];
+  int wrgb_slot;               // which copy of rgb_linear.weight in constant memory (c_wrgb)
+  unsigned long long* dbg;     // -DSWNERF_LW_DEBUG builds: 12 cycle counters per CTA (tools/lw_profile.py), else unused
+};
+#ifdef SWNERF_LW_DEBUG
+#define LW_T0() const long long lw_t0_ = clock64()
+#define LW_ACC(slot) do { if (g.dbg) atomicAdd(g.dbg + (size_t)blockIdx.x * 12 + (slot), (unsigned long long)(clock64() - lw_t0_)); } while (0)
+#else
+#define LW_T0() do {} while (0)
+#define LW_ACC(slot) do {} while (0)
+#endif
+
+__device__ __forceinline__ int lw_ring_of_layer(int l) { return 1 + (7 - l); }            // dy_l
+__device__ __forceinline__ int lw_ring_consumers(int ring) { return (ring == 0 || ring == 8) ? 1 : (ring == 3 ? 3 : 2); }
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_gpu_add(uint32_t* p, uint32_t v) {
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+// the producer of tile t has published slot t % LW_R of `ring`
+__device__ __forceinline__ void lw_wait_ready(const LwArgs& g, int ring, int64_t t) {
+  const uint32_t* f = g.flags + ring * LW_R + (int)(t % LW_R);
+  while (ld_acquire_gpu(f) != (uint32_t)(t + 1)) __nanosleep(40);
+}
+// every consumer of the slot's previous occupant (tile t - LW_R) has pulled it out
+__device__ __forceinline__ void lw_wait_free(const LwArgs& g, int ring, int64_t t) {
+  if (t < LW_R) return;
+  const uint32_t* f = g.flags + (LW_RINGS + ring) * LW_R + (int)(t % LW_R);
+  const uint32_t need = (uint32_t)(lw_ring_consumers(ring) * (t / LW_R));
+  while (ld_acquire_gpu(f) < need) __nanosleep(40);
+}
+__device__ __forceinline__ void lw_mark_done(const LwArgs& g, int ring, int64_t t) {
+  red_release_gpu_add(g.flags + (LW_RINGS + ring) * LW_R + (int)(t % LW_R), 1u);
+}
+__device__ __forceinline__ uint8_t* lw_slot(const LwArgs& g, int ring, int64_t t) {
+  return g.ring + ((int64_t)ring * LW_R + (t % LW_R)) * ACT_BYTES;
+}
+
+// rgb_linear.weight [3][128] of the network whose backward is running, one slot per stream (const_slot_acquire):
+// every access is warp-uniform, so the values are FFMA operands straight from the constant bank.
+constexpr int WRGB_SLOTS = 4;
+__constant__ float c_wrgb[WRGB_SLOTS][384];
+
+__device__ __forceinline__ void bulk_wait_group1() { asm volatile("cp.async.bulk.wait_group 1;" ::: "memory"); }
+// publish slot t % LW_R of `ring` after the bulk stores that filled it have completed
+__device__ __forceinline__ void lw_publish(const LwArgs& g, int ring, int64_t t) {
+  fence_proxy_async_all();
+  __threadfence();
+  st_release_gpu(g.flags + ring * LW_R + (int)(t % LW_R), (uint32_t)(t + 1));
+}
+
+__global__ void __launch_bounds__(384, 1) mlp_bwd_lw_kernel(const __grid_constant__ LwArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bars[32];
+  __shared__ uint32_t tmem_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int role = 0;
+  while (role + 1 < LW_ROLES && (int)blockIdx.x >= g.role_first[role + 1]) ++role;
+  const int P = g.role_first[role + 1] - g.role_first[role];
+  const int j = blockIdx.x - g.role_first[role];
+  const int64_t my_tiles = ((int64_t)j < g.num_tiles) ? (g.num_tiles - j + P - 1) / P : 0;
+  const int64_t mask_base = g.num_tiles * WS_TILE_BYTES;
+  const uint32_t* mask0 = reinterpret_cast<const uint32_t*>(g.ws + mask_base);
+#ifdef SWNERF_LW_DEBUG
+  const long long lw_start = clock64();
+  if (threadIdx.x == 0 && g.dbg) { g.dbg[(size_t)blockIdx.x * 12 + 6] = (unsigned long long)my_tiles; g.dbg[(size_t)blockIdx.x * 12 + 7] = (unsigned long long)role; }
+#endif
+
+  if (role <= 7) {
+    // =========================================================================================== D roles
+    // D(l): the layer's transposed weights are RESIDENT in shared memory (4 chunks, 128 KB: no weight streaming); the
+    // tiles' dy_l images arrive block by block (16 KB = one K-chunk) through a 6-block ring, so the next tile loads while
+    // this one multiplies; two accumulators alternate, and the epilogue stores the gated fp16 result STRAIGHT to the
+    // output ring slot in global memory - transposed across lanes first, so that eight lanes write one full 128-byte line.
+    // D(H): three resident head chunks (96 KB) and two head-image buffers (written by the head prep; operand of the MMAs
+    // and source of the bulk store to ring 0).
+    const bool head = role == 0;
+    const int l = 8 - role;                       // D(l): consumes dy_l, produces dy_{l-1}     (head: produces dyH and dy7)
+    const int in_ring = head ? -1 : lw_ring_of_layer(l);
+    const int out_ring = head ? lw_ring_of_layer(7) : lw_ring_of_layer(l - 1);
+    const int mask_layer = head ? 7 : l - 1;
+    const int nch = head ? 3 : 4;
+    const int cbase = head ? 0 : 3 + (7 - l) * 4;
+    uint8_t* s_w = smem;                          // resident weights: nch x [256 x 64] K-major images
+    uint8_t* s_in = smem + nch * CHUNK_B;         // D(l): 6 x 16 KB input blocks | D(H): 2 x 64 KB head images
+    uint64_t* w_bar = bars;                       // weights landed
+    uint64_t* blk_full = bars + 1;                // [6]  (D(H): img_full[2], 8 arrivals)
+    uint64_t* blk_empty = bars + 7;               // [6]  (D(H): img_empty[2]: the MMAs have read the image)
+    uint64_t* d_full = bars + 13;                 // [2]
+    uint64_t* d_empty = bars + 15;                // [2]  8 arrivals (epilogue warps)
+    uint64_t* hs_done = bars + 17;                // [2]  D(H): the head image's bulk store has read the buffer
+    uint64_t* pub_full = bars + 19;               // [2]  8 arrivals: the epilogue warps have stored the tile's output image
+    if (threadIdx.x == 0) {
+      mbar_init(w_bar, 1);
+      for (int i = 0; i < LW_IN_BLKS; ++i) { mbar_init(&blk_full[i], head ? 8 : 1); mbar_init(&blk_empty[i], 1); }
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 8); mbar_init(&hs_done[i], 1); mbar_init(&pub_full[i], 8);
+      }
+      mbar_fence_init();
+    }
+    if (warp == 10) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+
+    if (warp == 8 && lane == 0) {                 // resident weights, once
+      mbar_expect_tx(w_bar, (uint32_t)nch * CHUNK_B);
+      for (int c = 0; c < nch; ++c)
+        bulk_g2s(s_w + c * CHUNK_B, g.packed_t + (size_t)(cbase + c) * CHUNK_B, CHUNK_B, w_bar);
+    }
+    if (warp == 8 && !head) {
+      // ---------------- loader (D(l)): the tiles' dy_l images block by block
+      if (lane == 0) {
+        {
+          uint32_t cnt = 0;
+          for (int64_t t = j; t < g.num_tiles; t += P) {
+            { LW_T0(); lw_wait_ready(g, in_ring, t); LW_ACC(1); }
+            fence_proxy_async_all();              // the image was written with generic stores by another SM
+            const uint8_t* src = lw_slot(g, in_ring, t);
+            for (int ci = 0; ci < 4; ++ci, ++cnt) {
+              const uint32_t pos = cnt % LW_IN_BLKS, ph = (cnt / LW_IN_BLKS) & 1;
+              { LW_T0(); mbar_wait(&blk_empty[pos], ph ^ 1); LW_ACC(2); }
+              mbar_expect_tx(&blk_full[pos], ACT_BLK);
+              bulk_g2s(s_in + pos * ACT_BLK, src + ci * ACT_BLK, ACT_BLK, &blk_full[pos]);
+            }
+          }
+        }
+      }
+    } else if (warp == 9) {
+      // ---------------- MMA issuer (converged warp, one elected lane issues)
+      const uint32_t idesc = umma_idesc_f16(128, 256, 0, 0);
+      const uint32_t w_u32 = smem_u32(s_w), in_u32 = smem_u32(s_in);
+      mbar_wait(w_bar, 0);
+      uint32_t cnt = 0, dcnt = 0;
+      for (int64_t t = j; t < g.num_tiles; t += P, ++dcnt) {
+        const uint32_t a = dcnt & 1;
+        if (dcnt >= 2) { LW_T0(); mbar_wait(&d_empty[a], ((dcnt >> 1) - 1) & 1); if (lane == 0) LW_ACC(5); }
+        const uint32_t d_tmem = tmem + a * 256;
+        if (head) {
+          { LW_T0(); mbar_wait(&blk_full[a], (dcnt >> 1) & 1); if (lane == 0) LW_ACC(4); }     // head image `a` written
+          tc_fence_after();
+          const uint32_t img = in_u32 + a * ACT_BYTES;
+          if (elect_one()) {
+            for (int ci = 0; ci < 3; ++ci) {
+              const int nks = (ci == 2) ? 1 : 4;                   // sigma block: only the first 16 columns
+              for (int ks = 0; ks < nks; ++ks)
+                umma_f16(d_tmem, umma_desc_kmajor(img + ci * ACT_BLK + ks * 32), umma_desc_kmajor(w_u32 + ci * CHUNK_B + ks * 32),
+                         idesc, (ci > 0 || ks > 0) ? 1u : 0u);
+            }
+            umma_commit(&blk_empty[a]);
+            umma_commit(&d_full[a]);
+          }
+          __syncwarp();
+        } else {
+          for (int ci = 0; ci < 4; ++ci, ++cnt) {
+            const uint32_t pos = cnt % LW_IN_BLKS;
+            { LW_T0(); mbar_wait(&blk_full[pos], (cnt / LW_IN_BLKS) & 1); if (lane == 0) LW_ACC(4); }
+            tc_fence_after();
+            if (elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                umma_f16(d_tmem, umma_desc_kmajor(in_u32 + pos * ACT_BLK + ks * 32), umma_desc_kmajor(w_u32 + ci * CHUNK_B + ks * 32),
+                         idesc, (ci > 0 || ks > 0) ? 1u : 0u);
+              umma_commit(&blk_empty[pos]);
+              if (ci == 3) umma_commit(&d_full[a]);
+            }
+            __syncwarp();
+          }
+          // all four blocks of the tile have landed in shared memory: the ring slot may be overwritten
+          if (elect_one()) lw_mark_done(g, in_ring, t);
+          __syncwarp();
+        }
+      }
+    } else if (warp == 10) {
+      // ---------------- publisher: the epilogue warps only STORE the output image (generic stores) and arrive on
+      // pub_full; this lane makes those stores visible at GPU scope (the fence is cumulative over what it has observed
+      // through the barrier) and publishes the slot, so the 1.5 - 3 us a fence waits for L2's write acknowledgements
+      // never sit in the epilogue's path.
+      if (lane == 0) {
+        uint32_t dcnt = 0;
+        for (int64_t t = j; t < g.num_tiles; t += P, ++dcnt) {
+          mbar_wait(&pub_full[dcnt & 1], (dcnt >> 1) & 1);
+          __threadfence();
+          st_release_gpu(g.flags + out_ring * LW_R + (int)(t % LW_R), (uint32_t)(t + 1));
+        }
+      }
+      __syncwarp();
+    } else if (head && (warp == 8 || warp == 11)) {
+      // ---------------- D(H): head images -> ring 0 (bulk stores from the image buffers; one warp per buffer, because a
+      // 64-KB store takes ~2.8 us from issue to completion).  A slot is published as soon as ITS stores have completed -
+      // never later: a producer that sat on an unpublished tile while waiting for a free slot further down its list
+      // would close a cycle with its consumers.
+      if (lane == 0) {
+        const uint32_t b = warp == 11 ? 1u : 0u;
+        const uint8_t* img = s_in + b * ACT_BYTES;
+        uint32_t use = 0;
+        for (int64_t t = j + (int64_t)b * P; t < g.num_tiles; t += 2 * (int64_t)P, ++use) {
+          mbar_wait(&blk_full[b], use & 1);
+          LW_T0();
+          lw_wait_free(g, 0, t);
+          uint8_t* dst = lw_slot(g, 0, t);
+          for (int c = 0; c < 4; ++c) bulk_s2g(dst + c * ACT_BLK, img + c * ACT_BLK, ACT_BLK);
+          bulk_commit();
+          bulk_wait_read0();
+          mbar_arrive(&hs_done[b]);                         // the buffer may be rewritten (once the MMAs have read it too)
+          bulk_wait_all0();
+          lw_publish(g, 0, t);
+          LW_ACC(11);
+        }
+      }
+      __syncwarp();
+    } else if (warp < 8) {
+      // ---------------- epilogue warps (and, for D(H), the head image).  Warp w: TMEM lane quarter q = w & 3 (rows
+      // 32q .. 32q+31), blocks 2 (w >> 2) and 2 (w >> 2) + 1 - all 64 columns of each, i.e. whole 128-byte image rows.
+      const int q = warp & 3, bh = warp >> 2;
+      const int row = q * 32 + lane;
+      const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+      const float scale = grad_scale_from(g.absmax, g.fixed_scale);
+      const float* wrgb = c_wrgb[g.wrgb_slot];
+      // D(H): head image of tile t = [dy9 0..63 | dy9 64..127 | (d_sigma, 0..) | (d_rgb, 0..)] into buffer it & 1
+      // (thread: row `row`, dy9 block bh, and unit 0/1 of block 2 + bh)
+      auto head_prep = [&](int64_t t, uint32_t it) {
+        LW_T0();
+        const uint32_t ib = it & 1;
+        const uint32_t* ws_mask = mask0 + t * (9 * 8 * 128);
+        float4 dr = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t * TILE + row < g.P) dr = __ldg(reinterpret_cast<const float4*>(g.d_raw) + t * TILE + row);
+        dr.x *= scale; dr.y *= scale; dr.z *= scale; dr.w *= scale;
+        const uint32_t hm0 = __ldg(ws_mask + (8 * 8 + bh * 2 + 0) * 128 + row), hm1 = __ldg(ws_mask + (8 * 8 + bh * 2 + 1) * 128 + row);
+        if (it >= 2) {                                         // the buffer's previous image: MMAs and bulk store have read it
+          mbar_wait(&blk_empty[ib], ((it >> 1) - 1) & 1);
+          mbar_wait(&hs_done[ib], ((it >> 1) - 1) & 1);
+        }
+        if (threadIdx.x == 0) LW_ACC(2);
+        uint8_t* img = s_in + ib * ACT_BYTES;
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) {
+          const int c0 = bh * 64 + jj * 32;
+          const uint32_t m = jj ? hm1 : hm0;
+          float val[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float v = dr.x * wrgb[c0 + i] + dr.y * wrgb[128 + c0 + i] + dr.z * wrgb[256 + c0 + i];
+            val[i] = ((m >> i) & 1u) ? v : 0.f;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u)
+            *reinterpret_cast<uint4*>(img + bh * ACT_BLK + tile_unit_off(row, jj * 4 + u)) =
+                make_uint4(pack_half2(val[8 * u], val[8 * u + 1]), pack_half2(val[8 * u + 2], val[8 * u + 3]),
+                           pack_half2(val[8 * u + 4], val[8 * u + 5]), pack_half2(val[8 * u + 6], val[8 * u + 7]));
+        }
+        uint4 u0 = make_uint4(0u, 0u, 0u, 0u);
+        if (bh == 0) u0.x = pack_half2(dr.w, 0.f);
+        else { u0.x = pack_half2(dr.x, dr.y); u0.y = pack_half2(dr.z, 0.f); }
+        *reinterpret_cast<uint4*>(img + (2 + bh) * ACT_BLK + tile_unit_off(row, 0)) = u0;
+        *reinterpret_cast<uint4*>(img + (2 + bh) * ACT_BLK + tile_unit_off(row, 1)) = make_uint4(0u, 0u, 0u, 0u);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&blk_full[ib]);
+        if (threadIdx.x == 0) LW_ACC(8);
+      };
+      uint32_t dcnt = 0;
+      if (head && my_tiles > 0) head_prep(j, 0);
+      const int lg = lane & 7, lq = lane >> 3;               // position in the 8-lane transpose group, group in the warp
+      for (int64_t t = j; t < g.num_tiles; t += P, ++dcnt) {
+        const uint32_t a = dcnt & 1;
+        const uint32_t* ws_mask = mask0 + t * (9 * 8 * 128);
+        uint32_t m[2][2];                                      // sign words of this row: [block][column half]
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb)
+#pragma unroll
+          for (int h2 = 0; h2 < 2; ++h2) m[jb][h2] = __ldg(ws_mask + (mask_layer * 8 + (2 * bh + jb) * 2 + h2) * 128 + row);
+        if (head && t + P < g.num_tiles) head_prep(t + P, dcnt + 1);      // next tile's image while this tile's MMAs run
+        if (threadIdx.x == 0) { LW_T0(); lw_wait_free(g, out_ring, t); LW_ACC(10); }
+        named_bar_sync(1, 256);
+        { LW_T0(); mbar_wait(&d_full[a], (dcnt >> 1) & 1); if (threadIdx.x == 0) LW_ACC(3); }
+        tc_fence_after();
+        LW_T0();
+        uint8_t* dst = lw_slot(g, out_ring, t);
+        const uint32_t acc = tmem + lane_addr + a * 256 + bh * 128;
+#pragma unroll
+        for (int jb = 0; jb < 2; ++jb) {
+          uint32_t va[32], vb[32];
+          tmem_ld32(acc + jb * 64, va);
+          tmem_ld32(acc + jb * 64 + 32, vb);
+          tmem_ld_wait();
+          if (jb == 1) {                         // every accumulator read of this thread is complete: hand the accumulator back
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&d_empty[a]);
+          }
+          uint4 x[8];                            // x[u] = 16-byte unit u (columns 8u .. 8u+7) of this thread's row
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const uint32_t (&v)[32] = (u < 4) ? va : vb;
+            const uint32_t mk = m[jb][u >> 2];
+            uint32_t pk[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int i = 8 * (u & 3) + 2 * e;
+              float f0 = ((mk >> i) & 1u) ? __uint_as_float(v[i]) : 0.f;
+              float f1 = ((mk >> (i + 1)) & 1u) ? __uint_as_float(v[i + 1]) : 0.f;
+              pk[e] = pack_half2(f0, f1);
+            }
+            x[u] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+          // 8 x 8 transpose of the units inside each group of eight lanes: afterwards lane i of a group holds unit i of
+          // the group's eight rows, so one store instruction writes four complete 128-byte lines (32 separate lines
+          // before: the LSU spent 4096 line-cycles per tile on them)
+#pragma unroll
+          for (int sft = 4; sft >= 1; sft >>= 1) {
+            const bool up = (lg & sft) != 0;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              if ((u & sft) == 0) {
+                const uint4 snd = up ? x[u] : x[u | sft];
+                uint4 rcv;
+                rcv.x = __shfl_xor_sync(0xffffffffu, snd.x, sft); rcv.y = __shfl_xor_sync(0xffffffffu, snd.y, sft);
+                rcv.z = __shfl_xor_sync(0xffffffffu, snd.z, sft); rcv.w = __shfl_xor_sync(0xffffffffu, snd.w, sft);
+                if (up) x[u] = rcv; else x[u | sft] = rcv;
+              }
+            }
+          }
+          uint8_t* blk = dst + (2 * bh + jb) * ACT_BLK;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {          // x[k] = unit lg of row q*32 + 8*lq + k; it lives at 16-byte slot lg ^ k of that row
+            const int r = q * 32 + 8 * lq + k;
+            *reinterpret_cast<uint4*>(blk + (r >> 3) * 1024 + k * 128 + ((lg ^ k) << 4)) = x[k];
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&pub_full[a]);             // (release at CTA scope: orders this warp's stores before it)
+        if (threadIdx.x == 0) LW_ACC(9);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+#ifdef SWNERF_LW_DEBUG
+    if (threadIdx.x == 0 && g.dbg) g.dbg[(size_t)blockIdx.x * 12] = (unsigned long long)(clock64() - lw_start);
+#endif
+    if (warp == 10) tmem_dealloc<512>(tmem);
+    return;
+  }
+
+  // ============================================================================================= W roles
+  // The jobs of mlp_bwd_weight_kernel with the dy operands pulled from the rings instead of the dy workspace.
+  {
+    const int job = (role == 16) ? 9 : (role == 17 ? 10 : (role == 8 ? 8 : 16 - role));      // roles 9..15 -> jobs 7..1
+    const WgJob& J = c_jobs[0][job];
+    uint64_t* s_full = bars;            // [3]
+    uint64_t* s_empty = bars + 3;       // [3]
+    uint64_t* s_done = bars + 6;
+    const int64_t nhalf = my_tiles * 2;
+    if (threadIdx.x == 0) {
+      for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1 + 4); }
+      mbar_init(s_done, 1);
+      mbar_fence_init();
+    }
+    if (warp == 10) tmem_alloc<512>(&tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    // ring of a dy piece: its offset inside the dy tile record names the layer (8 = the head image)
+    auto piece_ring = [](const WgPiece& pc) { const int L = pc.tile_off / ACT_BYTES; return L == 8 ? 0 : 1 + (7 - L); };
+
+    if (warp == 0) {
+      if (lane == 0) {
+        uint32_t bytes = 0;
+        for (int p = 0; p < J.npieces; ++p) bytes += J.pc[p].nblk * HALF_BLK;
+        for (int64_t h = 0; h < nhalf; ++h) {
+          const uint32_t stage = h % J.nstage, ph = (h / J.nstage) & 1;
+          const int64_t tile = j + (h >> 1) * P;
+          const int half = h & 1;
+          if (half == 0) {
+            LW_T0();
+            for (int p = 0; p < J.npieces; ++p)
+              if (J.pc[p].from_dy) lw_wait_ready(g, piece_ring(J.pc[p]), tile);
+            LW_ACC(1);
+            fence_proxy_async_all();
+          }
+          { LW_T0(); mbar_wait(&s_empty[stage], ph ^ 1); LW_ACC(2); }
+          mbar_expect_tx(&s_full[stage], bytes);
+          uint8_t* dst = smem + stage * J.stage_bytes;
+          for (int p = 0; p < J.npieces; ++p) {
+            const WgPiece& pc = J.pc[p];
+            const uint8_t* src = (pc.from_dy ? lw_slot(g, piece_ring(pc), tile) + pc.tile_off % ACT_BYTES
+                                             : g.ws + tile * WS_TILE_BYTES + pc.tile_off) + half * HALF_BLK;
+            for (int b = 0; b < pc.nblk; ++b)
+              bulk_g2s(dst + pc.smem_off + b * HALF_BLK, src + (size_t)b * ACT_BLK, HALF_BLK, &s_full[stage]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t smem0 = smem_u32(smem);
+      for (int64_t h = 0; h < nhalf; ++h) {
+        const uint32_t stage = h % J.nstage;
+        { LW_T0(); mbar_wait(&s_full[stage], (h / J.nstage) & 1); if (lane == 0) LW_ACC(4); }
+        tc_fence_after();
+        const uint32_t base = smem0 + stage * J.stage_bytes;
+        if (elect_one()) {
+          for (int m = 0; m < J.nmma; ++m) {
+            const WgMma& mm = J.mm[m];
+            const uint32_t idesc = umma_idesc_f16(128, mm.N, 1, 1);
+            for (int ks = 0; ks < 4; ++ks)
+              umma_f16(tmem + mm.dcol, umma_desc_mnmajor(base + mm.a_off + ks * 2048, HALF_BLK),
+                       umma_desc_mnmajor(base + mm.b_off + ks * 2048, HALF_BLK), idesc, (h > 0 || ks > 0) ? 1u : 0u);
+          }
+          umma_commit(&s_empty[stage]);
+          if (h & 1) {                  // both halves of the tile are in shared memory: release its ring slots
+            const int64_t tile = j + (h >> 1) * P;
+            for (int p = 0; p < J.npieces; ++p)
+              if (J.pc[p].from_dy) lw_mark_done(g, piece_ring(J.pc[p]), tile);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(s_done);
+      __syncwarp();
+    } else if (warp >= 4 && warp < 8) {
+      // bias gradients on the CUDA cores + the final flush: as mlp_bwd_weight_kernel
+      const int bt = threadIdx.x - 128;
+      const int b_blk = bt >> 5, b_u = bt & 7, b_rg = (bt >> 3) & 3;
+      float bacc[WG_MAX_BIAS][8];
+#pragma unroll
+      for (int b = 0; b < WG_MAX_BIAS; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) bacc[b][e] = 0.f;
+      for (int64_t h = 0; h < nhalf; ++h) {
+        uint32_t stage = h % J.nstage;
+        mbar_wait(&s_full[stage], (h / J.nstage) & 1);
+        const uint8_t* st = smem + stage * J.stage_bytes;
+#pragma unroll
+        for (int b = 0; b < WG_MAX_BIAS; ++b) {
+          if (b < J.nbias && b_blk * 64 + b_u * 8 < J.bs[b].ncols) {
+            const uint8_t* blk = st + J.bs[b].smem_off + b_blk * HALF_BLK;
+#pragma unroll 4
+            for (int rr = 0; rr < 16; ++rr) {
+              const uint4 q4 = *reinterpret_cast<const uint4*>(blk + tile_unit_off(b_rg * 16 + rr, b_u));
+              const __half2* h2 = reinterpret_cast<const __half2*>(&q4);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float2 f = __half22float2(h2[e]);
+                bacc[b][2 * e] += f.x; bacc[b][2 * e + 1] += f.y;
+              }
+            }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[stage]);
+      }
+#pragma unroll
+      for (int b = 0; b < WG_MAX_BIAS; ++b)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          bacc[b][e] += __shfl_xor_sync(0xffffffffu, bacc[b][e], 8);
+          bacc[b][e] += __shfl_xor_sync(0xffffffffu, bacc[b][e], 16);
+        }
+      mbar_wait(s_done, 0);
+      tc_fence_after();
+      if (nhalf > 0) {
+        const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < WG_MAX_BIAS; ++b) {
+          if (b < J.nbias && b_rg == 0) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const int col = b_blk * 64 + b_u * 8 + e;
+              if (col < J.bs[b].nvalid) {
+                const float v = bacc[b][e] * inv;
+                if (J.bs[b].out_param >= 0) atomicAdd(g.grads[J.bs[b].out_param] + J.bs[b].out_off + col, v);
+                else if (J.bs[b].out_param == -1) { atomicAdd(g.unfold + 128 * 256 + col, v); atomicAdd(g.grads[17] + col, v); }
+              }
+            }
+          }
+        }
+        for (int m = 0; m < J.nmma; ++m) {
+          const WgMma& mm = J.mm[m];
+          float* base = (mm.out_param >= 0 ? g.grads[mm.out_param] : g.unfold) + mm.out_off + (size_t)r * mm.row_stride;
+          for (int c0 = 0; c0 < mm.ncols; c0 += 32) {
+            uint32_t v[32];
+            tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mm.dcol + c0, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < mm.ncols) atomicAdd(base + (size_t)(c0 + i) * mm.col_stride, __uint_as_float(v[i]) * inv);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+#ifdef SWNERF_LW_DEBUG
+    if (threadIdx.x == 0 && g.dbg) g.dbg[(size_t)blockIdx.x * 12] = (unsigned long long)(clock64() - lw_start);
+#endif
+    if (warp == 10) tmem_dealloc<512>(tmem);
+  }
+}
+
+#ifdef SWNERF_LW_DEBUG
+static unsigned long long* g_lw_dbg = nullptr;
+extern "C" int swnerf_tc_lw_debug(unsigned long long* dev_buf) { g_lw_dbg = dev_buf; return 0; }
+#endif
+
+// CTAs per role.  Every role costs about one "full" unit per tile (16 MMAs of 128 x 256 x 16, or the load time of its
+// operands), the head roles a little less; SWNERF_LW_ROLES="n0,n1,...,n16" overrides (tuning).
+static void lw_assign_roles(int n_cta, int* first) {
+  // measured (tools/lw_sweep.py, 786 k samples): 12,6x7,12,9x7,9,9 -> 3.64 ms; D(l) = 5 -> 4.2 ms
+  static const int weight_default[LW_ROLES] = {130, 65, 65, 65, 65, 65, 65, 65, 130, 100, 100, 100, 100, 100, 100, 100, 100, 100};
+  int cnt[LW_ROLES];
+  const char* env = getenv("SWNERF_LW_ROLES");
+  bool ok = false;
+  if (env) {
+    int n = 0, tot = 0;
+    const char* p = env;
+    while (*p && n < LW_ROLES) { cnt[n] = atoi(p); tot += cnt[n]; ++n; while (*p && *p != ',') ++p; if (*p == ',') ++p; }
+    ok = (n == LW_ROLES && tot <= n_cta);
+    for (int i = 0; ok && i < LW_ROLES; ++i) ok = cnt[i] >= 1;
+  }
+  if (!ok) {
+    int tot = 0, used = 0;
+    for (int i = 0; i < LW_ROLES; ++i) tot += weight_default[i];
+    for (int i = 0; i < LW_ROLES; ++i) { cnt[i] = n_cta * weight_default[i] / tot; if (cnt[i] < 1) cnt[i] = 1; used += cnt[i]; }
+    // left-over CTAs go to the full-cost roles first (largest remainder would give the same within one CTA)
+    for (int i = 0; used < n_cta; i = (i + 1) % LW_ROLES) { ++cnt[i]; ++used; }
+  }
+  first[0] = 0;
+  for (int i = 0; i < LW_ROLES; ++i) first[i + 1] = first[i] + cnt[i];
+}
+
 // job table ------------------------------------------------------------------------------------
 static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the layer input */, int col_off, int ld) {
   J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 8 * HALF_BLK; J.nstage = 3;
@@ -1081,7 +1662,7 @@ static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the 
 }
 
 static void build_jobs(WgJob* jobs, int kind) {
-  memset(jobs, 0, sizeof(WgJob) * WG_JOBS);
+  memset(jobs, 0, sizeof(WgJob) * WG_JOBS_ALL);
   const int ld0 = kind == 1 ? 84 : 63;               // pts_linears.0 is [256, 63]; _time.0 is [256, 63 + 21]
   // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :63], dW5[:, :63]
   {
@@ -1096,6 +1677,18 @@ static void build_jobs(WgJob* jobs, int kind) {
       for (int m = 0; m < 2; ++m)
         J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64, (a * 2 + m) * 64,
                            a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : 319), a == 0 ? ld0 : 319, 1, 63};
+  }
+  // jobs 9 / 10: the two halves of job 0 on their own (dy0 with PE -> dW0[:, :63], db0;  dy5 with PE -> dW5[:, :63],
+  // db5).  The layer-pipelined kernel gives each its own role: a role that needed dy5 AND dy0 of a tile would hold the
+  // dy5 slot until the tile has travelled five more stages.
+  for (int a = 0; a < 2; ++a) {
+    WgJob& J = jobs[9 + a];
+    J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 5 * HALF_BLK; J.nstage = 3;
+    J.bs[0] = {0, 256, 256, a == 0 ? (kind == 1 ? -2 : 1) : 11, 0};
+    J.pc[0] = {1, (a == 0 ? 0 : 5) * ACT_BYTES, 4, 0};
+    J.pc[1] = {0, WS_PE_OFF, 1, 4 * HALF_BLK};
+    for (int m = 0; m < 2; ++m)
+      J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 64, m * 64, a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : 319), a == 0 ? ld0 : 319, 1, 63};
   }
   for (int l = 1; l <= 4; ++l) wg_std_job(jobs[l], l, WS_H_OFF + (l - 1) * ACT_BYTES, 0, 256);
   wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, 63, 319);
@@ -1155,7 +1748,17 @@ static int g_prof = 0;
 static cudaEvent_t g_ev[4] = {nullptr, nullptr, nullptr, nullptr};
 static int g_prof_valid = 0;
 
+// -1 / 0 = the two-kernel backward (default), 1 = the layer-pipelined kernel for launches of more than two tiles per SM.
+// SWNERF_BWD_LW=0/1 presets it.
+static std::atomic<int> g_bwd_variant{[] { const char* e = getenv("SWNERF_BWD_LW"); return e ? (atoi(e) ? 1 : 0) : -1; }()};
+
 extern "C" {
+
+int swnerf_tc_set_bwd_variant(int variant) {
+  SW_REQUIRE(variant >= -1 && variant <= 1, "tc_set_bwd_variant: variant must be -1 (automatic), 0 or 1");
+  g_bwd_variant.store(variant);
+  return SWNERF_OK;
+}
 
 int swnerf_tc_set_profiling(int on) {
   g_prof = on;
@@ -1230,14 +1833,14 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   b.ws = ws; b.unfold = unfold; b.absmax = absmax; b.fixed_scale = grad_scale;
   for (int i = 0; i < 24; ++i) b.grads[i] = i < np ? grads[i] : nullptr;
   // job table: built once per process (host), uploaded once per DEVICE together with the shared-memory opt-ins
-  static WgJob jobs[2][WG_JOBS];
+  static WgJob jobs[2][WG_JOBS_ALL];
   static int wg_smem = 0;
   static std::once_flag jobs_once;
   std::call_once(jobs_once, [] {
     build_jobs(jobs[0], 0);
     build_jobs(jobs[1], 1);
     for (int k = 0; k < 2; ++k)
-      for (int j = 0; j < WG_JOBS; ++j) {
+      for (int j = 0; j < WG_JOBS_ALL; ++j) {
         int need = jobs[k][j].stage_bytes * jobs[k][j].nstage + 1024;
         if (need > wg_smem) wg_smem = need;
       }
@@ -1252,6 +1855,46 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (g_prof) cudaEventRecord(g_ev[0], s);
   int rc = SWNERF_OK;
+  // The layer-pipelined kernel (section 5) is OPT-IN (swnerf_tc_set_bwd_variant(1) / SWNERF_BWD_LW=1): it cuts the
+  // backward's DRAM traffic 3x (ncu: 3.86 GB against 11.5 GB for 786 k samples, dy never leaves L2) but is still slower
+  // than the two-kernel backward (3.6 against 2.1 ms): its roles are bound by the latency of their operand loads, not
+  // by HBM (profiles/r2_lw_backward.md).  The two-kernel backward stays the default.
+  const int lw_variant = g_bwd_variant.load();
+  const int lw_min_ctas = 2 * LW_ROLES;
+  if (kind == 0 && !d_pts && sm_count() >= lw_min_ctas && lw_variant == 1 && tiles > 2 * (int64_t)sm_count() &&
+      tiles * WS_DY_BYTES >= LW_RING_BYTES) {
+    const int lw_d_smem = 4 * CHUNK_B + LW_IN_BLKS * ACT_BLK + 1024;
+    const int lw_smem = lw_d_smem > wg_smem ? lw_d_smem : wg_smem;
+    if (once_per_device(ONCE_BWD_LW))
+      cudaFuncSetAttribute(mlp_bwd_lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, lw_smem);
+    LwArgs a;
+    a.d_raw = d_out; a.P = P; a.num_tiles = tiles;
+    a.packed = reinterpret_cast<const uint8_t*>(packed); a.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
+    a.ws = ws; a.ring = ws + tiles * (WS_TILE_BYTES + WS_MASK_BYTES);
+    a.flags = reinterpret_cast<uint32_t*>(tail + LW_FLAGS_OFF);
+    a.unfold = unfold; a.absmax = absmax; a.fixed_scale = grad_scale;
+    for (int i = 0; i < 24; ++i) a.grads[i] = grads[i];
+#ifdef SWNERF_LW_DEBUG
+    a.dbg = g_lw_dbg;
+#else
+    a.dbg = nullptr;
+#endif
+    cudaMemsetAsync(tail + LW_FLAGS_OFF, 0, LW_FLAG_WORDS * sizeof(uint32_t), s);
+    a.wrgb_slot = const_slot_acquire(CONST_FAMILY_BWD_WRGB, WRGB_SLOTS, s);
+    SW_REQUIRE(a.wrgb_slot >= 0, "tc_mlp_bwd: no current device");
+    if (cudaMemcpyToSymbolAsync(c_wrgb, reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF + F32_WRGB * sizeof(float),
+                                384 * sizeof(float), (size_t)a.wrgb_slot * 384 * sizeof(float), cudaMemcpyDeviceToDevice,
+                                s) != cudaSuccess)
+      return set_err(SWNERF_ERR_CUDA, "tc_mlp_bwd: staging rgb_linear.weight failed");
+    lw_assign_roles(sm_count(), a.role_first);
+    mlp_bwd_lw_kernel<<<a.role_first[LW_ROLES], 384, lw_smem, s>>>(a);
+    if (g_prof) { cudaEventRecord(g_ev[1], s); cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
+    rc = check_launch("tc_mlp_bwd_lw");
+    if (rc) return rc;
+    unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
+                                            grads[19], grads[16]);
+    return check_launch("tc_unfold_head");
+  }
   static const int dg_variant = [] { const char* e = getenv("SWNERF_BWD_PAIR"); return e ? atoi(e) : -1; }();
   if (dg_variant == 1 || (dg_variant < 0 && tiles > 2 * (int64_t)sm_count())) {
     if (once_per_device(ONCE_BWD_DATA_PAIR))

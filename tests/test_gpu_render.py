@@ -834,3 +834,32 @@ def test_dnerf_tc_two_times_before_backward(tmp_path):
     (loss_of(r1) + loss_of(r2)).backward()                  # both forwards first, then one backward
     joint = torch.cat([p.grad.reshape(-1) for p in model.parameters() if p.grad is not None])
     assert rel_l2(joint, sep) < 1e-4, rel_l2(joint, sep)
+
+
+@needs_tc_bwd
+def test_layer_pipelined_backward_matches_two_kernel_backward():
+    """swnerf_tc_set_bwd_variant(1): the layer-pipelined backward (dy images handed from role to role through an
+    L2-resident ring, never written to HBM) against the default two-kernel backward on the same saved activations:
+    identical roundings, so the gradients agree to the accumulation order (~3e-5), every tensor included.  Sizes: a
+    ragged fine pass of 1000 rays x 192 (1500 tiles) and the coarse shape 2500 x 64 (1250 tiles)."""
+    from swnerf_b200 import _lib
+    pc, pf, mc, mf, q = make_vanilla(21, 55, "tc")
+    try:
+        for N, S_ in ((1000, 192), (2500, 64)):
+            rays = T(O.blender_rays(N, 7))
+            z = torch.sort(torch.rand(N, S_, device=DEV) * 4 + 2, -1)[0]
+            cot = torch.randn(N, S_, 4, device=DEV)
+            res = {}
+            for variant in (0, 1):
+                _lib.call("swnerf_tc_set_bwd_variant", variant)
+                for p in mf.parameters():
+                    p.grad = None
+                (q.query_rays(rays, z, mf, 8) * cot).sum().backward()
+                torch.cuda.synchronize()
+                res[variant] = [p.grad.clone() for p in mf.param_list()]
+            flat0 = torch.cat([g.reshape(-1) for g in res[0]]); flat1 = torch.cat([g.reshape(-1) for g in res[1]])
+            assert rel_l2(flat1, flat0) < 2e-4, rel_l2(flat1, flat0)
+            for a, b in zip(res[1], res[0]):
+                assert rel_l2(a, b) < 1e-3
+    finally:
+        _lib.call("swnerf_tc_set_bwd_variant", -1)

@@ -137,11 +137,19 @@ int swnerf_colsum(const float* x, int64_t ld, int64_t rows, int cols, float* out
 
 /* ---- a3+a4+a5+a6 fused, tcgen05 (the hot kernel): see the second half of this header. ---- */
 
-/* Geometry of the fused 8x256 skip MLP (model.py:11-37 with D=8, W=256, skips=[4], use_viewdirs=True,
- * PE L=10/4 -> input_ch 63 / input_ch_views 27).  Other shapes run through swnerf_sgemm. */
+/* Geometry of the fused 8x256 skip MLP (model.py:11-37 with D=8, W=256, skips=[4], use_viewdirs=True).  The positional
+ * encodings are a per-network-family property passed to every call as one `enc` code:
+ *   SWNERF_TC_ENC(pos_L, view_L, time_L)   frequency counts of get_embedder (embedder.py:45-59); L <= 0 = identity
+ * configs/lego.txt and every D-NeRF config: (10, 4, 10) -> input_ch 63 / input_ch_views 27 / input_ch_time 21;
+ * the MultiRes pyramid (multires_dnerf.py:665, channels = (pos, time, view)): SWNERF_TC_ENC(20, 20, 8),
+ * SWNERF_TC_ENC(10, 10, 4) and SWNERF_TC_ENC(0, 0, 0).  Supported: pos_L, view_L in {0, 4, 10, 20}, time_L <= 20; a
+ * call with another code returns SWNERF_ERR_ARG.  Other shapes run through swnerf_sgemm / swnerf_hgemm_tc. */
 #define SWNERF_TC_TILE 128            /* sample rows per tile */
 #define SWNERF_TC_W 256
 #define SWNERF_TC_NPARAM 24           /* state_dict tensors, order below */
+#define SWNERF_TC_ENC(pos_L, view_L, time_L) \
+  (((pos_L) > 0 ? (pos_L) : 0) | (((view_L) > 0 ? (view_L) : 0) << 8) | (((time_L) > 0 ? (time_L) : 0) << 16))
+#define SWNERF_TC_ENC_DEFAULT SWNERF_TC_ENC(10, 4, 10)
 
 /* Parameter pointer order for `params` / `grads` (state_dict names, model.py:22-37):
  *   [2i], [2i+1]  pts_linears.i.weight / .bias   (i = 0..7)
@@ -151,20 +159,20 @@ int swnerf_colsum(const float* x, int64_t ld, int64_t rows, int cols, float* out
  *   [22],[23]     rgb_linear.weight / .bias                                                          */
 
 /* Bytes of the packed fp16 weight image (UMMA-canonical, 128B-swizzled K-major chunks + fp32 biases)
- * the fused kernels stream; and of the transposed image used by the backward-data kernel. */
+ * the fused kernels stream; and of the transposed image used by the backward-data kernel (sized for every encoding). */
 int64_t swnerf_tc_packed_bytes(void);
 /* Repack fp32 master weights (24 device pointers in a HOST array) into the packed image.  Also folds
  * feature_linear into views_linears (no nonlinearity between them, model.py:50-55). */
-int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream);
+int swnerf_tc_pack_weights(const float* const* params, int enc, void* packed, void* stream);
 
 /* Workspace bytes per call for n_points sample rows: saved activations (training only). */
-int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training);
+int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training, int enc);
 
-/* Fused forward: for every ray n and sample s: p = o + d*z[n,s]; x = [PE10(p) | PE4(viewdir)];
+/* Fused forward: for every ray n and sample s: p = o + d*z[n,s]; x = [PE(p) | PE(viewdir)];
  * raw[n,s,:] = MLP(x).  rays[N, ray_stride] as in nerf/run.py:152-158.  If training != 0 the
  * post-ReLU activations needed by the backward are written to `workspace`. */
 int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
-                      int n_samples, const void* packed, float* raw, void* workspace, int training,
+                      int n_samples, const void* packed, int enc, float* raw, void* workspace, int training,
                       void* stream);
 
 /* Fused backward: d_raw[N,S,4] -> fp32 gradients of the 24 parameter tensors, ACCUMULATED into
@@ -174,9 +182,9 @@ int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const flo
  * max|d_raw| on the device (no host sync). */
 int64_t swnerf_tc_packed_t_bytes(void);
 /* `packed` is the forward image of the same parameters (its folded head is reused). */
-int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream);
+int swnerf_tc_pack_weights_t(const float* const* params, int enc, const void* packed, void* packed_t, void* stream);
 int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
-                      const void* packed_t, const float* const* params, void* workspace,
+                      const void* packed_t, int enc, const float* const* params, void* workspace,
                       float* const* grads, float grad_scale, void* stream);
 
 /* ---- D-NeRF (a1d, a5d, a6d, a7) on the same fused kernels -------------------------------------------------
@@ -184,22 +192,22 @@ int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const v
  * explicit sample positions pts[N*S,3] = x + dx (model.py:148-150); its backward can also return d_pts
  * (the positional encoding sits inside the autograd graph there).
  * The deformation network `_time` / `_time_out` (model.py:113-136; 18 tensors: _time.i.weight/.bias i=0..7,
- * _time_out.weight/.bias) maps (x, t) -> dx[N*S,3].  `time_embedding`: PE(t), 21 floats (L=10, one time per call,
- * run_dnerf.py:53). */
+ * _time_out.weight/.bias) maps (x, t) -> dx[N*S,3].  `time_embedding`: PE(t), 1 + 2 time_L floats (21 for L=10; one
+ * time per call, run_dnerf.py:53). */
 int swnerf_tc_mlp_fwd_points(const float* rays, int ray_stride, int view_col, const float* pts, int64_t n_rays,
-                             int n_samples, const void* packed, float* raw, void* workspace, int training,
+                             int n_samples, const void* packed, int enc, float* raw, void* workspace, int training,
                              void* stream);
 int swnerf_tc_mlp_bwd_points(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
-                             const void* packed_t, const float* const* params, void* workspace, float* const* grads,
-                             float grad_scale, const float* pts, float* d_pts, void* stream);
-int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host21, void* packed,
+                             const void* packed_t, int enc, const float* const* params, void* workspace,
+                             float* const* grads, float grad_scale, const float* pts, float* d_pts, void* stream);
+int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host, int enc, void* packed,
                                 void* stream);
-int swnerf_tc_pack_weights_time_t(const float* const* params, const void* packed, void* packed_t, void* stream);
+int swnerf_tc_pack_weights_time_t(const float* const* params, int enc, const void* packed, void* packed_t, void* stream);
 int swnerf_tc_time_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
-                       int n_samples, const void* packed_time, float* dx, void* workspace, int training,
+                       int n_samples, const void* packed_time, int enc, float* dx, void* workspace, int training,
                        void* stream);
 int swnerf_tc_time_bwd(const float* d_dx, int64_t n_rays, int n_samples, const void* packed_time,
-                       const void* packed_time_t, const float* const* params, const float* time_embedding_dev21,
+                       const void* packed_time_t, int enc, const float* const* params, const float* time_embedding_dev,
                        void* workspace, float* const* grads, float grad_scale, void* stream);
 
 /* ---- next rows, one step either side of the path ------------------------------------------

@@ -41,16 +41,16 @@ _SIG = {
     "swnerf_act_bwd": [_VP, _I64, _VP, _I64, _I64, _I32, _I32, _VP, _I64, _VP],
     "swnerf_tc_packed_bytes": [],
     "swnerf_tc_packed_t_bytes": [],
-    "swnerf_tc_workspace_bytes": [_I64, _I32],
-    "swnerf_tc_pack_weights": [_VP, _VP, _VP],
-    "swnerf_tc_pack_weights_t": [_VP, _VP, _VP, _VP],
-    "swnerf_tc_mlp_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
-    "swnerf_tc_mlp_fwd_points": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
-    "swnerf_tc_mlp_bwd_points": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _F32, _VP, _VP, _VP],
-    "swnerf_tc_pack_weights_time": [_VP, _VP, _VP, _VP],
-    "swnerf_tc_pack_weights_time_t": [_VP, _VP, _VP, _VP],
-    "swnerf_tc_time_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _VP, _VP, _I32, _VP],
-    "swnerf_tc_time_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
+    "swnerf_tc_workspace_bytes": [_I64, _I32, _I32],
+    "swnerf_tc_pack_weights": [_VP, _I32, _VP, _VP],
+    "swnerf_tc_pack_weights_t": [_VP, _I32, _VP, _VP, _VP],
+    "swnerf_tc_mlp_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _I32, _VP],
+    "swnerf_tc_mlp_fwd_points": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _I32, _VP],
+    "swnerf_tc_mlp_bwd_points": [_VP, _I64, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _F32, _VP, _VP, _VP],
+    "swnerf_tc_pack_weights_time": [_VP, _VP, _I32, _VP, _VP],
+    "swnerf_tc_pack_weights_time_t": [_VP, _I32, _VP, _VP, _VP],
+    "swnerf_tc_time_fwd": [_VP, _I32, _I32, _VP, _I64, _I32, _VP, _I32, _VP, _VP, _I32, _VP],
+    "swnerf_tc_time_bwd": [_VP, _I64, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _VP, _F32, _VP],
     "swnerf_make_rays": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I64, _F32, _F32, _F32, _I32, _I32, _I32, _F32,
                          ctypes.c_double, _VP, _I32, _VP],
     "swnerf_pick_batch": [_I32, _I32, _F32, _F32, _F32, _F32, _VP, _VP, _I32, _I32, _I32, _I32, ctypes.c_uint64, _I64, _F32,
@@ -66,7 +66,7 @@ _SIG = {
     "swnerf_set_resample_variant": [_I32],
     "swnerf_resample_fallbacks": [_VP, _I32, _VP],
     "swnerf_tc_selftest_pair": [_VP, _VP, _VP, _I32, _I32, _I32, _I32, _VP, _VP, _VP],
-    "swnerf_tc_mlp_bwd": [_VP, _I64, _I32, _VP, _VP, _VP, _VP, _VP, _F32, _VP],
+    "swnerf_tc_mlp_bwd": [_VP, _I64, _I32, _VP, _VP, _I32, _VP, _VP, _VP, _F32, _VP],
 }
 _RET = {
     "swnerf_launch_count": _I64,

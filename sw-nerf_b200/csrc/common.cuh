@@ -31,8 +31,8 @@ constexpr int CONST_FAMILY_FWD_F32 = 0, CONST_FAMILY_BWD_WRGB = 1;
 // (id, current device) pair, whatever thread asks; callers run their setup when it returns true.  Ids below.
 bool once_per_device(int id);
 enum OnceId {
-  ONCE_FWD4 = 0, ONCE_FWD1_TRAIN, ONCE_FWD1_INFER, ONCE_BWD_BASE, ONCE_BWD_DATA_PAIR, ONCE_BWD_WEIGHT_PAIR,
-  ONCE_HGEMM, ONCE_HGEMM_WGRAD, ONCE_RESAMPLE64Q, ONCE_RESAMPLE64Q_CHECK, ONCE_FWDX, ONCE_BWDX, ONCE_BWD_LW, ONCE_COUNT
+  ONCE_FWD4 = 0, ONCE_FWD1_BASE, ONCE_FWD1_1, ONCE_FWD1_2, ONCE_FWD1_3, ONCE_FWD1_4, ONCE_FWD1_5, ONCE_BWD_BASE, ONCE_BWD_DATA_PAIR, ONCE_BWD_WEIGHT_PAIR,
+  ONCE_HGEMM, ONCE_HGEMM_WGRAD, ONCE_RESAMPLE64Q, ONCE_RESAMPLE64Q_CHECK, ONCE_FWDX, ONCE_BWDX, ONCE_BWD_LW, ONCE_BWD_INPUT_BASE, ONCE_BWD_INPUT_1, ONCE_BWD_INPUT_2, ONCE_BWD_INPUT_3, ONCE_BWD_INPUT_4, ONCE_COUNT
 };
 
 // u8 tensor map (1..3 dims, no swizzle / interleave) through the driver entry point fetched at run time, so the

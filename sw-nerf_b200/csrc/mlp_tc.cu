@@ -35,11 +35,12 @@ struct ParamPtrs {
   const float* p[24];
   // kind 0: vallina_NeRF / NeRFOriginal (24 tensors, order of include/swnerf_b200.h)
   // kind 1: D-NeRF deformation net (model.py:113-136): p[2i],p[2i+1] = _time.i, p[16],p[17] = _time_out.
-  //         It runs through the SAME kernels: its time embedding is constant per call, so W0[:, 63:] PE(t) is
+  //         It runs through the SAME kernels: its time embedding is constant per call, so W0[:, pc:] PE(t) is
   //         folded into the layer-0 bias, and its 256->3 output layer rides in rows 128..130 of the head
   //         (where alpha_linear sits for kind 0) with the view branch zeroed.
   int kind;
-  float tpe[24];       // PE(t), 21 values used
+  Enc enc;
+  float tpe[ENC_MAX_TW + 3];       // PE(t), enc.tw values used
 };
 
 // W_fv = W_v[:, :256] W_f (128 x 256), b_fv = W_v[:, :256] b_f + b_v      -> fold[128][257] fp32
@@ -49,12 +50,13 @@ __global__ void __launch_bounds__(1024) fold_head_kernel(ParamPtrs P, float* __r
   __shared__ float As[32][33], Bs[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int t = blockIdx.x;
+  const int ldv = 256 + P.enc.vc;                                        // views_linears.0.weight is [128, 256 + vc]
   if (t < 32) {
     const int r0 = (t >> 3) * 32, c0 = (t & 7) * 32;
     float acc = 0.f;
     if (P.kind == 0) {
       for (int j0 = 0; j0 < 256; j0 += 32) {
-        As[ty][tx] = P.p[16][(size_t)(r0 + ty) * 283 + j0 + tx];       // W_v[r, j]
+        As[ty][tx] = P.p[16][(size_t)(r0 + ty) * ldv + j0 + tx];       // W_v[r, j]
         Bs[ty][tx] = P.p[18][(size_t)(j0 + ty) * 256 + c0 + tx];       // W_f[j, c]
         __syncthreads();
 #pragma unroll
@@ -67,7 +69,7 @@ __global__ void __launch_bounds__(1024) fold_head_kernel(ParamPtrs P, float* __r
     const int r = (t - 32) * 32 + ty;
     float acc = 0.f;
     if (P.kind == 0) {
-      for (int j = tx; j < 256; j += 32) acc = fmaf(P.p[16][(size_t)r * 283 + j], P.p[19][j], acc);
+      for (int j = tx; j < 256; j += 32) acc = fmaf(P.p[16][(size_t)r * ldv + j], P.p[19][j], acc);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
       acc += P.p[17][r];
@@ -76,19 +78,29 @@ __global__ void __launch_bounds__(1024) fold_head_kernel(ParamPtrs P, float* __r
   }
 }
 
+// element (n, k) of forward chunk c: n = output unit (row of the K-major B image), k = input column inside the chunk
 __device__ __forceinline__ float fwd_weight(const ParamPtrs& P, const float* fold, int c, int n, int k) {
-  if (P.kind == 1) {
-    if (c == 0) return k < 63 ? P.p[0][n * 84 + k] : 0.f;
-    if (c == 30) return 0.f;
-    if (c >= 31) return (n >= 128 && n < 131) ? P.p[16][(n - 128) * 256 + (c - 31) * 64 + k] : 0.f;
+  const Enc& E = P.enc;
+  const int pc = E.pc, vc = E.vc;
+  const int ld0 = pc + (P.kind == 1 ? E.tw : 0);                         // _time.0 is [256, pc + tw]
+  if (c < E.PC) { const int kk = c * 64 + k; return kk < pc ? P.p[0][(size_t)n * ld0 + kk] : 0.f; }
+  c -= E.PC;
+  if (c < 16) { const int l = 1 + c / 4, kc = c % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
+  c -= 16;
+  if (c < E.PC) { const int kk = c * 64 + k; return kk < pc ? P.p[10][(size_t)n * (256 + pc) + kk] : 0.f; }
+  c -= E.PC;
+  if (c < 4) return P.p[10][(size_t)n * (256 + pc) + pc + c * 64 + k];
+  c -= 4;
+  if (c < 8) { const int l = 6 + c / 4, kc = c % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
+  c -= 8;
+  // head: VC view chunks, then 4 chunks on h7
+  if (c < E.VC) {
+    const int kk = c * 64 + k;
+    return (P.kind == 0 && n < 128 && kk < vc) ? P.p[16][(size_t)n * (256 + vc) + 256 + kk] : 0.f;
   }
-  if (c == 0) return k < 63 ? P.p[0][n * 63 + k] : 0.f;
-  if (c <= 16) { int l = 1 + (c - 1) / 4, kc = (c - 1) % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
-  if (c == 17) return k < 63 ? P.p[10][n * 319 + k] : 0.f;
-  if (c <= 21) return P.p[10][n * 319 + 63 + (c - 18) * 64 + k];
-  if (c <= 29) { int l = 6 + (c - 22) / 4, kc = (c - 22) % 4; return P.p[2 * l][n * 256 + kc * 64 + k]; }
-  if (c == 30) return (n < 128 && k < 27) ? P.p[16][n * 283 + 256 + k] : 0.f;
-  int kk = (c - 31) * 64 + k;
+  c -= E.VC;
+  const int kk = c * 64 + k;
+  if (P.kind == 1) return (n >= 128 && n < 131) ? P.p[16][(n - 128) * 256 + kk] : 0.f;
   if (n < 128) return fold[n * 257 + kk];
   if (n == 128) return P.p[20][kk];
   return 0.f;
@@ -96,12 +108,13 @@ __device__ __forceinline__ float fwd_weight(const ParamPtrs& P, const float* fol
 
 __global__ void pack_fwd_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
   const float* fold = reinterpret_cast<const float*>(packed + PK_FOLD_OFF);
+  const int n_full = P.enc.n_full(), n_all = P.enc.n_chunks();
   int unit = blockIdx.x * blockDim.x + threadIdx.x;
-  if (unit < PK_CHUNK_BYTES / 16) {
+  if (unit < chunk_off_n(n_all, n_full) / 16) {
     int byte = unit * 16;
     int c, in;
-    if (byte < N_FULL_CHUNKS * CHUNK_B) { c = byte / CHUNK_B; in = byte % CHUNK_B; }
-    else { int b2 = byte - N_FULL_CHUNKS * CHUNK_B; c = N_FULL_CHUNKS + b2 / HCHUNK_B; in = b2 % HCHUNK_B; }
+    if (byte < n_full * CHUNK_B) { c = byte / CHUNK_B; in = byte % CHUNK_B; }
+    else { int b2 = byte - n_full * CHUNK_B; c = n_full + b2 / HCHUNK_B; in = b2 % HCHUNK_B; }
     int n = (in >> 10) * 8 + ((in >> 7) & 7);
     int pu = (in >> 4) & 7;
     int k0 = (pu ^ (n & 7)) * 8;
@@ -117,8 +130,10 @@ __global__ void pack_fwd_kernel(ParamPtrs P, uint8_t* __restrict__ packed) {
     if (unit < F32_BHEAD) {
       int l = unit / 256, n = unit % 256;
       v = P.p[2 * l + 1][n];
-      if (P.kind == 1 && l == 0)
-        for (int k = 0; k < 21; ++k) v = fmaf(P.p[0][n * 84 + 63 + k], P.tpe[k], v);     // + W0[:, 63:84] PE(t)
+      if (P.kind == 1 && l == 0) {
+        const int pc = P.enc.pc, tw = P.enc.tw;
+        for (int k = 0; k < tw; ++k) v = fmaf(P.p[0][(size_t)n * (pc + tw) + pc + k], P.tpe[k], v);     // + W0[:, pc:] PE(t)
+      }
     } else if (P.kind == 1) {
       int n = unit - F32_BHEAD;
       v = (unit < F32_WRGB && n >= 128 && n < 131) ? P.p[17][n - 128] : 0.f;
@@ -139,7 +154,9 @@ struct FwdArgs {
   const float* pts;                           // optional explicit sample positions [P,3] (D-NeRF: x + dx)
   const uint8_t* packed; float* raw;          // kind 0: raw[P,4];  kind 1: dx[P,3]
   uint8_t* ws; int64_t num_tiles;
+  uint8_t* ws_ext;                            // two-chunk encodings: second blocks of the saved PE / view images, [tile][PE1 | VW1]
   int kind;
+  int Lp, Lv, PC, VC;                         // encoding (mlp_tc_layout.cuh: Enc)
   int f32_slot;                               // CTA-pair kernel: which copy of the bias block in constant memory
 #ifdef SWNERF_EXPERIMENTS
   int ko;                                     // knock-out experiments (profiles/r1_knockout_experiments.md): bench builds only
@@ -162,24 +179,40 @@ __device__ __forceinline__ void sincos_turns(float th, float tl, float scale, fl
   c = __cosf(ang);
 }
 
-template <int L, int NCOL>
-__device__ __forceinline__ void encode3(const float (&x)[3], float (&f)[NCOL]) {
-  // f[0..3(1+2L)) = [x, sin(2^k x), cos(2^k x)]_k ; the rest stays zero
+// columns [64 CH, 64 CH + 64) of [x, sin(2^k x), cos(2^k x)]_{k < L} (embedder.py:33-42); columns past 3 (1 + 2 L) stay zero
+template <int L, int CH>
+__device__ __forceinline__ void encode3(const float (&x)[3], float (&f)[64]) {
+  constexpr int lo = 64 * CH, hi = lo + 64;
 #pragma unroll
-  for (int i = 0; i < NCOL; ++i) f[i] = 0.f;
+  for (int i = 0; i < 64; ++i) f[i] = 0.f;
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    f[j] = x[j];
-    const float hi = 0.15915494f, lo = 6.4206e-9f;      // 1/(2 pi) = hi + lo
-    float th = x[j] * hi;
-    float tl = fmaf(x[j], hi, -th) + x[j] * lo;
+    if (CH == 0) f[j] = x[j];
+    const float h1 = 0.15915494f, l1 = 6.4206e-9f;      // 1/(2 pi) = h1 + l1
+    float th = x[j] * h1;
+    float tl = fmaf(x[j], h1, -th) + x[j] * l1;
 #pragma unroll
     for (int k = 0; k < L; ++k) {
-      float s, c;
-      sincos_turns(th, tl, (float)(1 << k), s, c);
-      f[3 + 6 * k + j] = s;
-      f[6 + 6 * k + j] = c;
+      const int cs = 3 + 6 * k + j, cc = 6 + 6 * k + j;         // compile-time once unrolled
+      const bool s_in = cs >= lo && cs < hi, c_in = cc >= lo && cc < hi;
+      if (s_in || c_in) {
+        float sn, cn;
+        sincos_turns(th, tl, (float)(1 << k), sn, cn);
+        if (s_in) f[s_in ? cs - lo : 0] = sn;
+        if (c_in) f[c_in ? cc - lo : 0] = cn;
+      }
     }
+  }
+}
+// run-time frequency count (the encodings the reference instantiates: identity, 4, 10, 20), chunk ch of the image
+__device__ __forceinline__ void encode3_any(int L, int ch, const float (&x)[3], float (&f)[64]) {
+  switch (L) {
+    case 0: encode3<0, 0>(x, f); break;
+    case 4: encode3<4, 0>(x, f); break;
+    case 10: encode3<10, 0>(x, f); break;
+    default:
+      if (ch == 0) encode3<20, 0>(x, f); else encode3<20, 1>(x, f);
+      break;
   }
 }
 
@@ -195,17 +228,35 @@ __device__ __forceinline__ void store_row64(uint8_t* img, int row, const float (
   }
 }
 
-template <bool TRAIN>
+// MODE 0: the default encoding (PE L = 10 / 4) at compile time; 1: one-chunk encodings chosen at run time (g.Lp, g.Lv);
+// 2: two-chunk encodings (L = 20: 123 columns): 32-KB position / view images and a two-stage weight ring
+template <int MODE> struct Fwd1Smem {
+  static constexpr int EB = MODE == 2 ? 2 : 1;                  // 16-KB blocks per encoding image
+  static constexpr int NS = MODE == 2 ? 2 : NSTAGE;             // weight ring depth
+  static constexpr int ACT = 0;
+  static constexpr int PE = ACT + ACT_BYTES;
+  static constexpr int VW = PE + EB * ACT_BLK;
+  static constexpr int RING = VW + EB * ACT_BLK;
+  static constexpr int F32 = RING + NS * CHUNK_B;
+  static constexpr int SCR = F32 + ((F32_COUNT * 4 + 127) / 128) * 128;
+  static constexpr int BAR = SCR + TILE * 16;
+  static constexpr int TOTAL = BAR + 256 + 1024;                // + alignment slack
+};
+static_assert(Fwd1Smem<0>::TOTAL == SM_TOTAL && Fwd1Smem<2>::TOTAL <= 232448, "shared memory budget");
+
+template <bool TRAIN, int MODE>
 __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
+  using SL = Fwd1Smem<MODE>;
+  constexpr int NS = SL::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_act = smem + SM_ACT;
-  uint8_t* s_pe = smem + SM_PE;
-  uint8_t* s_vw = smem + SM_VW;
-  uint8_t* s_ring = smem + SM_RING;
-  float* s_f32 = reinterpret_cast<float*>(smem + SM_F32);
-  float4* s_scr = reinterpret_cast<float4*>(smem + SM_SCR);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+  uint8_t* s_act = smem + SL::ACT;
+  uint8_t* s_pe = smem + SL::PE;
+  uint8_t* s_vw = smem + SL::VW;
+  uint8_t* s_ring = smem + SL::RING;
+  float* s_f32 = reinterpret_cast<float*>(smem + SL::F32);
+  float4* s_scr = reinterpret_cast<float4*>(smem + SL::SCR);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::BAR);
   uint64_t* w_full = bars;            // [3]
   uint64_t* w_empty = bars + 3;       // [3]
   uint64_t* pe_full = bars + 6;
@@ -217,11 +268,12 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
   uint64_t* st_done = bars + 17;      // [4] training: block j's bulk store has finished reading shared memory
   uint64_t* h9_full = bars + 21;      //     training: head epilogue has written h9 into blocks 0,1
+  const int PC = MODE == 2 ? g.PC : 1, VC = MODE == 2 ? g.VC : 1;       // K-chunks of the position / view image
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < NSTAGE; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
+    for (int i = 0; i < NS; ++i) { mbar_init(&w_full[i], 1); mbar_init(&w_empty[i], 1); }
     mbar_init(pe_full, 4); mbar_init(pe_empty, 1);       // one arrival per PE warp
     mbar_init(vw_full, 4); mbar_init(vw_empty, 1);
     for (int j = 0; j < 4; ++j) mbar_init(&act_full[j], 8);   // one arrival per epilogue warp
@@ -247,13 +299,14 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
     // ===================== weight producer =====================
     if (lane == 0) {
       uint32_t cnt = 0;
+      const int n_full = 28 + 2 * PC, n_all = 32 + 2 * PC + VC;
       for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x) {
-        for (int c = 0; c < N_CHUNKS; ++c, ++cnt) {
-          uint32_t stage = cnt % NSTAGE, ph = (cnt / NSTAGE) & 1;
+        for (int c = 0; c < n_all; ++c, ++cnt) {
+          uint32_t stage = cnt % NS, ph = (cnt / NS) & 1;
           mbar_wait(&w_empty[stage], ph ^ 1);
-          uint32_t bytes = c < N_FULL_CHUNKS ? CHUNK_B : HCHUNK_B;
+          uint32_t bytes = c < n_full ? CHUNK_B : HCHUNK_B;
           mbar_expect_tx(&w_full[stage], bytes);
-          bulk_g2s(s_ring + stage * CHUNK_B, g.packed + chunk_off(c), bytes, &w_full[stage]);
+          bulk_g2s(s_ring + stage * CHUNK_B, g.packed + chunk_off_n(c, n_full), bytes, &w_full[stage]);
         }
       }
     }
@@ -270,21 +323,21 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
       for (int li = 0; li < 9; ++li, ++dcnt) {
         const uint32_t d_tmem = tmem + (dcnt & 1) * 256;
         const uint32_t idesc = (li == 8) ? idesc144 : idesc256;
-        const int nch = (li == 0) ? 1 : ((li == 5 || li == 8) ? 5 : 4);
+        const int nenc = (li == 0 || li == 5) ? PC : (li == 8 ? VC : 0);    // encoding chunks in front of the layer's input
+        const int nch = (li == 0) ? PC : nenc + 4;
         for (int ci = 0; ci < nch; ++ci) {
           // which A operand feeds this chunk
-          int aj = (li == 5 || li == 8) ? ci - 1 : ci;       // activation block index, -1 = extra input
-          if (li == 0) aj = -1;
+          const int aj = ci - nenc;                          // activation block index, < 0 = encoding image chunk ci
           uint32_t a_base;
           if (aj < 0) {
-            if (li == 8) { mbar_wait(vw_full, it & 1); a_base = vw_u32; }
-            else { if (li == 0) mbar_wait(pe_full, it & 1); a_base = pe_u32; }
+            if (li == 8) { if (ci == 0) mbar_wait(vw_full, it & 1); a_base = vw_u32 + ci * ACT_BLK; }
+            else { if (li == 0 && ci == 0) mbar_wait(pe_full, it & 1); a_base = pe_u32 + ci * ACT_BLK; }
           } else {
             mbar_wait(&act_full[aj], alayer & 1);
             a_base = act_u32 + aj * ACT_BLK;
           }
-          const uint32_t stage = cnt % NSTAGE;
-          mbar_wait(&w_full[stage], (cnt / NSTAGE) & 1);
+          const uint32_t stage = cnt % NS;
+          mbar_wait(&w_full[stage], (cnt / NS) & 1);
           tc_fence_after();
           const uint32_t b_base = ring_u32 + stage * CHUNK_B;
           if (elect_one()) {
@@ -293,8 +346,8 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
               umma_f16(d_tmem, umma_desc_kmajor(a_base + ks * 32), umma_desc_kmajor(b_base + ks * 32), idesc,
                        (ci > 0 || ks > 0) ? 1u : 0u);
             umma_commit(&w_empty[stage]);
-            if (aj < 0 && li == 5) umma_commit(pe_empty);
-            if (aj < 0 && li == 8) umma_commit(vw_empty);
+            if (aj == -1 && li == 5) umma_commit(pe_empty);      // the image's last chunk has been read
+            if (aj == -1 && li == 8) umma_commit(vw_empty);
             if (ci == nch - 1) umma_commit(&d_full[dcnt & 1]);
           }
           __syncwarp();
@@ -449,27 +502,33 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
         }
       }
       float f[64];
-      encode3<10, 64>(pos, f);
-      if (!valid) {
+      for (int ch = 0; ch < PC; ++ch) {
+        if (MODE == 0) encode3<10, 0>(pos, f); else encode3_any(g.Lp, ch, pos, f);
+        if (!valid) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) f[i] = 0.f;
+          for (int i = 0; i < 64; ++i) f[i] = 0.f;
+        }
+        if (ch == 0) {             // (after the first chunk's arithmetic: it overlaps the wait)
+          if (it > 0) mbar_wait(pe_empty, (it - 1) & 1);
+          if (TRAIN && it > 0) {
+            if (p0) bulk_wait_read0();
+            named_bar_sync(2, 128);
+          }
+        }
+        store_row64(s_pe + ch * ACT_BLK, p, f);
       }
-      if (it > 0) mbar_wait(pe_empty, (it - 1) & 1);
-      if (TRAIN && it > 0) {
-        if (p0) bulk_wait_read0();
-        named_bar_sync(2, 128);
-      }
-      store_row64(s_pe, p, f);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(pe_full);
-      encode3<4, 64>(dir, f);
-      if (!valid) {
+      for (int ch = 0; ch < VC; ++ch) {
+        if (MODE == 0) encode3<4, 0>(dir, f); else encode3_any(g.Lv, ch, dir, f);
+        if (!valid) {
 #pragma unroll
-        for (int i = 0; i < 64; ++i) f[i] = 0.f;
+          for (int i = 0; i < 64; ++i) f[i] = 0.f;
+        }
+        if (ch == 0 && it > 0) mbar_wait(vw_empty, (it - 1) & 1);
+        store_row64(s_vw + ch * ACT_BLK, p, f);
       }
-      if (it > 0) mbar_wait(vw_empty, (it - 1) & 1);
-      store_row64(s_vw, p, f);
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(vw_full);
@@ -479,6 +538,11 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
           uint8_t* ws_tile = g.ws + tile * WS_TILE_BYTES;
           bulk_s2g(ws_tile + WS_PE_OFF, s_pe, ACT_BLK);
           bulk_s2g(ws_tile + WS_VW_OFF, s_vw, ACT_BLK);
+          if (MODE == 2) {       // second blocks of the images (zero when the encoding has one chunk)
+            uint8_t* ext = g.ws_ext + tile * (2 * (int64_t)ACT_BLK);
+            if (PC > 1) bulk_s2g(ext, s_pe + ACT_BLK, ACT_BLK);
+            if (VC > 1) bulk_s2g(ext + ACT_BLK, s_vw + ACT_BLK, ACT_BLK);
+          }
           bulk_commit();
         }
       }
@@ -543,7 +607,8 @@ __constant__ float c_f32s[F32_SLOTS][F32_PAD];
 // completion (tcgen05.commit) is multicast to the same barrier offset in both CTAs.
 // Shared memory per CTA: 2 x 64 KB activation images, 2 x 16 KB encoding images (PE until the skip layer has read
 // it, then the view encoding for the head), 3 x 16 KB weight ring.
-template <bool TRAIN>
+// DEFENC: the default encoding (PE L = 10 / 4) at compile time; otherwise a one-chunk encoding chosen at run time.
+template <bool TRAIN, bool DEFENC>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_kernel(const __grid_constant__ FwdArgs g, const __grid_constant__ CUtensorMap tm_trunk,
                                                                                    const __grid_constant__ CUtensorMap tm_head) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -848,7 +913,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
           }
         }
         float f[64];
-        encode3<10, 64>(pos, f);
+        if (DEFENC) encode3<10, 0>(pos, f); else encode3_any(g.Lp, 0, pos, f);
         if (!valid) {
 #pragma unroll
           for (int i = 0; i < 64; ++i) f[i] = 0.f;
@@ -874,7 +939,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(512, 1) mlp_fwd4_ker
         const int64_t tile = quad * 4 + t * 2 + rank;
         const bool valid = tile * TILE + p < g.P;
         float f[64];
-        encode3<4, 64>(dirs[t], f);
+        if (DEFENC) encode3<4, 0>(dirs[t], f); else encode3_any(g.Lv, 0, dirs[t], f);
         if (!valid) {
 #pragma unroll
           for (int i = 0; i < 64; ++i) f[i] = 0.f;
@@ -940,25 +1005,27 @@ extern "C" {
 
 int64_t swnerf_tc_packed_bytes(void) { return PK_TOTAL_BYTES; }
 
-int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training) {
-  if (!training || n_points <= 0) return 0;
+int64_t swnerf_tc_workspace_bytes(int64_t n_points, int training, int enc) {
+  Enc E;
+  if (!training || n_points <= 0 || !decode_enc(enc, &E)) return 0;
   int64_t tiles = (n_points + TILE - 1) / TILE;
-  return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES) + WS_TAIL_BYTES;
+  return tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES) + WS_TAIL_BYTES + (E.wide() ? tiles * WS_EXT_BYTES : 0);
 }
 
-static int pack_impl(const float* const* params, int kind, const float* tpe_host, void* packed, void* stream) {
+static int pack_impl(const float* const* params, int kind, const float* tpe_host, int enc, void* packed, void* stream) {
   SW_REQUIRE(params && packed, "tc_pack_weights: null pointer");
   SW_REQUIRE(kind == 0 || kind == 1, "tc_pack_weights: kind must be 0 (canonical net) or 1 (deformation net)");
   SW_REQUIRE(kind == 0 || tpe_host, "tc_pack_weights: the deformation net needs the time embedding");
   SW_REQUIRE(aligned16(packed), "tc_pack_weights: packed must be 16-byte aligned");
   ParamPtrs P;
+  SW_REQUIRE(decode_enc(enc, &P.enc), "tc_pack_weights: unsupported encoding code 0x%x (SWNERF_TC_ENC: L in {0, 4, 10, 20})", enc);
   const int np = kind == 0 ? 24 : 18;
   for (int i = 0; i < 24; ++i) {
     SW_REQUIRE(i >= np || params[i], "tc_pack_weights: null parameter %d", i);
     P.p[i] = i < np ? params[i] : nullptr;
   }
   P.kind = kind;
-  for (int i = 0; i < 24; ++i) P.tpe[i] = (kind == 1 && i < 21) ? tpe_host[i] : 0.f;
+  for (int i = 0; i < ENC_MAX_TW + 3; ++i) P.tpe[i] = (kind == 1 && i < P.enc.tw) ? tpe_host[i] : 0.f;
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
   fold_head_kernel<<<36, 1024, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
@@ -968,13 +1035,13 @@ static int pack_impl(const float* const* params, int kind, const float* tpe_host
   return check_launch("tc_pack_weights");
 }
 
-int swnerf_tc_pack_weights(const float* const* params, void* packed, void* stream) {
-  return pack_impl(params, 0, nullptr, packed, stream);
+int swnerf_tc_pack_weights(const float* const* params, int enc, void* packed, void* stream) {
+  return pack_impl(params, 0, nullptr, enc, packed, stream);
 }
 
-int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host21, void* packed,
+int swnerf_tc_pack_weights_time(const float* const* params, const float* time_embedding_host, int enc, void* packed,
                                 void* stream) {
-  return pack_impl(params, 1, time_embedding_host21, packed, stream);
+  return pack_impl(params, 1, time_embedding_host, enc, packed, stream);
 }
 
 // Tensor maps over the packed weight image seen as rows of 128 bytes: boxes of 128 rows (half a trunk chunk) and 72
@@ -1006,8 +1073,18 @@ static int stage_f32_block(const uint8_t* src, cudaStream_t s, int* slot_out) {
 // SWNERF_FWD_PAIR=0/1 presets it.
 static std::atomic<int> g_fwd_variant{[] { const char* e = getenv("SWNERF_FWD_PAIR"); return e ? (atoi(e) ? 1 : 0) : -1; }()};
 
+}  // extern "C"
+
+template <bool TRAIN, int MODE>
+static int launch_fwd1(const FwdArgs& g, int grid, cudaStream_t s) {
+  if (once_per_device(ONCE_FWD1_BASE + (TRAIN ? 3 : 0) + MODE))
+    cudaFuncSetAttribute(mlp_fwd_kernel<TRAIN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Fwd1Smem<MODE>::TOTAL);
+  mlp_fwd_kernel<TRAIN, MODE><<<grid, 512, Fwd1Smem<MODE>::TOTAL, s>>>(g);
+  return check_launch("tc_mlp_fwd");
+}
+
 static int fwd_impl(const float* rays, int ray_stride, int view_col, const float* z_vals, const float* pts,
-                    int64_t n_rays, int n_samples, const void* packed, float* out, void* workspace, int training,
+                    int64_t n_rays, int n_samples, const void* packed, int enc, float* out, void* workspace, int training,
                     int kind, void* stream) {
   SW_REQUIRE(rays && packed && out && (z_vals || pts), "tc_mlp_fwd: null pointer");
   SW_REQUIRE(view_col >= 0 && view_col + 3 <= ray_stride, "tc_mlp_fwd: the fused kernel needs viewdirs in the ray batch");
@@ -1015,23 +1092,32 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
   SW_REQUIRE(aligned16(out) || kind == 1, "tc_mlp_fwd: raw must be 16-byte aligned");
   SW_REQUIRE(aligned16(packed) && aligned16(workspace), "tc_mlp_fwd: buffers must be 16-byte aligned");
   SW_REQUIRE(n_samples >= 1 && n_rays >= 0, "tc_mlp_fwd: bad sizes");
+  Enc E;
+  SW_REQUIRE(decode_enc(enc, &E), "tc_mlp_fwd: unsupported encoding code 0x%x", enc);
   if (n_rays == 0) return SWNERF_OK;
   FwdArgs g;
   g.rays = rays; g.ray_stride = ray_stride; g.view_col = view_col; g.z = z_vals; g.S = n_samples;
   g.P = n_rays * n_samples; g.pts = pts; g.packed = reinterpret_cast<const uint8_t*>(packed); g.raw = out;
   g.ws = reinterpret_cast<uint8_t*>(workspace); g.num_tiles = (g.P + TILE - 1) / TILE; g.kind = kind; g.f32_slot = 0;
+  g.Lp = E.Lp; g.Lv = E.Lv; g.PC = E.PC; g.VC = E.VC;
+  g.ws_ext = (training && E.wide())
+      ? g.ws + g.num_tiles * (WS_TILE_BYTES + WS_MASK_BYTES + WS_DY_BYTES) + WS_TAIL_BYTES : nullptr;
 #ifdef SWNERF_EXPERIMENTS
   { static const char* ko = getenv("SWNERF_KO"); g.ko = ko ? atoi(ko) : 0; }
 #endif
   int grid = (int)(g.num_tiles < sm_count() ? g.num_tiles : sm_count());
   cudaStream_t s = (cudaStream_t)stream;
   const int variant = g_fwd_variant.load();
+  const bool defenc = enc == ENC_DEFAULT_CODE;
   // automatic: a launch that does not fill the GPU twice over runs one tile per CTA (a pair CTA works through its two
-  // slots back to back: 0.055 vs 0.033 ms at 128 tiles; equal from ~500 tiles; 17 % faster at 6144)
-  if (variant == 1 || (variant < 0 && g.num_tiles > 2 * (int64_t)sm_count())) {        // CTA-pair kernel
+  // slots back to back: 0.055 vs 0.033 ms at 128 tiles; equal from ~500 tiles; 17 % faster at 6144).  Two-chunk
+  // encodings always run one CTA per tile: the pair kernel's shared memory has no room for 32-KB encoding images.
+  if (!E.wide() && (variant == 1 || (variant < 0 && g.num_tiles > 2 * (int64_t)sm_count()))) {        // CTA-pair kernel
     if (once_per_device(ONCE_FWD4)) {
-      cudaFuncSetAttribute(mlp_fwd4_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
-      cudaFuncSetAttribute(mlp_fwd4_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+      cudaFuncSetAttribute(mlp_fwd4_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+      cudaFuncSetAttribute(mlp_fwd4_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+      cudaFuncSetAttribute(mlp_fwd4_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
+      cudaFuncSetAttribute(mlp_fwd4_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S4_TOTAL);
     }
     const int64_t num_quads = (g.num_tiles + 3) / 4;
     const int grid4 = 2 * (int)(num_quads < sm_count() / 2 ? num_quads : sm_count() / 2);
@@ -1040,21 +1126,21 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
     if (rc) return rc;
     rc = stage_f32_block(reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF, s, &g.f32_slot);
     if (rc) return rc;
-    if (training) mlp_fwd4_kernel<true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
-    else mlp_fwd4_kernel<false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+    if (training) {
+      if (defenc) mlp_fwd4_kernel<true, true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+      else mlp_fwd4_kernel<true, false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+    } else {
+      if (defenc) mlp_fwd4_kernel<false, true><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+      else mlp_fwd4_kernel<false, false><<<grid4, 512, S4_TOTAL, s>>>(g, tm_trunk, tm_head);
+    }
     return check_launch("tc_mlp_fwd");
   }
-  if (training) {
-    if (once_per_device(ONCE_FWD1_TRAIN))
-      cudaFuncSetAttribute(mlp_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    mlp_fwd_kernel<true><<<grid, 512, SM_TOTAL, s>>>(g);
-  } else {
-    if (once_per_device(ONCE_FWD1_INFER))
-      cudaFuncSetAttribute(mlp_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SM_TOTAL);
-    mlp_fwd_kernel<false><<<grid, 512, SM_TOTAL, s>>>(g);
-  }
-  return check_launch("tc_mlp_fwd");
+  const int mode = E.wide() ? 2 : (defenc ? 0 : 1);
+  if (training) return mode == 0 ? launch_fwd1<true, 0>(g, grid, s) : mode == 1 ? launch_fwd1<true, 1>(g, grid, s) : launch_fwd1<true, 2>(g, grid, s);
+  return mode == 0 ? launch_fwd1<false, 0>(g, grid, s) : mode == 1 ? launch_fwd1<false, 1>(g, grid, s) : launch_fwd1<false, 2>(g, grid, s);
 }
+
+extern "C" {
 
 int swnerf_tc_set_fwd_variant(int variant) {
   SW_REQUIRE(variant >= -1 && variant <= 1, "tc_set_fwd_variant: variant must be -1 (automatic), 0 or 1");
@@ -1063,27 +1149,27 @@ int swnerf_tc_set_fwd_variant(int variant) {
 }
 
 int swnerf_tc_mlp_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
-                      int n_samples, const void* packed, float* raw, void* workspace, int training,
+                      int n_samples, const void* packed, int enc, float* raw, void* workspace, int training,
                       void* stream) {
   SW_REQUIRE(z_vals, "tc_mlp_fwd: null pointer");
-  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed, raw, workspace, training, 0,
-                  stream);
+  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed, enc, raw, workspace, training,
+                  0, stream);
 }
 
 int swnerf_tc_mlp_fwd_points(const float* rays, int ray_stride, int view_col, const float* pts, int64_t n_rays,
-                             int n_samples, const void* packed, float* raw, void* workspace, int training,
+                             int n_samples, const void* packed, int enc, float* raw, void* workspace, int training,
                              void* stream) {
   SW_REQUIRE(pts, "tc_mlp_fwd_points: null pointer");
-  return fwd_impl(rays, ray_stride, view_col, nullptr, pts, n_rays, n_samples, packed, raw, workspace, training, 0,
+  return fwd_impl(rays, ray_stride, view_col, nullptr, pts, n_rays, n_samples, packed, enc, raw, workspace, training, 0,
                   stream);
 }
 
 int swnerf_tc_time_fwd(const float* rays, int ray_stride, int view_col, const float* z_vals, int64_t n_rays,
-                       int n_samples, const void* packed_time, float* dx, void* workspace, int training,
+                       int n_samples, const void* packed_time, int enc, float* dx, void* workspace, int training,
                        void* stream) {
   SW_REQUIRE(z_vals, "tc_time_fwd: null pointer");
-  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed_time, dx, workspace, training,
-                  1, stream);
+  return fwd_impl(rays, ray_stride, view_col, z_vals, nullptr, n_rays, n_samples, packed_time, enc, dx, workspace,
+                  training, 1, stream);
 }
 
 }  // extern "C"

@@ -30,6 +30,7 @@ using namespace tcl;
 struct ParamPtrsB {
   const float* p[24];
   int kind;            // 0: canonical net (24 tensors); 1: deformation net (_time.0..7, _time_out), see mlp_tc.cu
+  Enc enc;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -44,7 +45,7 @@ __device__ __forceinline__ float bwd_weight(const ParamPtrsB& P, const float* fo
   }
   int t = (c - 3) / 4, kc = (c - 3) % 4;
   int l = 7 - t;                                                  // 7,6,5,4,3,2,1
-  int ld = (l == 5) ? 319 : 256, off = (l == 5) ? 63 : 0;
+  int ld = (l == 5) ? 256 + P.enc.pc : 256, off = (l == 5) ? P.enc.pc : 0;      // pts_linears.5 is [256, pc + 256]
   return P.p[2 * l][(size_t)(kc * 64 + k) * ld + off + n];
 }
 
@@ -62,18 +63,22 @@ __global__ void pack_bwd_kernel(ParamPtrsB P, const uint8_t* __restrict__ packed
 #pragma unroll
     for (int i = 0; i < 8; ++i) h[i] = __float2half_rn(bwd_weight(P, fold, c, n, k0 + i));
   } else {
-    // input-gradient weights: chunk (layer 0 | 5, kc): image row = pe column c, image column = unit kc*64 + k
+    // input-gradient weights, one group of eight [64 x 64] images per 64-column chunk of the position encoding:
+    // chunk (layer 0 | 5, kc): image row = pe column c (inside the chunk), image column = unit kc*64 + k
     int b2 = byte - PKT_DPE_OFF;
-    int ch = b2 / DPE_CHUNK_B, in = b2 % DPE_CHUNK_B;
+    int grp = b2 / (8 * DPE_CHUNK_B);
+    int ch = (b2 / DPE_CHUNK_B) & 7, in = b2 % DPE_CHUNK_B;
     int cc = (in >> 10) * 8 + ((in >> 7) & 7);
     int pu = (in >> 4) & 7;
     int k0 = (pu ^ (cc & 7)) * 8;
     const float* Wl = (ch < 4) ? P.p[0] : P.p[10];
-    int ld = (ch < 4) ? (P.kind == 1 ? 84 : 63) : 319;
+    const int pc = P.enc.pc;
+    int ld = (ch < 4) ? pc + (P.kind == 1 ? P.enc.tw : 0) : 256 + pc;
+    const int col = grp * 64 + cc;
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       int nn = (ch & 3) * 64 + k0 + i;
-      h[i] = __float2half_rn(cc < 63 ? Wl[(size_t)nn * ld + cc] : 0.f);
+      h[i] = __float2half_rn(col < pc ? Wl[(size_t)nn * ld + col] : 0.f);
     }
   }
   *reinterpret_cast<uint4*>(packed_t + byte) = *reinterpret_cast<const uint4*>(h);
@@ -590,10 +595,10 @@ mlp_bwd_data_pair_kernel(const __grid_constant__ BwdArgs g, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 // 2. backward weights
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_MAX_PIECES = 4, WG_MAX_MMA = 5, WG_JOBS = 9;
+constexpr int WG_MAX_PIECES = 5, WG_MAX_MMA = 5, WG_JOBS = 9;
 
 struct WgPiece {      // one operand of a job: nblk 64-column blocks of a saved tile image
-  int from_dy;        // 0: forward workspace tile, 1: dy workspace tile
+  int from_dy;        // 0: forward workspace tile, 1: dy workspace tile, 2: the tile's record of second encoding blocks
   int tile_off;       // byte offset of block 0 inside the tile record
   int nblk;
   int smem_off;       // inside the stage (each block contributes 8 KB = 64 samples x 128 B)
@@ -621,17 +626,23 @@ struct WgJob {
 };
 struct WgArgs {
   uint8_t* ws; int64_t num_tiles;
+  uint8_t* ws_ext;                           // two-chunk encodings (WS_EXT_BYTES per tile), else unused
   float* grads[24]; float* unfold;
   const uint32_t* absmax; float fixed_scale;
   int job_first_cta[WG_JOBS + 1];
   int kind;
 };
 constexpr int WG_JOBS_ALL = WG_JOBS + 2;     // + the two halves of job 0 as separate jobs (layer-pipelined kernel)
-__constant__ WgJob c_jobs[2][WG_JOBS_ALL];   // [kind]
+// The job table depends on the network kind and on the encoding widths (leading dimensions, column counts, one or two
+// encoding blocks): the host builds it per call and hands it to the kernels as a parameter (3.5 KB of the constant
+// bank).  The layer-pipelined kernel serves the default encoding only and keeps its copy in c_jobs.
+struct WgJobTable { WgJob j[WG_JOBS_ALL]; };
+__constant__ WgJob c_jobs[2][WG_JOBS_ALL];   // [kind], default encoding (mlp_bwd_lw_kernel)
 
 constexpr int HALF_BLK = 64 * 128;     // 64 samples of one 64-column block
 
-__global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
+__global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_constant__ WgArgs g,
+                                                                const __grid_constant__ WgJobTable T) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ uint64_t s_full[3], s_empty[3], s_done;
@@ -640,7 +651,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
 
   int job = 0;
   while (job + 1 < WG_JOBS && (int)blockIdx.x >= g.job_first_cta[job + 1]) ++job;
-  const WgJob& J = c_jobs[g.kind][job];
+  const WgJob& J = T.j[job];
   const int ncta = g.job_first_cta[job + 1] - g.job_first_cta[job];
   const int cta = blockIdx.x - g.job_first_cta[job];
   const int64_t t_begin = g.num_tiles * cta / ncta, t_end = g.num_tiles * (cta + 1) / ncta;
@@ -672,8 +683,9 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(WgArgs g) {
         uint8_t* dst = smem + stage * J.stage_bytes;
         for (int p = 0; p < J.npieces; ++p) {
           const WgPiece& pc = J.pc[p];
-          const uint8_t* src = g.ws + (pc.from_dy ? dy_base + tile * WS_DY_BYTES : tile * WS_TILE_BYTES) + pc.tile_off +
-                               half * HALF_BLK;
+          const uint8_t* src = (pc.from_dy == 2 ? g.ws_ext + tile * WS_EXT_BYTES
+                                : g.ws + (pc.from_dy ? dy_base + tile * WS_DY_BYTES : tile * WS_TILE_BYTES)) +
+                               pc.tile_off + half * HALF_BLK;
           for (int b = 0; b < pc.nblk; ++b)
             bulk_g2s(dst + pc.smem_off + b * HALF_BLK, src + (size_t)b * ACT_BLK, HALF_BLK, &s_full[stage]);
         }
@@ -804,10 +816,11 @@ struct WgPairMaps { CUtensorMap fwd, dy; };      // workspace as [16-KB block][1
 constexpr int WGP_STAGE = 4 * HALF_BLK;           // dy half (2 blocks) | x half (2 blocks), 64 samples each
 constexpr int WGP_NST = 6;
 constexpr int WGP_SMEM = WGP_NST * WGP_STAGE + HALF_BLK + 1024;      // + ones block + alignment slack
-constexpr int WGP_JOBS = 7;                       // c_jobs[kind][1..7]
+constexpr int WGP_JOBS = 7;                       // jobs 1..7 of the table
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_constant__ WgPairMaps tm) {
+mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_constant__ WgPairMaps tm,
+                           const __grid_constant__ WgJobTable T) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* s_ones = smem + WGP_NST * WGP_STAGE;
@@ -845,7 +858,7 @@ mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_co
       for (int64_t w = w_begin; w < w_end; ++w) {
         const int job = 1 + (int)(w / g.num_tiles);
         const int64_t tile = w % g.num_tiles;
-        const WgJob& J = c_jobs[g.kind][job];
+        const WgJob& J = T.j[job];
         const int dy_blk = (int)(tile * 36) + J.pc[0].tile_off / ACT_BLK + 2 * (int)rank;
         const int x_blk = (int)(tile * 36) + J.pc[1].tile_off / ACT_BLK + 2 * (int)rank;
         for (int half = 0; half < 2; ++half, ++cnt) {
@@ -899,7 +912,7 @@ mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_co
       const int job = 1 + (int)(w / g.num_tiles);
       int64_t seg_end = (int64_t)job * g.num_tiles;            // first work item of the next layer
       if (seg_end > w_end) seg_end = w_end;
-      const WgJob& J = c_jobs[g.kind][job];
+      const WgJob& J = T.j[job];
       const WgMma& mm = J.mm[rank];
       mbar_wait(&s_done, seg & 1);
       tc_fence_after();
@@ -940,7 +953,8 @@ mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_co
 __global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restrict__ Wv, const float* __restrict__ Wf,
                                                             const float* __restrict__ bf, const float* __restrict__ G,
                                                             const float* __restrict__ gb, float* __restrict__ dWf,
-                                                            float* __restrict__ dbf, float* __restrict__ dWv) {
+                                                            float* __restrict__ dbf, float* __restrict__ dWv,
+                                                            int ldv /* 256 + view columns */) {
   __shared__ float As[32][33], Bs[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   int t = blockIdx.x;
@@ -948,7 +962,7 @@ __global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restri
   if (t < 64) {                       // dW_f tile (c0, k0), reduce over u
     const int c0 = (t >> 3) * 32, k0 = (t & 7) * 32;
     for (int u0 = 0; u0 < 128; u0 += 32) {
-      As[ty][tx] = Wv[(size_t)(u0 + ty) * 283 + c0 + tx];
+      As[ty][tx] = Wv[(size_t)(u0 + ty) * ldv + c0 + tx];
       Bs[ty][tx] = G[(size_t)(u0 + ty) * 256 + k0 + tx];
       __syncthreads();
 #pragma unroll
@@ -968,11 +982,11 @@ __global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restri
       __syncthreads();
     }
     acc = fmaf(gb[u0 + ty], bf[c0 + tx], acc);
-    atomicAdd(dWv + (size_t)(u0 + ty) * 283 + c0 + tx, acc);
+    atomicAdd(dWv + (size_t)(u0 + ty) * ldv + c0 + tx, acc);
   } else {                            // db_f
     t -= 96;
     const int c = t * 32 + tx;
-    for (int u = ty; u < 128; u += 32) acc = fmaf(Wv[(size_t)u * 283 + c], gb[u], acc);
+    for (int u = ty; u < 128; u += 32) acc = fmaf(Wv[(size_t)u * ldv + c], gb[u], acc);
     As[ty][tx] = acc;
     __syncthreads();
     if (ty == 0) {
@@ -995,6 +1009,8 @@ struct DpeArgs {
   const uint32_t* absmax; float fixed_scale;
 };
 
+// One launch per 64-column chunk GRP of the position encoding (L = 20: two launches, the second accumulates).
+template <int L, int GRP>
 __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -1013,7 +1029,7 @@ __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
   const float inv = 1.f / grad_scale_from(g.absmax, g.fixed_scale);
   if (threadIdx.x == 128) {
     mbar_expect_tx(&b_w, 8 * DPE_CHUNK_B);
-    bulk_g2s(s_w, g.packed_t + PKT_DPE_OFF, 8 * DPE_CHUNK_B, &b_w);
+    bulk_g2s(s_w, g.packed_t + PKT_DPE_OFF + GRP * 8 * DPE_CHUNK_B, 8 * DPE_CHUNK_B, &b_w);
   }
   uint32_t it = 0;
   for (int64_t tile = blockIdx.x; tile < g.num_tiles; tile += gridDim.x, ++it) {
@@ -1050,17 +1066,24 @@ __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
         float d[64];
 #pragma unroll
         for (int i = 0; i < 32; ++i) { d[i] = __uint_as_float(va[i]); d[32 + i] = __uint_as_float(vb[i]); }
+        constexpr int lo = 64 * GRP, hi = lo + 64;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           float x = __ldg(g.pts + idx * 3 + j);
-          float acc = d[j];
+          float acc = GRP == 0 ? d[j] : 0.f;
 #pragma unroll
-          for (int k = 0; k < 10; ++k) {
-            float f = (float)(1 << k), sn, cs;
-            sincosf(x * f, &sn, &cs);
-            acc += f * (cs * d[3 + 6 * k + j] - sn * d[6 + 6 * k + j]);
+          for (int k = 0; k < L; ++k) {
+            const int cs = 3 + 6 * k + j, cc = 6 + 6 * k + j;       // columns of sin / cos (2^k x_j): compile-time once unrolled
+            const bool s_in = cs >= lo && cs < hi, c_in = cc >= lo && cc < hi;
+            if (s_in || c_in) {
+              float f = (float)(1 << k), sn, cs_;
+              sincosf(x * f, &sn, &cs_);
+              if (s_in) acc += f * cs_ * d[s_in ? cs - lo : 0];
+              if (c_in) acc -= f * sn * d[c_in ? cc - lo : 0];
+            }
           }
-          g.d_pts[idx * 3 + j] = acc * inv;
+          if (GRP == 0) g.d_pts[idx * 3 + j] = acc * inv;
+          else g.d_pts[idx * 3 + j] += acc * inv;
         }
       }
       tc_fence_before();
@@ -1661,26 +1684,29 @@ static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the 
     J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 256, m * 256, 2 * l, m * 128 * ld + col_off, ld, 1, 256};
 }
 
-static void build_jobs(WgJob* jobs, int kind) {
+static void build_jobs(WgJob* jobs, int kind, const Enc& E) {
   memset(jobs, 0, sizeof(WgJob) * WG_JOBS_ALL);
-  const int ld0 = kind == 1 ? 84 : 63;               // pts_linears.0 is [256, 63]; _time.0 is [256, 63 + 21]
-  // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :63], dW5[:, :63]
+  const int pc = E.pc, vc = E.vc, PC = E.PC, VC = E.VC;
+  const int ld0 = pc + (kind == 1 ? E.tw : 0);       // pts_linears.0 is [256, pc]; _time.0 is [256, pc + tw]
+  const int ld5 = 256 + pc;                          // pts_linears.5 is [256, pc + 256]
+  // job 0: PE inputs of layer 0 and of the skip layer 5:  dW0[:, :pc], dW5[:, :pc].  stage: dy0 (4 blk) | dy5 (4) | PE (PC)
   {
     WgJob& J = jobs[0];
-    J.npieces = 3; J.nmma = 4; J.nbias = 2; J.stage_bytes = 9 * HALF_BLK; J.nstage = 3;
+    J.npieces = 2 + PC; J.nmma = 4; J.nbias = 2; J.stage_bytes = (8 + PC) * HALF_BLK; J.nstage = PC > 1 ? 2 : 3;
     J.bs[0] = {0, 256, 256, kind == 1 ? -2 : 1, 0};  // db of pts_linears.0 (deformation net: also kept per call, see bwd_impl)
     J.bs[1] = {4 * HALF_BLK, 256, 256, 11, 0};       // db of pts_linears.5
     J.pc[0] = {1, 0 * ACT_BYTES, 4, 0};
     J.pc[1] = {1, 5 * ACT_BYTES, 4, 4 * HALF_BLK};
     J.pc[2] = {0, WS_PE_OFF, 1, 8 * HALF_BLK};
+    if (PC > 1) J.pc[3] = {2, 0, 1, 9 * HALF_BLK};   // second 64 columns of the position encoding
     for (int a = 0; a < 2; ++a)
       for (int m = 0; m < 2; ++m)
-        J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64, (a * 2 + m) * 64,
-                           a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : 319), a == 0 ? ld0 : 319, 1, 63};
+        J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64 * PC, (a * 2 + m) * 64 * PC,
+                           a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : ld5), a == 0 ? ld0 : ld5, 1, pc};
   }
-  // jobs 9 / 10: the two halves of job 0 on their own (dy0 with PE -> dW0[:, :63], db0;  dy5 with PE -> dW5[:, :63],
+  // jobs 9 / 10: the two halves of job 0 on their own (dy0 with PE -> dW0[:, :pc], db0;  dy5 with PE -> dW5[:, :pc],
   // db5).  The layer-pipelined kernel gives each its own role: a role that needed dy5 AND dy0 of a tile would hold the
-  // dy5 slot until the tile has travelled five more stages.
+  // dy5 slot until the tile has travelled five more stages.  (One-chunk encodings only.)
   for (int a = 0; a < 2; ++a) {
     WgJob& J = jobs[9 + a];
     J.npieces = 2; J.nmma = 2; J.nbias = 1; J.stage_bytes = 5 * HALF_BLK; J.nstage = 3;
@@ -1688,29 +1714,33 @@ static void build_jobs(WgJob* jobs, int kind) {
     J.pc[0] = {1, (a == 0 ? 0 : 5) * ACT_BYTES, 4, 0};
     J.pc[1] = {0, WS_PE_OFF, 1, 4 * HALF_BLK};
     for (int m = 0; m < 2; ++m)
-      J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 64, m * 64, a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : 319), a == 0 ? ld0 : 319, 1, 63};
+      J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 64, m * 64, a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : ld5), a == 0 ? ld0 : ld5, 1,
+                 pc < 64 ? pc : 64};
   }
   for (int l = 1; l <= 4; ++l) wg_std_job(jobs[l], l, WS_H_OFF + (l - 1) * ACT_BYTES, 0, 256);
-  wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, 63, 319);
+  wg_std_job(jobs[5], 5, WS_H_OFF + 4 * ACT_BYTES, pc, ld5);
   jobs[5].nbias = 0;                                 // pts_linears.5.bias is summed by job 0
   wg_std_job(jobs[6], 6, WS_H_OFF + 5 * ACT_BYTES, 0, 256);
   wg_std_job(jobs[7], 7, WS_H_OFF + 6 * ACT_BYTES, 0, 256);
-  // job 8: head.  stage: dyH (4 blk) | views (1) | h7 (4) | h9 (2)
+  // job 8: head.  stage: dyH (4 blk) | views (VC) | h7 (4) | h9 (2)
   {
     WgJob& J = jobs[8];
-    J.npieces = 4; J.nmma = 5; J.nbias = 3; J.stage_bytes = 11 * HALF_BLK; J.nstage = 2;
+    const int V = 4, H7 = 4 + VC, H9 = 8 + VC;       // first stage block of views / h7 / h9
+    J.npieces = 3 + VC; J.nmma = 5; J.nbias = 3; J.stage_bytes = (10 + VC) * HALF_BLK; J.nstage = 2;
     J.bs[0] = {0, 128, 128, -1, 0};                  // folded head bias -> gb (un-fold) and views_linears.0.bias
     J.bs[1] = {2 * HALF_BLK, 8, 1, 21, 0};           // alpha_linear.bias
     J.bs[2] = {3 * HALF_BLK, 8, 3, 23, 0};           // rgb_linear.bias
     J.pc[0] = {1, WS_DYH_OFF, 4, 0};
-    J.pc[1] = {0, WS_VW_OFF, 1, 4 * HALF_BLK};
-    J.pc[2] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, 5 * HALF_BLK};
-    J.pc[3] = {0, WS_H9_OFF, 2, 9 * HALF_BLK};
-    J.mm[0] = {0, 4 * HALF_BLK, 64, 0, 16, 256, 283, 1, 27};                 // dW_v[:, 256:283] = dy9^T views
-    J.mm[1] = {0, 5 * HALF_BLK, 256, 64, -1, 0, 256, 1, 256};                // G = dy9^T h7  (d W_fv)
-    J.mm[2] = {5 * HALF_BLK, 2 * HALF_BLK, 16, 320, 20, 0, 1, 0, 1};         // d w_alpha[0:128]   = h7^T d_sigma
-    J.mm[3] = {7 * HALF_BLK, 2 * HALF_BLK, 16, 336, 20, 128, 1, 0, 1};       // d w_alpha[128:256]
-    J.mm[4] = {9 * HALF_BLK, 3 * HALF_BLK, 16, 352, 22, 0, 1, 128, 3};       // dW_rgb[j][c] = h9^T d_rgb
+    J.pc[1] = {0, WS_VW_OFF, 1, V * HALF_BLK};
+    J.pc[2] = {0, WS_H_OFF + 7 * ACT_BYTES, 4, H7 * HALF_BLK};
+    J.pc[3] = {0, WS_H9_OFF, 2, H9 * HALF_BLK};
+    if (VC > 1) J.pc[4] = {2, ACT_BLK, 1, (V + 1) * HALF_BLK};               // second 64 columns of the view encoding
+    const int c0 = 64 * VC;                          // accumulator columns behind the view block
+    J.mm[0] = {0, V * HALF_BLK, 64 * VC, 0, 16, 256, 256 + vc, 1, vc};       // dW_v[:, 256:256+vc] = dy9^T views
+    J.mm[1] = {0, H7 * HALF_BLK, 256, c0, -1, 0, 256, 1, 256};               // G = dy9^T h7  (d W_fv)
+    J.mm[2] = {H7 * HALF_BLK, 2 * HALF_BLK, 16, c0 + 256, 20, 0, 1, 0, 1};           // d w_alpha[0:128]   = h7^T d_sigma
+    J.mm[3] = {(H7 + 2) * HALF_BLK, 2 * HALF_BLK, 16, c0 + 272, 20, 128, 1, 0, 1};   // d w_alpha[128:256]
+    J.mm[4] = {H9 * HALF_BLK, 3 * HALF_BLK, 16, c0 + 288, 22, 0, 1, 128, 3};         // dW_rgb[j][c] = h9^T d_rgb
     if (kind == 1) {
       // deformation net: only its 256->3 output layer lives in the head.  stage: dyH block 2 | h7 (4 blocks)
       memset(&J, 0, sizeof(J));
@@ -1780,10 +1810,11 @@ int swnerf_tc_last_bwd_ms(float* data_ms, float* weight_ms) {
 
 int64_t swnerf_tc_packed_t_bytes(void) { return PKT_TOTAL_BYTES; }
 
-static int pack_t_impl(const float* const* params, int kind, const void* packed, void* packed_t, void* stream) {
+static int pack_t_impl(const float* const* params, int kind, int enc, const void* packed, void* packed_t, void* stream) {
   SW_REQUIRE(params && packed && packed_t, "tc_pack_weights_t: null pointer");
   SW_REQUIRE(aligned16(packed_t), "tc_pack_weights_t: packed_t must be 16-byte aligned");
   ParamPtrsB P;
+  SW_REQUIRE(decode_enc(enc, &P.enc), "tc_pack_weights_t: unsupported encoding code 0x%x", enc);
   const int np = kind == 0 ? 24 : 18;
   for (int i = 0; i < 24; ++i) {
     SW_REQUIRE(i >= np || params[i], "tc_pack_weights_t: null parameter %d", i);
@@ -1795,16 +1826,28 @@ static int pack_t_impl(const float* const* params, int kind, const void* packed,
   return check_launch("tc_pack_weights_t");
 }
 
-int swnerf_tc_pack_weights_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
-  return pack_t_impl(params, 0, packed, packed_t, stream);
+int swnerf_tc_pack_weights_t(const float* const* params, int enc, const void* packed, void* packed_t, void* stream) {
+  return pack_t_impl(params, 0, enc, packed, packed_t, stream);
 }
-int swnerf_tc_pack_weights_time_t(const float* const* params, const void* packed, void* packed_t, void* stream) {
-  return pack_t_impl(params, 1, packed, packed_t, stream);
+int swnerf_tc_pack_weights_time_t(const float* const* params, int enc, const void* packed, void* packed_t, void* stream) {
+  return pack_t_impl(params, 1, enc, packed, packed_t, stream);
 }
 
-static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
+}  // extern "C"
+
+template <int L, int GRP>
+static int launch_input_grad(const DpeArgs& d, int grid, int smem, cudaStream_t s) {
+  if (once_per_device(ONCE_BWD_INPUT_BASE + (L == 0 ? 0 : L == 4 ? 1 : L == 10 ? 2 : 3 + GRP)))
+    cudaFuncSetAttribute(mlp_bwd_input_kernel<L, GRP>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  mlp_bwd_input_kernel<L, GRP><<<grid, 192, smem, s>>>(d);
+  return check_launch("tc_mlp_bwd_input");
+}
+
+static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const void* packed, const void* packed_t, int enc,
                     const float* const* params, void* workspace, float* const* grads, float grad_scale, int kind,
                     const float* tpe_dev, const float* pts, float* d_pts, void* stream) {
+  Enc E;
+  SW_REQUIRE(decode_enc(enc, &E), "tc_mlp_bwd: unsupported encoding code 0x%x", enc);
   SW_REQUIRE(d_out && packed && packed_t && params && workspace && grads, "tc_mlp_bwd: null pointer");
   SW_REQUIRE(aligned16(workspace) && (kind == 1 || aligned16(d_out)), "tc_mlp_bwd: buffers must be 16-byte aligned");
   SW_REQUIRE(grad_scale >= 0.f, "tc_mlp_bwd: grad_scale must be >= 0 (0 = automatic)");
@@ -1832,25 +1875,33 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   b.packed = reinterpret_cast<const uint8_t*>(packed); b.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
   b.ws = ws; b.unfold = unfold; b.absmax = absmax; b.fixed_scale = grad_scale;
   for (int i = 0; i < 24; ++i) b.grads[i] = i < np ? grads[i] : nullptr;
-  // job table: built once per process (host), uploaded once per DEVICE together with the shared-memory opt-ins
-  static WgJob jobs[2][WG_JOBS_ALL];
+  // job table of the default encoding: built once per process (host), uploaded once per DEVICE (c_jobs, read by the
+  // layer-pipelined kernel) together with the shared-memory opt-ins; this call's table (kind, encoding) is a parameter
+  static WgJobTable jobs_def[2];
   static int wg_smem = 0;
   static std::once_flag jobs_once;
   std::call_once(jobs_once, [] {
-    build_jobs(jobs[0], 0);
-    build_jobs(jobs[1], 1);
+    Enc D, Wd;
+    decode_enc(ENC_DEFAULT_CODE, &D);
+    decode_enc(20 | (20 << 8) | (20 << 16), &Wd);
+    WgJobTable wide[2];
+    for (int k = 0; k < 2; ++k) { build_jobs(jobs_def[k].j, k, D); build_jobs(wide[k].j, k, Wd); }
     for (int k = 0; k < 2; ++k)
       for (int j = 0; j < WG_JOBS_ALL; ++j) {
-        int need = jobs[k][j].stage_bytes * jobs[k][j].nstage + 1024;
+        int need = jobs_def[k].j[j].stage_bytes * jobs_def[k].j[j].nstage + 1024;
+        int need_w = wide[k].j[j].stage_bytes * wide[k].j[j].nstage + 1024;
         if (need > wg_smem) wg_smem = need;
+        if (need_w > wg_smem) wg_smem = need_w;
       }
   });
+  WgJobTable table_local;
+  const WgJobTable* table = &jobs_def[kind];
+  if (enc != ENC_DEFAULT_CODE) { build_jobs(table_local.j, kind, E); table = &table_local; }
   const int dpe_smem = 8 * DPE_CHUNK_B + 2 * ACT_BYTES + 1024;
   if (once_per_device(ONCE_BWD_BASE)) {
     cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
-    cudaMemcpyToSymbol(c_jobs, jobs, sizeof(jobs));
+    cudaMemcpyToSymbol(c_jobs, jobs_def, sizeof(jobs_def));
     cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem);
-    cudaFuncSetAttribute(mlp_bwd_input_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, dpe_smem);
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   if (g_prof) cudaEventRecord(g_ev[0], s);
@@ -1861,7 +1912,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   // by HBM (profiles/r2_lw_backward.md).  The two-kernel backward stays the default.
   const int lw_variant = g_bwd_variant.load();
   const int lw_min_ctas = 2 * LW_ROLES;
-  if (kind == 0 && !d_pts && sm_count() >= lw_min_ctas && lw_variant == 1 && tiles > 2 * (int64_t)sm_count() &&
+  if (kind == 0 && enc == ENC_DEFAULT_CODE && !d_pts && sm_count() >= lw_min_ctas && lw_variant == 1 && tiles > 2 * (int64_t)sm_count() &&
       tiles * WS_DY_BYTES >= LW_RING_BYTES) {
     const int lw_d_smem = 4 * CHUNK_B + LW_IN_BLKS * ACT_BLK + 1024;
     const int lw_smem = lw_d_smem > wg_smem ? lw_d_smem : wg_smem;
@@ -1892,7 +1943,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     rc = check_launch("tc_mlp_bwd_lw");
     if (rc) return rc;
     unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
-                                            grads[19], grads[16]);
+                                            grads[19], grads[16], 256 + E.vc);
     return check_launch("tc_unfold_head");
   }
   static const int dg_variant = [] { const char* e = getenv("SWNERF_BWD_PAIR"); return e ? atoi(e) : -1; }();
@@ -1918,13 +1969,21 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     DpeArgs d;
     d.ws = ws; d.num_tiles = tiles; d.P = P; d.packed_t = reinterpret_cast<const uint8_t*>(packed_t);
     d.pts = pts; d.d_pts = d_pts; d.absmax = absmax; d.fixed_scale = grad_scale;
-    mlp_bwd_input_kernel<<<grid, 192, dpe_smem, s>>>(d);
-    rc = check_launch("tc_mlp_bwd_input");
+    switch (E.Lp) {
+      case 0: rc = launch_input_grad<0, 0>(d, grid, dpe_smem, s); break;
+      case 4: rc = launch_input_grad<4, 0>(d, grid, dpe_smem, s); break;
+      case 10: rc = launch_input_grad<10, 0>(d, grid, dpe_smem, s); break;
+      default:
+        rc = launch_input_grad<20, 0>(d, grid, dpe_smem, s);
+        if (!rc) rc = launch_input_grad<20, 1>(d, grid, dpe_smem, s);        // columns 64..122 of the encoding: accumulates
+        break;
+    }
     if (rc) return rc;
   }
 
   WgArgs w;
   w.ws = ws; w.num_tiles = tiles; w.unfold = unfold; w.absmax = absmax; w.fixed_scale = grad_scale; w.kind = kind;
+  w.ws_ext = E.wide() ? tail + WS_TAIL_BYTES : nullptr;
   for (int i = 0; i < 24; ++i) w.grads[i] = i < np ? grads[i] : nullptr;
   int n_cta = sm_count();
   if (n_cta < WG_JOBS) n_cta = WG_JOBS;
@@ -1948,12 +2007,12 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     rc = encode_u8_tensor_map(&maps.dy, ws + tiles * (WS_TILE_BYTES + WS_MASK_BYTES), 3, dims, strides, box);
     if (rc) return rc;
     const int n_pair_ctas = (sm_count() / 2) * 2;
-    mlp_bwd_weight_pair_kernel<<<n_pair_ctas, 256, WGP_SMEM, s>>>(pw, maps);
+    mlp_bwd_weight_pair_kernel<<<n_pair_ctas, 256, WGP_SMEM, s>>>(pw, maps, *table);
     rc = check_launch("tc_mlp_bwd_weight_pair");
     if (rc) return rc;
     if (g_prof) cudaEventRecord(g_ev[3], s);
   }
-  mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w);
+  mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w, *table);
   if (g_prof) { cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
   rc = check_launch("tc_mlp_bwd_weight");
   if (rc) return rc;
@@ -1961,35 +2020,37 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   if (kind == 0) {
     // un-fold the head: G = d W_fv, gb = d b_fv -> feature_linear / views_linears gradients (db_v was added above)
     unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
-                                            grads[19], grads[16]);
+                                            grads[19], grads[16], 256 + E.vc);
     rc = check_launch("tc_unfold_head");
   } else {
-    // _time.0.weight[:, 63:84]: the time embedding is the same for every sample, so this block of the gradient
+    // _time.0.weight[:, pc:pc+tw]: the time embedding is the same for every sample, so this block of the gradient
     // is the outer product (sum_s dy0[s]) x PE(t) = d b0 x PE(t); this call's d b0 sits in the scratch.
-    rc = swnerf_sgemm(0, unfold, 1, tpe_dev, 1, grads[0] + 63, 84, 256, 21, 1, nullptr, 1, 0, nullptr, 0, stream);
+    rc = swnerf_sgemm(0, unfold, 1, tpe_dev, 1, grads[0] + E.pc, E.pc + E.tw, 256, E.tw, 1, nullptr, 1, 0, nullptr, 0, stream);
   }
   return rc;
 }
 
+extern "C" {
+
 int swnerf_tc_mlp_bwd(const float* d_raw, int64_t n_rays, int n_samples, const void* packed, const void* packed_t,
-                      const float* const* params, void* workspace, float* const* grads, float grad_scale,
+                      int enc, const float* const* params, void* workspace, float* const* grads, float grad_scale,
                       void* stream) {
-  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, params, workspace, grads, grad_scale, 0, nullptr, nullptr,
-                  nullptr, stream);
+  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, enc, params, workspace, grads, grad_scale, 0, nullptr,
+                  nullptr, nullptr, stream);
 }
 
 int swnerf_tc_mlp_bwd_points(const float* d_raw, int64_t n_rays, int n_samples, const void* packed,
-                             const void* packed_t, const float* const* params, void* workspace, float* const* grads,
-                             float grad_scale, const float* pts, float* d_pts, void* stream) {
-  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, params, workspace, grads, grad_scale, 0, nullptr, pts,
+                             const void* packed_t, int enc, const float* const* params, void* workspace,
+                             float* const* grads, float grad_scale, const float* pts, float* d_pts, void* stream) {
+  return bwd_impl(d_raw, n_rays, n_samples, packed, packed_t, enc, params, workspace, grads, grad_scale, 0, nullptr, pts,
                   d_pts, stream);
 }
 
 int swnerf_tc_time_bwd(const float* d_dx, int64_t n_rays, int n_samples, const void* packed_time,
-                       const void* packed_time_t, const float* const* params, const float* time_embedding_dev21,
+                       const void* packed_time_t, int enc, const float* const* params, const float* time_embedding_dev,
                        void* workspace, float* const* grads, float grad_scale, void* stream) {
-  return bwd_impl(d_dx, n_rays, n_samples, packed_time, packed_time_t, params, workspace, grads, grad_scale, 1,
-                  time_embedding_dev21, nullptr, nullptr, stream);
+  return bwd_impl(d_dx, n_rays, n_samples, packed_time, packed_time_t, enc, params, workspace, grads, grad_scale, 1,
+                  time_embedding_dev, nullptr, nullptr, stream);
 }
 
 }  // extern "C"

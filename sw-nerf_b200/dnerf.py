@@ -70,13 +70,17 @@ class DNerfNetworkQuery:
         self.precision = precision or os.environ.get("SWNERF_PRECISION", "tc")
         if self.precision not in ("tc", "fp32"):
             raise ValueError("precision must be 'tc' or 'fp32'")
+        self.allow_fused = True          # False: 'tc' runs layer by layer on the tcgen05 GEMM even where a fused kernel exists (tests)
 
     def uses_tc(self, network_fn, has_views):
-        """Fused tcgen05 kernels for the shape every reference D-NeRF config uses (8x256, PE 10 / 10 / 4)."""
-        return (self.precision == "tc" and tc.available() and tc.bwd_available() and has_views
+        """Fused tcgen05 kernels for 8x256 DirectTemporalNeRF networks: the D-NeRF configs (PE 10 / 10 / 4) and every
+        level of the MultiRes pyramid ((pos, time, view) = (20, 8, 20), (10, 4, 10), identity; multires_dnerf.py:665)."""
+        return (self.precision == "tc" and self.allow_fused and tc.available() and tc.bwd_available() and has_views
                 and hasattr(network_fn, "_time") and tc.dnerf_tc_eligible(network_fn)
-                and getattr(self.embed_fn, "L", None) == 10 and getattr(self.embedtime_fn, "L", None) == 10
-                and getattr(self.embeddirs_fn, "L", None) == 4)
+                and self._enc(network_fn) is not None)
+
+    def _enc(self, network_fn):
+        return tc.enc_for(self.embed_fn, self.embeddirs_fn, self.embedtime_fn, network_fn)
 
     def _arm(self, network_fn):
         """Shapes without a fused kernel (MultiRes encoding widths, ...) run layer by layer: on the tcgen05 GEMM in 'tc'
@@ -94,7 +98,7 @@ class DNerfNetworkQuery:
         N, S = z_vals.shape
         dev = z_vals.device
         if self.uses_tc(network_fn, view_col >= 0):
-            return tc.dnerf_query(network_fn, ray_batch, z_vals, view_col, float(cur_time))
+            return tc.dnerf_query(network_fn, ray_batch, z_vals, view_col, float(cur_time), enc=self._enc(network_fn))
         self._arm(network_fn)
         L_pos = self.embed_fn.L
         L_dir = self.embeddirs_fn.L if view_col >= 0 else -1

@@ -56,9 +56,11 @@ class _NerfBase(nn.Module):
         return ps
 
     def tc_eligible(self) -> bool:
-        """Shape the fused tcgen05 kernels are instantiated for (configs/lego.txt: 8x256, PE 10/4)."""
+        """Shape the fused tcgen05 kernels are instantiated for (8x256, skips [4], view branch; configs/lego.txt).  The
+        input widths must be those of encodings the kernels serve (tc.enc_for checks them against the embedders)."""
+        widths = (3, 27, 63, 123)                              # 3 (1 + 2 L), L in {identity, 4, 10, 20}
         return (self.use_viewdirs and self.D == 8 and self.W == 256 and list(self.skips) == [4]
-                and self.input_ch == 63 and self.input_ch_views == 27 and self.rgb_linear.out_features == 3)
+                and self.input_ch in widths and self.input_ch_views in widths and self.rgb_linear.out_features == 3)
 
     def _forward_embedded(self, x):
         x2 = x.reshape(-1, x.shape[-1])

@@ -54,6 +54,7 @@ class NetworkQuery:
         self.precision = precision or os.environ.get("SWNERF_PRECISION", "tc")
         if self.precision not in ("tc", "fp32"):
             raise ValueError("precision must be 'tc' or 'fp32'")
+        self.allow_fused = True          # False: 'tc' runs layer by layer on the tcgen05 GEMM even where a fused kernel exists (tests)
 
     def __call__(self, inputs, viewdirs, network_fn):
         """Reference signature (nerf/run.py:248).  Also accepts the 2-D point lists of the mesh tools
@@ -66,7 +67,8 @@ class NetworkQuery:
             vd = viewdirs.reshape(n, 3).float().contiguous()
             params = network_fn.param_list()
             training = torch.is_grad_enabled() and (inputs.requires_grad or any(p.requires_grad for p in params))
-            out = tc.TcOccPointsFn.apply(network_fn, vd, pts3.reshape(-1, 3).float(), s_, 0, 0.0, training, *params)
+            out = tc.TcOccPointsFn.apply(network_fn, vd, pts3.reshape(-1, 3).float(), s_, 0, 0.0, training,
+                                         self._enc(network_fn), *params)
             return out.reshape(n, 4) if squeeze else out
         self._arm(network_fn)
         if inputs.dim() == 2:                                  # load_model.py:57-58
@@ -88,14 +90,18 @@ class NetworkQuery:
         if torch.is_grad_enabled() and not tc.bwd_available() and \
                 any(p.requires_grad for p in network_fn.parameters()):
             return False
-        return (self.precision == "tc" and tc.available() and has_views and getattr(network_fn, "tc_eligible", lambda: False)()
-                and getattr(self.embed_fn, "L", None) == 10 and getattr(self.embeddirs_fn, "L", None) == 4)
+        return (self.precision == "tc" and self.allow_fused and tc.available() and has_views
+                and getattr(network_fn, "tc_eligible", lambda: False)() and self._enc(network_fn) is not None)
+
+    def _enc(self, network_fn):
+        """Encoding code of the fused kernels for this query's embedders (None: not served, or widths do not match)."""
+        return tc.enc_for(self.embed_fn, self.embeddirs_fn, None, network_fn)
 
     def query_rays(self, ray_batch, z_vals, network_fn, view_col):
         """raw[N, S, out] for points o + d*z of every ray (nerf/run.py:385-389 fused)."""
         N, S = z_vals.shape
         if self.uses_tc(network_fn, view_col >= 0):
-            return tc.mlp_query(network_fn, ray_batch, z_vals, view_col)
+            return tc.mlp_query(network_fn, ray_batch, z_vals, view_col, enc=self._enc(network_fn))
         self._arm(network_fn)
         L_pos = getattr(self.embed_fn, "L", None)
         L_dir = getattr(self.embeddirs_fn, "L", -1) if view_col >= 0 else -1

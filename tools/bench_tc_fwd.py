@@ -18,9 +18,9 @@ st = tc.packed_weights(m)
 raw = torch.empty(N, Ssamp, 4, device=dev)
 ws = None
 if train:
-    ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(N * Ssamp, 1)), dtype=torch.uint8, device=dev)
+    ws = torch.empty(int(_lib.lib().swnerf_tc_workspace_bytes(N * Ssamp, 1, tc.ENC_DEFAULT)), dtype=torch.uint8, device=dev)
 def run():
-    _lib.call("swnerf_tc_mlp_fwd", rays.data_ptr(), 11, 8, z.data_ptr(), N, Ssamp, st.fwd.data_ptr(), raw.data_ptr(),
+    _lib.call("swnerf_tc_mlp_fwd", rays.data_ptr(), 11, 8, z.data_ptr(), N, Ssamp, st.fwd.data_ptr(), tc.ENC_DEFAULT, raw.data_ptr(),
               None if ws is None else ws.data_ptr(), train, _lib.stream())
 for _ in range(3): run()
 torch.cuda.synchronize()

@@ -350,7 +350,10 @@ def main():
             single = flat_.flat
             rel = float((sharded - single).norm() / single.norm())
             dp_check["grad_rel_l2_%s_%dx%d_rays" % (prec, world, n_local)] = rel
-            assert rel < (1e-5 if prec == "fp32" else 1e-3), "sharded gradient differs from the single-process one: %g" % rel
+            # fp32 mode is the exactness proof (summation order only).  In tc mode the backward scales d_raw by a power of two
+            # chosen per CALL from max|d_raw| (fp16 range), so a shard and the whole batch round their fp16 operands
+            # differently: measured 1e-4 (2 ranks) .. 6e-4 (8 ranks), an order below the operand-format floor (3e-3)
+            assert rel < (1e-5 if prec == "fp32" else 3e-3), "sharded gradient differs from the single-process one: %g" % rel
             del mc_, mf_, q_, flat_
         torch.cuda.empty_cache()
 

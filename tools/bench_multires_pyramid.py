@@ -1,6 +1,6 @@
 """MultiRes D-NeRF pyramid step (config #5: multires_dnerf.py:665 - four level networks with PE (20,8,20), (10,4,10),
 (10,4,10), identity and 1024 / 256 / 64 / 16 rays per step, one loss.backward over all levels, Adam):
-`python tools/bench_multires_pyramid.py [rays_scale]`.  'fp32' = fp32 SIMT GEMMs, 'tc' = layer-wise tcgen05 GEMMs."""
+`python tools/bench_multires_pyramid.py [rays_scale]`.  'fp32' = fp32 SIMT GEMMs, 'tc' = the fused tcgen05 kernels (every level's encoding widths: SWNERF_TC_ENC)."""
 import sys, os, tempfile
 from argparse import Namespace
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -228,6 +228,22 @@ def time_embedding(t: float, L: int = 10):
     return [float(v) for v in vals]
 
 
+def _tpe_device(model, t, L, dev):
+    """PE(t) on the device, cached per (time, L, device): frame times repeat (one per training image), and a cached tensor
+    keeps the call free of host-to-device copies, so a training step can be captured into a CUDA graph."""
+    cache = getattr(model, "_swnerf_tpe", None)
+    if cache is None:
+        cache = {}
+        object.__setattr__(model, "_swnerf_tpe", cache)
+    key = (float(t), int(L), str(dev))
+    v = cache.get(key)
+    if v is None:
+        if len(cache) > 4096:
+            cache.clear()
+        v = cache[key] = torch.tensor(time_embedding(t, L), dtype=F32, device=dev)
+    return v
+
+
 def dnerf_tc_eligible(model) -> bool:
     """DirectTemporalNeRF in the shape every reference D-NeRF / MultiRes config uses (8x256, skips [4]); the encoding
     widths are checked against the embedders by enc_for()."""
@@ -283,7 +299,7 @@ class TcTimeFn(torch.autograd.Function):
         if training:
             ctx.ws, ctx.shape, ctx.params, ctx.grad_scale = ws, (N, S), params, grad_scale
             ctx.packed, ctx.lease = (st.fwd, st.bwd), st.lease()
-            ctx.tpe = torch.tensor(time_embedding(t, (enc >> 16) & 255), dtype=F32, device=dev)
+            ctx.tpe = _tpe_device(model, t, (enc >> 16) & 255, dev)
             ctx.enc = enc
         return dx
 

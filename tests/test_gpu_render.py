@@ -920,3 +920,45 @@ def test_layer_pipelined_backward_matches_two_kernel_backward():
                 assert rel_l2(a, b) < 1e-3
     finally:
         _lib.call("swnerf_tc_set_bwd_variant", -1)
+
+
+@needs_tc_bwd
+def test_dnerf_training_step_replays_from_a_cuda_graph(tmp_path):
+    """Config #4 / #5 steps are launch-bound at their batch sizes, so bench.py replays forward + backward from a CUDA
+    graph: the whole D-NeRF render (stratified draw, deformation + canonical network, resampling, compositing) and its
+    backward must be capturable (no host-device copy or sync inside: the host frame time rides on the ray batch, PE(t) is
+    cached on the device) and a replay must give the gradients of the eager pass."""
+    args = _dnerf_args(tmp_path); args.swnerf_precision = "tc"; args.perturb = 0.0
+    kw, _, _, gv, _ = dnerf.create_nerf(args, device=torch.device(DEV))
+    model = kw["network_fn"]
+    load(model, O.make_params(O.dnerf_param_shapes(), 332))
+    kw = {k: v for k, v in kw.items() if k not in ("use_viewdirs", "ndc")}
+    rays = T(O.blender_rays(200, 33, frame_time=0.37)); rays._swnerf_frame_time = 0.37
+    tgt = torch.rand(200, 3, device=DEV)
+
+    def fwd_bwd():
+        for p in gv:
+            if p.grad is not None:
+                p.grad.zero_()
+        ret = dnerf.render_rays(rays, **kw)
+        loss = torch.mean((ret["rgb_map"] - tgt) ** 2) + 0.1 * torch.sum(ret["position_delta"] ** 2)
+        loss.backward()
+        return loss
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            l_eager = fwd_bwd()
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    g_eager = torch.cat([p.grad.reshape(-1) for p in gv]).clone()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        l_graph = fwd_bwd()
+    for p in gv:
+        p.grad.fill_(123.0)
+    graph.replay()
+    torch.cuda.synchronize()
+    g_graph = torch.cat([p.grad.reshape(-1) for p in gv])
+    assert abs(float(l_graph.detach()) - float(l_eager.detach())) < 1e-6
+    assert rel_l2(g_graph, g_eager) < 1e-5, rel_l2(g_graph, g_eager)

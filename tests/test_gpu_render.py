@@ -1,9 +1,14 @@
 """GPU parity of the MLP paths and of render_rays end to end (forward and backward) against the CPU
 oracle and the reference's golden vectors.
 
-Tolerances (north_star): fp32-accumulate check mode: maps <= 1e-5 relative to the map's range,
-flat gradient <= 5e-4 relative L2; fused tcgen05 mode (fp16 operands, fp32 accumulate): maps <= 1e-3,
-flat gradient <= 5e-3 relative L2 (per-element 1e-3 is not attainable with 11-bit operands)."""
+Tolerances as ASSERTED below (DESIGN.md section 2 has the table; every bound looser than the north_star's wording is
+backed by a committed floor measurement, tests/test_parity_floors.py):
+  fp32-accumulate check mode, same sample positions: maps <= 1e-5 relative to the map's range, flat gradient <= 5e-4
+  relative L2; end to end through the resampling: fine maps <= 5e-3 (the reference against itself with the coarse
+  weights moved by one ulp: ~2e-4; fp64 against fp32: ~2e-3).
+  fused tcgen05 mode (fp16 operands, fp32 accumulate), same sample positions: maps <= 1e-3, flat gradient <= 1e-2
+  relative L2 (measured 3.9e-3; the operand format's own floor is 2.8e-3), per tensor <= 5e-2 (layer 0: 2.7e-2, at the
+  emulation's floor); end to end through the resampling: fine maps <= 2e-2."""
 import os
 from argparse import Namespace
 

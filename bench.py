@@ -130,10 +130,15 @@ def reference_step_fn(device, rays_per_step):
     return step
 
 
-def cpu_reference_run(steps, warmup, rays_per_step, threads, budget_s=240.0):
+def cpu_reference_run(steps, warmup, rays_per_step, threads, budget_s=240.0, anomaly=False):
     """Host-core run.  Starts at `rays_per_step` (4096 = the full step); if the first step shows that steps+warmup of
-    them would not finish inside `budget_s`, the per-step sample is halved until they do (and the line says so)."""
+    them would not finish inside `budget_s`, the per-step sample is halved until they do (and the line says so).
+    anomaly=True times the step the way the reference ships it: utils.py:2 turns autograd anomaly detection ON for
+    every runner (a stack capture per op)."""
     torch.set_num_threads(threads)
+    if anomaly:
+        with torch.autograd.set_detect_anomaly(True):
+            return cpu_reference_run(steps, warmup, rays_per_step, threads, budget_s, anomaly=False)
     n = rays_per_step
     while True:
         step = reference_step_fn(torch.device("cpu"), n)
@@ -668,6 +673,11 @@ def main():
             cpu = {"value": rps, "unit": "rays/s", "cores": threads, "kind": "port",
                    "sample": "%d rays/step x 3 steps (after 1 warm-up) of the same training step (fwd+bwd+Adam), oracle "
                              "port of the reference, eager torch CPU fp32, anomaly mode off" % n_used}
+            try:        # the reference AS SHIPPED runs with autograd anomaly detection on (utils.py:2): context, 2 steps
+                rps_a, _, n_a = cpu_reference_run(2, 1, args.cpu_sample_rays, threads, budget_s=60.0, anomaly=True)
+                cpu["as_shipped_anomaly_mode_on"] = {"value": rps_a, "unit": "rays/s", "rays_per_step": n_a, "steps": 2}
+            except Exception as e:                  # noqa: BLE001
+                cpu["as_shipped_anomaly_mode_on"] = {"error": repr(e)}
         rays_total = rays_per_gpu * world * args.steps
         line = {"metric": "train_rays_per_s", "value": rays_total / (ms * 1e-3), "unit": "rays/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,

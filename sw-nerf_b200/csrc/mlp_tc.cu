@@ -44,37 +44,53 @@ struct ParamPtrs {
 };
 
 // W_fv = W_v[:, :256] W_f (128 x 256), b_fv = W_v[:, :256] b_f + b_v      -> fold[128][257] fp32
-// blocks 0..31: one 32 x 32 tile of W_fv each (shared-memory tiles over the 256-long reduction); blocks 32..35: 32
-// rows of the bias column each.
-__global__ void __launch_bounds__(1024) fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int t = blockIdx.x;
+// 64 blocks of two rows: the block keeps its rows of W_v in shared memory, thread c streams column c of W_f (coalesced
+// across the block, L2-resident) and forms both rows' dot products in ascending j; the bias column is a block reduction.
+constexpr int FOLD_ROWS = 2;
+__global__ void __launch_bounds__(256) fold_head_kernel(ParamPtrs P, float* __restrict__ fold) {
+  __shared__ float sv[FOLD_ROWS][256];
+  __shared__ float red[FOLD_ROWS][8];
+  const int c = threadIdx.x, r0 = blockIdx.x * FOLD_ROWS;
+  if (P.kind != 0) {                                                     // deformation net: no view branch to fold
+#pragma unroll
+    for (int r = 0; r < FOLD_ROWS; ++r) {
+      fold[(r0 + r) * 257 + c] = 0.f;
+      if (c == 0) fold[(r0 + r) * 257 + 256] = 0.f;
+    }
+    return;
+  }
   const int ldv = 256 + P.enc.vc;                                        // views_linears.0.weight is [128, 256 + vc]
-  if (t < 32) {
-    const int r0 = (t >> 3) * 32, c0 = (t & 7) * 32;
-    float acc = 0.f;
-    if (P.kind == 0) {
-      for (int j0 = 0; j0 < 256; j0 += 32) {
-        As[ty][tx] = P.p[16][(size_t)(r0 + ty) * ldv + j0 + tx];       // W_v[r, j]
-        Bs[ty][tx] = P.p[18][(size_t)(j0 + ty) * 256 + c0 + tx];       // W_f[j, c]
-        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < 32; ++j) acc = fmaf(As[ty][j], Bs[j][tx], acc);
-        __syncthreads();
-      }
-    }
-    fold[(r0 + ty) * 257 + c0 + tx] = acc;
-  } else {
-    const int r = (t - 32) * 32 + ty;
-    float acc = 0.f;
-    if (P.kind == 0) {
-      for (int j = tx; j < 256; j += 32) acc = fmaf(P.p[16][(size_t)r * ldv + j], P.p[19][j], acc);
+  for (int r = 0; r < FOLD_ROWS; ++r) sv[r][c] = P.p[16][(size_t)(r0 + r) * ldv + c];       // W_v[r, j]
+  __syncthreads();
+  float acc[FOLD_ROWS];
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-      acc += P.p[17][r];
-    }
-    if (tx == 0) fold[r * 257 + 256] = acc;
+  for (int r = 0; r < FOLD_ROWS; ++r) acc[r] = 0.f;
+  const float* Wf = P.p[18];
+  for (int j0 = 0; j0 < 256; j0 += 32) {                                 // 32 independent loads in flight per thread
+    float w[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) w[i] = __ldg(Wf + (size_t)(j0 + i) * 256 + c);      // W_f[j, c]
+#pragma unroll
+    for (int i = 0; i < 32; ++i)
+#pragma unroll
+      for (int r = 0; r < FOLD_ROWS; ++r) acc[r] = fmaf(sv[r][j0 + i], w[i], acc[r]);
+  }
+  const float bf = P.p[19][c];
+#pragma unroll
+  for (int r = 0; r < FOLD_ROWS; ++r) {
+    fold[(r0 + r) * 257 + c] = acc[r];
+    float pb = sv[r][c] * bf;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) pb += __shfl_xor_sync(0xffffffffu, pb, o);
+    if ((c & 31) == 0) red[r][c >> 5] = pb;
+  }
+  __syncthreads();
+  if (c < FOLD_ROWS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) sum += red[c][w];
+    fold[(r0 + c) * 257 + 256] = sum + P.p[17][r0 + c];
   }
 }
 
@@ -1028,7 +1044,7 @@ static int pack_impl(const float* const* params, int kind, const float* tpe_host
   for (int i = 0; i < ENC_MAX_TW + 3; ++i) P.tpe[i] = (kind == 1 && i < P.enc.tw) ? tpe_host[i] : 0.f;
   cudaStream_t s = (cudaStream_t)stream;
   uint8_t* pk = reinterpret_cast<uint8_t*>(packed);
-  fold_head_kernel<<<36, 1024, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
+  fold_head_kernel<<<128 / FOLD_ROWS, 256, 0, s>>>(P, reinterpret_cast<float*>(pk + PK_FOLD_OFF));
   int rc = check_launch("tc_fold_head");
   if (rc) return rc;
   pack_fwd_kernel<<<(PK_CHUNK_BYTES / 16 + 255) / 256, 256, 0, s>>>(P, pk);

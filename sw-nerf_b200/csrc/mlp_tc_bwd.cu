@@ -946,55 +946,81 @@ mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_co
 
 // ------------------------------------------------------------------------------------------------
 // 3. un-fold of the head (model.py:50-55):  G = d W_fv [128,256], gb = d b_fv [128]
-//      dW_f[c][k]  += sum_u W_v[u][c] G[u][k]                     (64 tiles of 32x32)
-//      dW_v[u][c]  += sum_k G[u][k] W_f[c][k] + gb[u] b_f[c]       (32 tiles)
-//      db_f[c]     += sum_u W_v[u][c] gb[u]                        (8 tiles, one column)
+//      dW_f[c][k]  += sum_u W_v[u][c] G[u][k]
+//      dW_v[u][c]  += sum_k G[u][k] W_f[c][k] + gb[u] b_f[c]
+//      db_f[c]     += sum_u W_v[u][c] gb[u]
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) unfold_head_kernel(const float* __restrict__ Wv, const float* __restrict__ Wf,
-                                                            const float* __restrict__ bf, const float* __restrict__ G,
-                                                            const float* __restrict__ gb, float* __restrict__ dWf,
-                                                            float* __restrict__ dbf, float* __restrict__ dWv,
-                                                            int ldv /* 256 + view columns */) {
-  __shared__ float As[32][33], Bs[32][33];
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  int t = blockIdx.x;
-  float acc = 0.f;
-  if (t < 64) {                       // dW_f tile (c0, k0), reduce over u
-    const int c0 = (t >> 3) * 32, k0 = (t & 7) * 32;
-    for (int u0 = 0; u0 < 128; u0 += 32) {
-      As[ty][tx] = Wv[(size_t)(u0 + ty) * ldv + c0 + tx];
-      Bs[ty][tx] = G[(size_t)(u0 + ty) * 256 + k0 + tx];
-      __syncthreads();
+// 64 blocks: four rows c of dW_f each (thread k streams column k of G, coalesced; the rows' W_v columns sit in shared
+// memory) | 32 blocks: four rows u of dW_v[:, :256] each (an NT product: W_f goes through a transposed 256 x 32 shared-
+// memory tile per 32 k) | 1 block: db_f.  Every element has one writer; atomicAdd because the buffers accumulate.
+constexpr int UNFOLD_BLOCKS = 64 + 32 + 1;
+__global__ void __launch_bounds__(256) unfold_head_kernel(const float* __restrict__ Wv, const float* __restrict__ Wf,
+                                                           const float* __restrict__ bf, const float* __restrict__ G,
+                                                           const float* __restrict__ gb, float* __restrict__ dWf,
+                                                           float* __restrict__ dbf, float* __restrict__ dWv,
+                                                           int ldv /* 256 + view columns */) {
+  __shared__ float sa[4][256];
+  __shared__ float tile[256][33];
+  const int t = threadIdx.x;
+  int blk = blockIdx.x;
+  if (blk < 64) {                     // dW_f[c0 + r][k] += sum_u W_v[u][c0 + r] G[u][k]
+    const int c0 = blk * 4;
 #pragma unroll
-      for (int u = 0; u < 32; ++u) acc = fmaf(As[u][ty], Bs[u][tx], acc);
-      __syncthreads();
+    for (int i = 0; i < 2; ++i) {     // 4 x 128 entries of W_v's columns c0 .. c0 + 3
+      const int e = t + 256 * i, r = e & 3, u = e >> 2;
+      sa[r][u] = Wv[(size_t)u * ldv + c0 + r];
     }
-    atomicAdd(dWf + (size_t)(c0 + ty) * 256 + k0 + tx, acc);
-  } else if (t < 96) {                // dW_v[:, :256] tile (u0, c0), reduce over k
-    t -= 64;
-    const int u0 = (t >> 3) * 32, c0 = (t & 7) * 32;
-    for (int k0 = 0; k0 < 256; k0 += 32) {
-      As[ty][tx] = G[(size_t)(u0 + ty) * 256 + k0 + tx];
-      Bs[ty][tx] = Wf[(size_t)(c0 + ty) * 256 + k0 + tx];
-      __syncthreads();
-#pragma unroll
-      for (int k = 0; k < 32; ++k) acc = fmaf(As[ty][k], Bs[tx][k], acc);
-      __syncthreads();
-    }
-    acc = fmaf(gb[u0 + ty], bf[c0 + tx], acc);
-    atomicAdd(dWv + (size_t)(u0 + ty) * ldv + c0 + tx, acc);
-  } else {                            // db_f
-    t -= 96;
-    const int c = t * 32 + tx;
-    for (int u = ty; u < 128; u += 32) acc = fmaf(Wv[(size_t)u * ldv + c], gb[u], acc);
-    As[ty][tx] = acc;
     __syncthreads();
-    if (ty == 0) {
-      float s2 = 0.f;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int u0 = 0; u0 < 128; u0 += 32) {                      // 32 independent loads in flight per thread
+      float g[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) s2 += As[i][tx];
-      atomicAdd(dbf + c, s2);
+      for (int i = 0; i < 32; ++i) g[i] = __ldg(G + (size_t)(u0 + i) * 256 + t);
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[r][u0 + i], g[i], acc[r]);
     }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) atomicAdd(dWf + (size_t)(c0 + r) * 256 + t, acc[r]);
+  } else if (blk < 96) {              // dW_v[u0 + r][c] += sum_k G[u0 + r][k] W_f[c][k] + gb[u0 + r] b_f[c]
+    const int u0 = (blk - 64) * 4;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) sa[r][t] = G[(size_t)(u0 + r) * 256 + t];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int lane = t & 31, w = t >> 5;
+    for (int k0 = 0; k0 < 256; k0 += 32) {
+      __syncthreads();                // (also orders the sa[] writes before their first use)
+      {
+        float v[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __ldg(Wf + (size_t)(w + 8 * i) * 256 + k0 + lane);      // W_f[c][k0 + lane]
+#pragma unroll
+        for (int i = 0; i < 32; ++i) tile[w + 8 * i][lane] = v[i];
+      }
+      __syncthreads();
+#pragma unroll 8
+      for (int kk = 0; kk < 32; ++kk) {
+        const float wv = tile[t][kk];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) acc[r] = fmaf(sa[r][k0 + kk], wv, acc[r]);
+      }
+    }
+    const float b = bf[t];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) atomicAdd(dWv + (size_t)(u0 + r) * ldv + t, fmaf(gb[u0 + r], b, acc[r]));
+  } else {                            // db_f[c] += sum_u W_v[u][c] gb[u]
+    if (t < 128) sa[0][t] = gb[t];
+    __syncthreads();
+    float acc = 0.f;
+    for (int u0 = 0; u0 < 128; u0 += 32) {
+      float v[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) v[i] = __ldg(Wv + (size_t)(u0 + i) * ldv + t);
+#pragma unroll
+      for (int i = 0; i < 32; ++i) acc = fmaf(v[i], sa[0][u0 + i], acc);
+    }
+    atomicAdd(dbf + t, acc);
   }
 }
 
@@ -1942,7 +1968,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     if (g_prof) { cudaEventRecord(g_ev[1], s); cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
     rc = check_launch("tc_mlp_bwd_lw");
     if (rc) return rc;
-    unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
+    unfold_head_kernel<<<UNFOLD_BLOCKS, 256, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
                                             grads[19], grads[16], 256 + E.vc);
     return check_launch("tc_unfold_head");
   }
@@ -2019,7 +2045,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
 
   if (kind == 0) {
     // un-fold the head: G = d W_fv, gb = d b_fv -> feature_linear / views_linears gradients (db_v was added above)
-    unfold_head_kernel<<<104, 1024, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
+    unfold_head_kernel<<<UNFOLD_BLOCKS, 256, 0, s>>>(params[16], params[18], params[19], unfold, unfold + 128 * 256, grads[18],
                                             grads[19], grads[16], 256 + E.vc);
     rc = check_launch("tc_unfold_head");
   } else {

@@ -618,11 +618,18 @@ struct WgBias {       // column sums of a dy operand sitting in the stage: bias 
   int out_off;
 };
 constexpr int WG_MAX_BIAS = 3;
+// Bias gradients on the tensor pipe instead: one more MMA of the dy operand (M = 128 channels: two blocks) against a
+// block of ones (N = 16), column 0 of its accumulator is the column sum.  Up to two row ranges of the 128 go to
+// gradient tensors (out_param as WgBias: -1 / -2 are the special targets).
+struct WgBiasSeg { int row0, nrow, out_param, out_off; };
+struct WgBiasMma { int a_off, dcol; WgBiasSeg seg[2]; };
+constexpr int WG_MAX_BMMA = 4;
 struct WgJob {
-  int npieces, nmma, nbias, stage_bytes, nstage;
+  int npieces, nmma, nbias, stage_bytes, nstage, nbmma;
   WgPiece pc[WG_MAX_PIECES];
   WgMma mm[WG_MAX_MMA];
   WgBias bs[WG_MAX_BIAS];
+  WgBiasMma bm[WG_MAX_BMMA];
 };
 struct WgArgs {
   uint8_t* ws; int64_t num_tiles;
@@ -658,9 +665,15 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
   const int64_t nhalf = (t_end - t_begin) * 2;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], 1 + 4); }   // MMA commit + 4 bias warps
+    // a stage is released by the MMA commit and, when the job sums bias columns on the CUDA cores, by the 4 bias warps
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&s_empty[i], J.nbias > 0 ? 1 + 4 : 1); }
     mbar_init(&s_done, 1);
     mbar_fence_init();
+  }
+  uint8_t* s_ones = smem + J.nstage * J.stage_bytes;          // [64 samples x 64] fp16 ones: B operand of the bias MMAs
+  if (J.nbmma > 0) {
+    for (int i = threadIdx.x; i < HALF_BLK / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(s_ones)[i] = 0x3c003c00u;
+    fence_async_smem();
   }
   if (warp == 2) tmem_alloc<512>(&tmem_slot);
   tc_fence_before();
@@ -692,7 +705,8 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
       }
     }
   } else if (warp == 1) {
-    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t smem0 = smem_u32(smem), ones = smem_u32(s_ones);
+    const uint32_t idesc_b = umma_idesc_f16(128, 16, 1, 1);
     for (int64_t h = 0; h < nhalf; ++h) {
       const uint32_t stage = h % J.nstage;
       mbar_wait(&s_full[stage], (h / J.nstage) & 1);
@@ -705,6 +719,12 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
           for (int ks = 0; ks < 4; ++ks)
             umma_f16(tmem + mm.dcol, umma_desc_mnmajor(base + mm.a_off + ks * 2048, HALF_BLK),
                      umma_desc_mnmajor(base + mm.b_off + ks * 2048, HALF_BLK), idesc, (h > 0 || ks > 0) ? 1u : 0u);
+        }
+        for (int m = 0; m < J.nbmma; ++m) {                     // column sums of the dy operand: bias gradients
+          const WgBiasMma& bm = J.bm[m];
+          for (int ks = 0; ks < 4; ++ks)
+            umma_f16(tmem + bm.dcol, umma_desc_mnmajor(base + bm.a_off + ks * 2048, HALF_BLK),
+                     umma_desc_mnmajor(ones + ks * 2048, HALF_BLK), idesc_b, (h > 0 || ks > 0) ? 1u : 0u);
         }
         umma_commit(&s_empty[stage]);
       }
@@ -723,7 +743,7 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
     for (int b = 0; b < WG_MAX_BIAS; ++b)
 #pragma unroll
       for (int e = 0; e < 8; ++e) bacc[b][e] = 0.f;
-    for (int64_t h = 0; h < nhalf; ++h) {
+    for (int64_t h = 0; J.nbias > 0 && h < nhalf; ++h) {
       uint32_t stage = h % J.nstage;
       mbar_wait(&s_full[stage], (h / J.nstage) & 1);
       const uint8_t* st = smem + stage * J.stage_bytes;
@@ -773,6 +793,23 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
               else if (J.bs[b].out_param == -1) { atomicAdd(g.unfold + 128 * 256 + col, v); atomicAdd(g.grads[17] + col, v); }
               else { atomicAdd(g.unfold + col, v); atomicAdd(g.grads[1] + col, v); }   // -2: d b0 of THIS call + grads
             }
+          }
+        }
+      }
+      for (int m = 0; m < J.nbmma; ++m) {                       // bias MMAs: column 0 of the N = 16 accumulator, row r
+        const WgBiasMma& bm = J.bm[m];
+        uint32_t v[32];
+        tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + bm.dcol, v);
+        tmem_ld_wait();
+        const float val = __uint_as_float(v[0]) * inv;
+#pragma unroll
+        for (int sg = 0; sg < 2; ++sg) {
+          const WgBiasSeg& S = bm.seg[sg];
+          const int col = r - S.row0;
+          if (col >= 0 && col < S.nrow) {
+            if (S.out_param >= 0) atomicAdd(g.grads[S.out_param] + S.out_off + col, val);
+            else if (S.out_param == -1) { atomicAdd(g.unfold + 128 * 256 + S.out_off + col, val); atomicAdd(g.grads[17] + S.out_off + col, val); }
+            else { atomicAdd(g.unfold + S.out_off + col, val); atomicAdd(g.grads[1] + S.out_off + col, val); }   // -2: d b0 of THIS call + grads
           }
         }
       }
@@ -1710,7 +1747,10 @@ static void wg_std_job(WgJob& J, int l, int x_off /* forward tile offset of the 
     J.mm[m] = {m * 2 * HALF_BLK, 4 * HALF_BLK, 256, m * 256, 2 * l, m * 128 * ld + col_off, ld, 1, 256};
 }
 
-static void build_jobs(WgJob* jobs, int kind, const Enc& E) {
+// bias_mma: the layer-0 / skip / head jobs form their bias gradients on the tensor pipe (WgBiasMma) when tensor memory
+// has room for the 16-column accumulators, instead of summing the dy images on the CUDA cores out of shared memory
+// (whose LDS traffic competes with the tensor pipe's operand reads).  The layer-pipelined kernel keeps the CUDA-core sums.
+static void build_jobs(WgJob* jobs, int kind, const Enc& E, bool bias_mma) {
   memset(jobs, 0, sizeof(WgJob) * WG_JOBS_ALL);
   const int pc = E.pc, vc = E.vc, PC = E.PC, VC = E.VC;
   const int ld0 = pc + (kind == 1 ? E.tw : 0);       // pts_linears.0 is [256, pc]; _time.0 is [256, pc + tw]
@@ -1729,6 +1769,14 @@ static void build_jobs(WgJob* jobs, int kind, const Enc& E) {
       for (int m = 0; m < 2; ++m)
         J.mm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 8 * HALF_BLK, 64 * PC, (a * 2 + m) * 64 * PC,
                            a == 0 ? 0 : 10, m * 128 * (a == 0 ? ld0 : ld5), a == 0 ? ld0 : ld5, 1, pc};
+    if (bias_mma && PC == 1) {                         // accumulators take 256 of the 512 columns: room for 4 x 16 more
+      J.nbias = 0; J.nbmma = 4;
+      for (int a = 0; a < 2; ++a)
+        for (int m = 0; m < 2; ++m) {
+          J.bm[a * 2 + m] = {(a * 4 + m * 2) * HALF_BLK, 256 + (a * 2 + m) * 16,
+                             {{0, 128, a == 0 ? (kind == 1 ? -2 : 1) : 11, m * 128}, {0, 0, 0, 0}}};
+        }
+    }
   }
   // jobs 9 / 10: the two halves of job 0 on their own (dy0 with PE -> dW0[:, :pc], db0;  dy5 with PE -> dW5[:, :pc],
   // db5).  The layer-pipelined kernel gives each its own role: a role that needed dy5 AND dy0 of a tile would hold the
@@ -1767,6 +1815,11 @@ static void build_jobs(WgJob* jobs, int kind, const Enc& E) {
     J.mm[2] = {H7 * HALF_BLK, 2 * HALF_BLK, 16, c0 + 256, 20, 0, 1, 0, 1};           // d w_alpha[0:128]   = h7^T d_sigma
     J.mm[3] = {(H7 + 2) * HALF_BLK, 2 * HALF_BLK, 16, c0 + 272, 20, 128, 1, 0, 1};   // d w_alpha[128:256]
     J.mm[4] = {H9 * HALF_BLK, 3 * HALF_BLK, 16, c0 + 288, 22, 0, 1, 128, 3};         // dW_rgb[j][c] = h9^T d_rgb
+    if (bias_mma) {
+      J.nbias = 0; J.nbmma = 2;
+      J.bm[0] = {0, c0 + 304, {{0, 128, -1, 0}, {0, 0, 0, 0}}};                      // dy9 (blocks 0, 1): folded head bias
+      J.bm[1] = {2 * HALF_BLK, c0 + 320, {{0, 1, 21, 0}, {64, 3, 23, 0}}};           // block 2 col 0 = d_sigma; block 3 cols 0..2 = d_rgb
+    }
     if (kind == 1) {
       // deformation net: only its 256->3 output layer lives in the head.  stage: dyH block 2 | h7 (4 blocks)
       memset(&J, 0, sizeof(J));
@@ -1903,7 +1956,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   for (int i = 0; i < 24; ++i) b.grads[i] = i < np ? grads[i] : nullptr;
   // job table of the default encoding: built once per process (host), uploaded once per DEVICE (c_jobs, read by the
   // layer-pipelined kernel) together with the shared-memory opt-ins; this call's table (kind, encoding) is a parameter
-  static WgJobTable jobs_def[2];
+  static WgJobTable jobs_def[2], jobs_lw[2];
   static int wg_smem = 0;
   static std::once_flag jobs_once;
   std::call_once(jobs_once, [] {
@@ -1911,22 +1964,24 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     decode_enc(ENC_DEFAULT_CODE, &D);
     decode_enc(20 | (20 << 8) | (20 << 16), &Wd);
     WgJobTable wide[2];
-    for (int k = 0; k < 2; ++k) { build_jobs(jobs_def[k].j, k, D); build_jobs(wide[k].j, k, Wd); }
+    for (int k = 0; k < 2; ++k) {
+      build_jobs(jobs_def[k].j, k, D, true); build_jobs(jobs_lw[k].j, k, D, false); build_jobs(wide[k].j, k, Wd, true);
+    }
     for (int k = 0; k < 2; ++k)
-      for (int j = 0; j < WG_JOBS_ALL; ++j) {
-        int need = jobs_def[k].j[j].stage_bytes * jobs_def[k].j[j].nstage + 1024;
-        int need_w = wide[k].j[j].stage_bytes * wide[k].j[j].nstage + 1024;
+      for (int j = 0; j < WG_JOBS_ALL; ++j) {          // ring + ones block + alignment slack
+        int need = jobs_def[k].j[j].stage_bytes * jobs_def[k].j[j].nstage + HALF_BLK + 1024;
+        int need_w = wide[k].j[j].stage_bytes * wide[k].j[j].nstage + HALF_BLK + 1024;
         if (need > wg_smem) wg_smem = need;
         if (need_w > wg_smem) wg_smem = need_w;
       }
   });
   WgJobTable table_local;
   const WgJobTable* table = &jobs_def[kind];
-  if (enc != ENC_DEFAULT_CODE) { build_jobs(table_local.j, kind, E); table = &table_local; }
+  if (enc != ENC_DEFAULT_CODE) { build_jobs(table_local.j, kind, E, true); table = &table_local; }
   const int dpe_smem = 8 * DPE_CHUNK_B + 2 * ACT_BYTES + 1024;
   if (once_per_device(ONCE_BWD_BASE)) {
     cudaFuncSetAttribute(mlp_bwd_data_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMB_TOTAL);
-    cudaMemcpyToSymbol(c_jobs, jobs_def, sizeof(jobs_def));
+    cudaMemcpyToSymbol(c_jobs, jobs_lw, sizeof(jobs_lw));
     cudaFuncSetAttribute(mlp_bwd_weight_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, wg_smem);
   }
   int grid = (int)(tiles < sm_count() ? tiles : sm_count());

@@ -78,3 +78,58 @@ def test_shard_bounds_cover_and_balance():
             assert all(b[i][1] == b[i + 1][0] for i in range(w - 1))
             sizes = [hi - lo for lo, hi in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+# ---- config #5 (MultiRes pyramid): several level networks of different shapes, every level's rays sharded over the
+#      ranks - the 16-ray level leaves a rank with 0 rays at world_size 3+ and an uneven split at 2 - ONE backward over all
+#      levels (multires_dnerf.py:1005), ONE all-reduce of a flat buffer that holds all models
+_LEVELS = [(11, 24, 40), (11, 16, 10), (11, 16, 4), (11, 8, 1)]          # (in, hidden, rays of the level)
+
+
+def _level_models():
+    torch.manual_seed(3)
+    return [torch.nn.Sequential(torch.nn.Linear(i, h), torch.nn.ReLU(), torch.nn.Linear(h, 3)) for i, h, _ in _LEVELS]
+
+
+def _level_data():
+    g = torch.Generator().manual_seed(4)
+    return [(torch.randn(n, i, generator=g), torch.rand(n, 3, generator=g)) for i, _, n in _LEVELS]
+
+
+def _pyramid_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        models, data = _level_models(), _level_data()
+        flat = parallel.FlatGrads([p for m in models for p in m.parameters()])
+        flat.zero_()
+        loss = None
+        for m, (rays, tgt) in zip(models, data):
+            n = rays.shape[0]
+            lo, hi = parallel.shard_bounds(n, rank, world)
+            if hi == lo:
+                continue                                   # this rank holds no ray of the level
+            l = parallel.sharded_mse(m(rays[lo:hi]), tgt[lo:hi], n)
+            loss = l if loss is None else loss + l
+        if loss is not None:
+            loss.backward()
+        assert flat.check_views()
+        flat.all_reduce()
+        if rank == 0:
+            torch.save(flat.flat.clone(), out)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dp_pyramid_levels_one_allreduce(tmp_path, world):
+    out = str(tmp_path / "r0.pt")
+    mp.spawn(_pyramid_worker, args=(world, _free_port(), out), nprocs=world, join=True)
+    got = torch.load(out)
+    models, data = _level_models(), _level_data()
+    loss = sum(torch.mean((m(r) - t) ** 2) for m, (r, t) in zip(models, data))     # F.mse_loss per level, summed
+    loss.backward()
+    ref = torch.cat([p.grad.reshape(-1) for m in models for p in m.parameters()])
+    assert got.numel() == ref.numel()
+    assert torch.allclose(got, ref, rtol=1e-5, atol=1e-7)

@@ -628,6 +628,7 @@ def test_point_query_callers_2d_and_3d():
 @needs_tc_bwd
 @pytest.mark.parametrize("opts", [dict(lindisp=True), dict(N_importance=0), dict(white_bkgd=False),
                                   dict(raw_noise_std=1.0, perturb=1.0), dict(N_samples=32, N_importance=64),
+                                  dict(N_importance=64),          # the 64 + 64 shape of the LLFF configs (nerf/configs/fern.txt)
                                   dict(N_samples=128, N_importance=256)])
 def test_render_rays_tc_option_matrix(opts):
     """render_rays options of the reference configs on the fused path vs the fp32 check path (same kernels for

@@ -185,16 +185,6 @@ struct FwdArgs {
 #define SW_KO(g, bit) 0
 #endif
 
-__device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
-  // angle = 2*pi*frac((th + tl) * scale): th*scale and the rounding to nearest integer are exact in fp32
-  float a = th * scale;
-  float r = a - rintf(a);
-  r = fmaf(tl, scale, r);
-  float ang = r * 6.283185307179586f;
-  s = __sinf(ang);
-  c = __cosf(ang);
-}
-
 // columns [64 CH, 64 CH + 64) of [x, sin(2^k x), cos(2^k x)]_{k < L} (embedder.py:33-42); columns past 3 (1 + 2 L) stay zero
 template <int L, int CH>
 __device__ __forceinline__ void encode3(const float (&x)[3], float (&f)[64]) {

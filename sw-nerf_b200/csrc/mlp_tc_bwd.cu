@@ -1061,6 +1061,15 @@ __global__ void __launch_bounds__(256) unfold_head_kernel(const float* __restric
   }
 }
 
+// deformation net: d _time.0.weight[:, pc : pc + tw] += d b0 (this call's, 256 values) x PE(t)   (K = 1 outer product)
+__global__ void __launch_bounds__(256) time_outer_kernel(const float* __restrict__ db0, const float* __restrict__ tpe,
+                                                          float* __restrict__ dW0, int ld, int pc, int tw) {
+  const int m = threadIdx.x;
+  const float a = db0[m];
+  float* row = dW0 + (size_t)m * ld + pc;
+  for (int n = 0; n < tw; ++n) row[n] += a * __ldg(tpe + n);
+}
+
 // ------------------------------------------------------------------------------------------------
 // 4. input gradient of the canonical net (D-NeRF: PE sits inside the graph, model.py:148-149)
 //      dPE[s, c] = sum_n dy0[s, n] W0[n, c] + dy5[s, n] W5[n, c]   (c < 63)        tcgen05, 128 x 64 x 512 per tile
@@ -1133,6 +1142,9 @@ __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           float x = __ldg(g.pts + idx * 3 + j);
+          const float h1 = 0.15915494f, l1 = 6.4206e-9f;   // 1/(2 pi) = h1 + l1
+          const float th = x * h1;
+          const float tl = fmaf(x, h1, -th) + x * l1;
           float acc = GRP == 0 ? d[j] : 0.f;
 #pragma unroll
           for (int k = 0; k < L; ++k) {
@@ -1140,7 +1152,7 @@ __global__ void __launch_bounds__(192, 1) mlp_bwd_input_kernel(DpeArgs g) {
             const bool s_in = cs >= lo && cs < hi, c_in = cc >= lo && cc < hi;
             if (s_in || c_in) {
               float f = (float)(1 << k), sn, cs_;
-              sincosf(x * f, &sn, &cs_);
+              sincos_turns(th, tl, f, sn, cs_);             // exact range reduction in turns, as the forward's encoder
               if (s_in) acc += f * cs_ * d[s_in ? cs - lo : 0];
               if (c_in) acc -= f * sn * d[c_in ? cc - lo : 0];
             }
@@ -2106,7 +2118,8 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   } else {
     // _time.0.weight[:, pc:pc+tw]: the time embedding is the same for every sample, so this block of the gradient
     // is the outer product (sum_s dy0[s]) x PE(t) = d b0 x PE(t); this call's d b0 sits in the scratch.
-    rc = swnerf_sgemm(0, unfold, 1, tpe_dev, 1, grads[0] + E.pc, E.pc + E.tw, 256, E.tw, 1, nullptr, 1, 0, nullptr, 0, stream);
+    time_outer_kernel<<<1, 256, 0, s>>>(unfold, tpe_dev, grads[0], E.pc + E.tw, E.pc, E.tw);
+    rc = check_launch("tc_time_outer");
   }
   return rc;
 }

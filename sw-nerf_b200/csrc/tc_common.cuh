@@ -291,5 +291,18 @@ __device__ __forceinline__ uint32_t pack_half2_relu(float lo, float hi) {
   return r;
 }
 
+// sin / cos of 2 pi frac((th + tl) * scale) for a power-of-two scale, where th + tl = x / (2 pi) as a two-float sum:
+// th * scale and its rounding to the nearest integer are exact in fp32, so the argument of the MUFU approximations stays
+// in [-pi, pi] whatever the frequency (2^19 x for an L = 20 encoding).  Used by the forward's encoders and by the input
+// gradient (d embed / d x).
+__device__ __forceinline__ void sincos_turns(float th, float tl, float scale, float& s, float& c) {
+  float a = th * scale;
+  float r = a - rintf(a);
+  r = fmaf(tl, scale, r);
+  float ang = r * 6.283185307179586f;
+  s = __sinf(ang);
+  c = __cosf(ang);
+}
+
 }  // namespace tc
 }  // namespace swnerf

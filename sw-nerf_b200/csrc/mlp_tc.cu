@@ -234,19 +234,30 @@ __device__ __forceinline__ void store_row64(uint8_t* img, int row, const float (
   }
 }
 
+// fp32 block of the packed weights (trunk biases, folded head bias, rgb_linear) for the CTA-pair kernel: staged per
+// call with a device-to-device copy on the launching stream.  Every access is warp-uniform, so constant-cache reads
+// cost the same as the shared-memory broadcast they replace, and the 10 KB of shared memory buy a 4th ring stage.
+// There are F32_SLOTS copies: a stream keeps the slot it used last, another stream takes another slot, so the coarse
+// and the fine network (or two callers) can run concurrently on different streams without sharing a bias block.
+constexpr int F32_SLOTS = 4;
+constexpr int F32_PAD = (F32_COUNT + 3) & ~3;
+__constant__ float c_f32s[F32_SLOTS][F32_PAD];
+
 // MODE 0: the default encoding (PE L = 10 / 4) at compile time; 1: one-chunk encodings chosen at run time (g.Lp, g.Lv);
 // 2: two-chunk encodings (L = 20: 123 columns): 32-KB position / view images and a two-stage weight ring
 template <int MODE> struct Fwd1Smem {
   static constexpr int EB = MODE == 2 ? 2 : 1;                  // 16-KB blocks per encoding image
-  static constexpr int NS = MODE == 2 ? 2 : NSTAGE;             // weight ring depth
+  static constexpr int NS = NSTAGE;                             // weight ring depth
   static constexpr int ACT = 0;
   static constexpr int PE = ACT + ACT_BYTES;
   static constexpr int VW = PE + EB * ACT_BLK;
   static constexpr int RING = VW + EB * ACT_BLK;
   static constexpr int F32 = RING + NS * CHUNK_B;
-  static constexpr int SCR = F32 + ((F32_COUNT * 4 + 127) / 128) * 128;
+  // MODE 2 has no room for the 10-KB fp32 block next to two 32-KB encoding images and a three-stage ring: it reads the
+  // biases from constant memory (the CTA-pair kernel's slots) and checks the alignment of the base instead of padding it
+  static constexpr int SCR = F32 + (MODE == 2 ? 0 : ((F32_COUNT * 4 + 127) / 128) * 128);
   static constexpr int BAR = SCR + TILE * 16;
-  static constexpr int TOTAL = BAR + 256 + 1024;                // + alignment slack
+  static constexpr int TOTAL = BAR + 256 + (MODE == 2 ? 0 : 1024);      // + alignment slack
 };
 static_assert(Fwd1Smem<0>::TOTAL == SM_TOTAL && Fwd1Smem<2>::TOTAL <= 232448, "shared memory budget");
 
@@ -255,12 +266,15 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   using SL = Fwd1Smem<MODE>;
   constexpr int NS = SL::NS;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = MODE == 2 ? smem_raw
+                            : reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (MODE == 2 && (smem_u32(smem) & 1023u)) __trap();
   uint8_t* s_act = smem + SL::ACT;
   uint8_t* s_pe = smem + SL::PE;
   uint8_t* s_vw = smem + SL::VW;
   uint8_t* s_ring = smem + SL::RING;
-  float* s_f32 = reinterpret_cast<float*>(smem + SL::F32);
+  float* s_f32w = reinterpret_cast<float*>(smem + SL::F32);              // MODE 0 / 1: staged copy of the fp32 block
+  const float* s_f32 = MODE == 2 ? c_f32s[g.f32_slot] : s_f32w;          // MODE 2: constant memory (warp-uniform reads)
   float4* s_scr = reinterpret_cast<float4*>(smem + SL::SCR);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SL::BAR);
   uint64_t* w_full = bars;            // [3]
@@ -291,7 +305,8 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   if (warp == 14) tmem_alloc<512>(tmem_slot);
   {
     const float* src = reinterpret_cast<const float*>(g.packed + PK_F32_OFF);
-    for (int i = threadIdx.x; i < F32_COUNT; i += blockDim.x) s_f32[i] = __ldg(src + i);
+    if (MODE != 2)
+      for (int i = threadIdx.x; i < F32_COUNT; i += blockDim.x) s_f32w[i] = __ldg(src + i);
   }
   tc_fence_before();
   __syncthreads();
@@ -589,15 +604,6 @@ __global__ void __launch_bounds__(512, 1) mlp_fwd_kernel(FwdArgs g) {
   if (warp == 14) tmem_dealloc<512>(tmem);
 }
 
-
-// fp32 block of the packed weights (trunk biases, folded head bias, rgb_linear) for the CTA-pair kernel: staged per
-// call with a device-to-device copy on the launching stream.  Every access is warp-uniform, so constant-cache reads
-// cost the same as the shared-memory broadcast they replace, and the 10 KB of shared memory buy a 4th ring stage.
-// There are F32_SLOTS copies: a stream keeps the slot it used last, another stream takes another slot, so the coarse
-// and the fine network (or two callers) can run concurrently on different streams without sharing a bias block.
-constexpr int F32_SLOTS = 4;
-constexpr int F32_PAD = (F32_COUNT + 3) & ~3;
-__constant__ float c_f32s[F32_SLOTS][F32_PAD];
 
 // ======================================================================================================
 // Forward kernel on CTA pairs (cta_group::2), two tile slots per CTA.
@@ -1142,6 +1148,10 @@ static int fwd_impl(const float* rays, int ray_stride, int view_col, const float
     return check_launch("tc_mlp_fwd");
   }
   const int mode = E.wide() ? 2 : (defenc ? 0 : 1);
+  if (mode == 2) {
+    int rc = stage_f32_block(reinterpret_cast<const uint8_t*>(packed) + PK_F32_OFF, s, &g.f32_slot);
+    if (rc) return rc;
+  }
   if (training) return mode == 0 ? launch_fwd1<true, 0>(g, grid, s) : mode == 1 ? launch_fwd1<true, 1>(g, grid, s) : launch_fwd1<true, 2>(g, grid, s);
   return mode == 0 ? launch_fwd1<false, 0>(g, grid, s) : mode == 1 ? launch_fwd1<false, 1>(g, grid, s) : launch_fwd1<false, 2>(g, grid, s);
 }

@@ -93,6 +93,12 @@ __global__ void absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* 
   if ((threadIdx.x & 31) == 0 && m > 0.f && m < __int_as_float(0x7f800000)) atomicMax(out, __float_as_uint(m));
 }
 
+// four consecutive fp32 reductions as ONE 16-byte request (the flush of an accumulator row is otherwise 32 separate
+// 4-byte reductions into 32 different lines per warp instruction); p must be 16-byte aligned
+__device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ float grad_scale_from(const uint32_t* absmax, float fixed) {
   if (fixed > 0.f) return fixed;
   float mx = __uint_as_float(*absmax);
@@ -816,13 +822,22 @@ __global__ void __launch_bounds__(256, 1) mlp_bwd_weight_kernel(const __grid_con
       for (int m = 0; m < J.nmma; ++m) {
         const WgMma& mm = J.mm[m];
         float* base = (mm.out_param >= 0 ? g.grads[mm.out_param] : g.unfold) + mm.out_off + (size_t)r * mm.row_stride;
+        // rows of 16-byte-aligned, contiguous outputs (the 256-wide blocks) go out as four-wide reductions
+        const bool vec = mm.col_stride == 1 && (mm.ncols & 31) == 0 && (reinterpret_cast<uintptr_t>(base) & 15) == 0;
         for (int c0 = 0; c0 < mm.ncols; c0 += 32) {
           uint32_t v[32];
           tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + mm.dcol + c0, v);
           tmem_ld_wait();
+          if (vec) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c0 + i < mm.ncols) atomicAdd(base + (size_t)(c0 + i) * mm.col_stride, __uint_as_float(v[i]) * inv);
+            for (int i = 0; i < 32; i += 4)
+              red_add_v4(base + c0 + i, __uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv,
+                         __uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (c0 + i < mm.ncols) atomicAdd(base + (size_t)(c0 + i) * mm.col_stride, __uint_as_float(v[i]) * inv);
+          }
         }
       }
     }
@@ -954,12 +969,20 @@ mlp_bwd_weight_pair_kernel(const __grid_constant__ WgPairArgs g, const __grid_co
       mbar_wait(&s_done, seg & 1);
       tc_fence_after();
       float* base = g.grads[mm.out_param] + mm.out_off + (size_t)r * mm.row_stride;
+      const bool vec = (reinterpret_cast<uintptr_t>(base) & 15) == 0;     // every trunk layer but the skip layer (ld 319)
       for (int c0 = 0; c0 < 256; c0 += 32) {
         uint32_t v[32];
         tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + c0, v);
         tmem_ld_wait();
+        if (vec) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) atomicAdd(base + c0 + i, __uint_as_float(v[i]) * inv);
+          for (int i = 0; i < 32; i += 4)
+            red_add_v4(base + c0 + i, __uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv,
+                       __uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) atomicAdd(base + c0 + i, __uint_as_float(v[i]) * inv);
+        }
       }
       if (J.nbias > 0) {
         uint32_t v[32];
@@ -2078,9 +2101,15 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
   w.ws = ws; w.num_tiles = tiles; w.unfold = unfold; w.absmax = absmax; w.fixed_scale = grad_scale; w.kind = kind;
   w.ws_ext = E.wide() ? tail + WS_TAIL_BYTES : nullptr;
   for (int i = 0; i < 24; ++i) w.grads[i] = i < np ? grads[i] : nullptr;
-  int n_cta = sm_count();
-  if (n_cta < WG_JOBS) n_cta = WG_JOBS;
   const bool wg_pair = tiles > 2 * (int64_t)sm_count();      // small launches: every job on the one-CTA kernel
+  // Every CTA ends with a flush of its accumulators (tens of thousands of red.add into the same gradient tensors the
+  // job's other CTAs flush into), whatever its share of the tiles.  With ~3 us per tile and ~0.65 us of flush per CTA
+  // the time is ~ 3 tiles jobs / n + 0.65 n, smallest at n ~ 2.1 sqrt(tiles jobs): a small launch (a MultiRes level of
+  // 16 or 64 rays) takes only that many CTAs, at least one per job
+  const int jobs_active = wg_pair ? 2 : WG_JOBS;
+  int want = (int)(2.1 * sqrt((double)tiles * jobs_active));
+  int n_cta = want < sm_count() ? want : sm_count();
+  if (n_cta < WG_JOBS) n_cta = WG_JOBS;
   assign_ctas(n_cta, w.job_first_cta, kind, wg_pair);
   if (g_prof) cudaEventRecord(g_ev[1], s);
   if (wg_pair) {
@@ -2105,7 +2134,7 @@ static int bwd_impl(const float* d_out, int64_t n_rays, int n_samples, const voi
     if (rc) return rc;
     if (g_prof) cudaEventRecord(g_ev[3], s);
   }
-  mlp_bwd_weight_kernel<<<n_cta, 256, wg_smem, s>>>(w, *table);
+  mlp_bwd_weight_kernel<<<w.job_first_cta[WG_JOBS], 256, wg_smem, s>>>(w, *table);
   if (g_prof) { cudaEventRecord(g_ev[2], s); g_prof_valid = 1; }
   rc = check_launch("tc_mlp_bwd_weight");
   if (rc) return rc;

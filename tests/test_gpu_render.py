@@ -968,3 +968,59 @@ def test_dnerf_training_step_replays_from_a_cuda_graph(tmp_path):
     g_graph = torch.cat([p.grad.reshape(-1) for p in gv])
     assert abs(float(l_graph.detach()) - float(l_eager.detach())) < 1e-6
     assert rel_l2(g_graph, g_eager) < 1e-5, rel_l2(g_graph, g_eager)
+
+
+@needs_tc_bwd
+@pytest.mark.parametrize("Lp,Lv", [(10, 4), (20, 20), (20, 4)])
+def test_fused_kernels_stay_inside_workspace_and_packed_images(Lp, Lv, monkeypatch):
+    """The training workspace and the packed weight images are sized by swnerf_tc_workspace_bytes / packed_bytes and
+    addressed by offset arithmetic in the kernels (two-chunk encodings add a region behind the workspace tail): a guard
+    band behind each buffer must come back untouched from a forward + backward (ragged last tile, input gradient on)."""
+    GUARD = 1 << 20
+    made = []
+    real_empty = torch.empty
+
+    def guarded_workspace(self, nbytes, dev):
+        buf = real_empty(nbytes + GUARD, dtype=torch.uint8, device=dev)
+        buf[nbytes:].fill_(0xA5)
+        made.append((buf, nbytes))
+        self.ws, self.ws_leases = buf, []
+        tok = tc._Token()
+        self.ws_leases.append(__import__("weakref").ref(tok))
+        return buf, tok
+    monkeypatch.setattr(tc._Packed, "workspace", guarded_workspace)
+    real_packed = tc.packed_weights
+
+    def guarded_packed(network, need_bwd=False, enc=tc.ENC_DEFAULT):
+        st = getattr(network, "_swnerf_packed", None)
+        if st is None:
+            st = tc._Packed()
+            object.__setattr__(network, "_swnerf_packed", st)
+        dev = network.param_list()[0].device
+        if st.fwd is None:
+            n = int(tc._lib.lib().swnerf_tc_packed_bytes())
+            st.fwd = real_empty(n + GUARD, dtype=torch.uint8, device=dev); st.fwd[n:].fill_(0xA5); made.append((st.fwd, n))
+        if need_bwd and st.bwd is None:
+            n = int(tc._lib.lib().swnerf_tc_packed_t_bytes())
+            st.bwd = real_empty(n + GUARD, dtype=torch.uint8, device=dev); st.bwd[n:].fill_(0xA5); made.append((st.bwd, n))
+        return real_packed(network, need_bwd, enc)
+    monkeypatch.setattr(tc, "packed_weights", guarded_packed)
+    ef, ic = S.get_embedder(Lp, 3, Lp)
+    vf, vc = S.get_embedder(Lv, 3, Lv)
+    from swnerf_b200 import synth
+    m = S.NeRFOriginal(D=8, W=256, input_ch=ic, input_ch_views=vc, input_ch_time=1, output_ch=5, skips=[4],
+                       use_viewdirs=True, embed_fn=ef)
+    m.load_state_dict(synth.scene_params(m, 78)); m.to(DEV)
+    q = S.NetworkQuery(ef, vf, 1 << 30, precision="tc")
+    assert q.uses_tc(m, True)
+    g = torch.Generator(device=DEV).manual_seed(9)
+    n, s_ = 333, 7                                   # 2331 points: 19 tiles, ragged last tile
+    pts = ((torch.rand(n, s_, 3, device=DEV, generator=g) - 0.5) * 4).requires_grad_()
+    vd = torch.nn.functional.normalize(torch.randn(n, 3, device=DEV, generator=g), dim=-1)
+    out = q(pts, vd, m)
+    out.square().sum().backward()
+    torch.cuda.synchronize()
+    assert len(made) >= 3
+    for buf, n_ in made:
+        assert bool((buf[n_:] == 0xA5).all()), "a fused kernel wrote behind a buffer of %d bytes" % n_
+    assert torch.isfinite(pts.grad).all()

@@ -126,10 +126,23 @@ def direct_grads(params, on=True):
         p._swnerf_direct_grad = bool(on)
 
 
+def _zero_grads(params):
+    """Zero-initialised gradient tensors for a backward that returns them to autograd: views into ONE buffer (one fill
+    kernel instead of one per parameter tensor; AccumulateGrad takes each view over as the parameter's .grad)."""
+    total = sum(p.numel() for p in params)
+    flat = torch.zeros(total, dtype=F32, device=params[0].device)
+    out, off = [], 0
+    for p in params:
+        n = p.numel()
+        out.append(flat[off:off + n].view(p.shape))
+        off += n
+    return out
+
+
 def _grad_targets(params):
     direct = all(getattr(p, "_swnerf_direct_grad", False) and p.grad is not None and p.grad.dtype == F32
                  and p.grad.is_contiguous() and p.grad.device == p.device for p in params)
-    return direct, ([p.grad for p in params] if direct else [torch.zeros_like(p) for p in params])
+    return direct, ([p.grad for p in params] if direct else _zero_grads(params))
 
 
 def _take_ws(ctx):
@@ -195,7 +208,7 @@ class TcMlpFn(torch.autograd.Function):
         # result loss.backward() leaves there, without 24 zero-fills and 24 AccumulateGrad adds per network.
         direct, grads = _grad_targets(params)
         if direct and torch.is_grad_enabled():                   # create_graph=True: autograd needs real outputs
-            direct, grads = False, [torch.zeros_like(p) for p in params]
+            direct, grads = False, _zero_grads(params)
         fwd, bwd = ctx.packed
         ws = _take_ws(ctx)
         call("swnerf_tc_mlp_bwd", ptr(d_raw, F32, "d_raw"), N, S, fwd.data_ptr(), bwd.data_ptr(), ctx.enc,

@@ -800,12 +800,17 @@ constexpr int kQWarps = 4;                 // warps per block (16 rays): 29 KB o
 
 // CHECK adds the test entry's cdf-in / inds-out / cdf-out (swnerf_resample_check); the production instances
 // (CHECK = false) carry none of it.
-template <bool RANDOM, bool CHECK = false>
+// NI = 128 (configs/lego.txt and every D-NeRF / MultiRes config) or 64 (the LLFF configs and hotdog / materials:
+// nerf/configs/fern.txt): NPL = NI / 8 samples per lane, a merged row of 64 + NI floats = NF float4 per lane.
+template <bool RANDOM, bool CHECK = false, int NI = 128>
 __global__ void __launch_bounds__(kQWarps * 32, 5)
 resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ weights, const float* __restrict__ u_in,
                    int64_t N, float* __restrict__ z_samples, float* __restrict__ z_fine, float* __restrict__ z_std,
                    const ResampleCheck ck = ResampleCheck{nullptr, nullptr, nullptr, 0}) {
-  constexpr int S = 64, Ni = 128;
+  constexpr int S = 64, Ni = NI;
+  constexpr int NPL = NI / 8;                // samples per lane
+  constexpr int NF = (64 + NI) / 32;         // float4 of the merged row per lane (6 or 4)
+  static_assert(NI == 128 || NI == 64, "eight-lane resample kernel: 64 + 128 or 64 + 64 samples");
   extern __shared__ __align__(16) float smem[];
   const unsigned full = 0xffffffffu;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -823,11 +828,11 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   float* recf = row + 200;                                     // record k at (k ^ (k >> 3)) * 4
   float* outb = recf;                                          // [192], after the last read of the records
 
-  float u[16];
+  float u[NPL];
   if (RANDOM) {
-    const float4* up = reinterpret_cast<const float4*>(u_in + rr * Ni) + 4 * g;
+    const float4* up = reinterpret_cast<const float4*>(u_in + rr * Ni) + (NPL / 4) * g;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NPL / 4; ++j) {
       const float4 t = __ldg(up + j);
       u[4 * j] = t.x; u[4 * j + 1] = t.y; u[4 * j + 2] = t.z; u[4 * j + 3] = t.w;
     }
@@ -841,55 +846,55 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
     q[0] = c.x; q[1] = c.y; q[2] = c.z; q[3] = c.w; q[4] = d.x; q[5] = d.y; q[6] = d.z; q[7] = d.w;
   }
   if (RANDOM) {
-    // bitonic sort of the ray's 128 uniforms, element e = 16 g + i, in the all-ascending form: each merge of size k
+    // bitonic sort of the ray's NI uniforms, element e = NPL g + i, in the all-ascending form: each merge of size k
     // starts with the mirror step (e against e ^ (k-1)) and continues with the strides k/4 .. 1, and the lower
     // index always keeps the minimum, so comparators inside a lane have no run-time direction
 #pragma unroll
     for (int k = 2; k <= Ni; k <<= 1) {
-      if (k <= 16) {
+      if (k <= NPL) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < NPL; ++i) {
           if ((i & (k >> 1)) == 0) sort2(u[i], u[i ^ (k - 1)]);
         }
       } else {
-        const bool keep_min = (g & (k >> 5)) == 0;              // bit k/2 of e clear
-        float o[16];
+        const bool keep_min = (g & (k / (2 * NPL))) == 0;       // bit k/2 of e clear
+        float o[NPL];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) o[i] = __shfl_xor_sync(full, u[15 - i], (k >> 4) - 1);
+        for (int i = 0; i < NPL; ++i) o[i] = __shfl_xor_sync(full, u[NPL - 1 - i], k / NPL - 1);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) u[i] = keep_min ? fminf(u[i], o[i]) : fmaxf(u[i], o[i]);
+        for (int i = 0; i < NPL; ++i) u[i] = keep_min ? fminf(u[i], o[i]) : fmaxf(u[i], o[i]);
       }
 #pragma unroll
       for (int j = k >> 2; j > 0; j >>= 1) {
-        if (j >= 16) {
-          const bool keep_min = (g & (j >> 4)) == 0;
+        if (j >= NPL) {
+          const bool keep_min = (g & (j / NPL)) == 0;
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float o = __shfl_xor_sync(full, u[i], j >> 4);
+          for (int i = 0; i < NPL; ++i) {
+            const float o = __shfl_xor_sync(full, u[i], j / NPL);
             u[i] = keep_min ? fminf(u[i], o) : fmaxf(u[i], o);
           }
         } else {
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
+          for (int i = 0; i < NPL; ++i) {
             if ((i & j) == 0) sort2(u[i], u[i | j]);
           }
         }
       }
     }
-    // blocked (16 g + i) -> interleaved (g + 8 i) ownership through shared memory, element e at e + (e >> 4)
+    // blocked (NPL g + i) -> interleaved (g + 8 i) ownership through shared memory, element e at e + e / NPL
 #pragma unroll
-    for (int i = 0; i < 16; ++i) recf[17 * g + i] = u[i];
+    for (int i = 0; i < NPL; ++i) recf[(NPL + 1) * g + i] = u[i];
     __syncwarp();
 #pragma unroll
-    for (int i = 0; i < 16; ++i) u[i] = recf[g + 8 * i + (i >> 1)];
+    for (int i = 0; i < NPL; ++i) u[i] = recf[g + 8 * i + (NPL == 16 ? (i >> 1) : i)];
     __syncwarp();
   } else {
-    // torch.linspace(0, 1, 128), symmetric evaluation (linspace01), sample j = g + 8 i
+    // torch.linspace(0, 1, NI), symmetric evaluation (linspace01), sample j = g + 8 i
     const float step = 1.0f / (float)(Ni - 1), fg = (float)g;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) u[i] = __fmul_rn(step, fg + (float)(8 * i));
+    for (int i = 0; i < NPL / 2; ++i) u[i] = __fmul_rn(step, fg + (float)(8 * i));
 #pragma unroll
-    for (int i = 8; i < 16; ++i) u[i] = __fsub_rn(1.0f, __fmul_rn(step, (float)(Ni - 1 - 8 * i) - fg));
+    for (int i = NPL / 2; i < NPL; ++i) u[i] = __fsub_rn(1.0f, __fmul_rn(step, (float)(Ni - 1 - 8 * i) - fg));
   }
 
   bool ok = true;
@@ -977,10 +982,10 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   const unsigned cdf_sa = (unsigned)__cvta_generic_to_shared(cdf);
   const unsigned zs_sa = (unsigned)__cvta_generic_to_shared(zs);
   const unsigned rec_sa = (unsigned)__cvta_generic_to_shared(recf);
-  float sv[16];
-  int pos[16];
+  float sv[NPL];
+  int pos[NPL];
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < NPL; ++i) {
     const float uu = u[i];
     // p = number of cdf entries <= u (searchsorted right=True): three probes on registers, three on the level tables
     const bool h1 = c31 <= uu;
@@ -1012,59 +1017,75 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
   {
     const float sn = __int_as_float(SENT);
 #pragma unroll
-    for (int j = 0; j < 6; ++j) reinterpret_cast<float4*>(outb)[g + 8 * j] = make_float4(sn, sn, sn, sn);
+    for (int j = 0; j < NF; ++j) reinterpret_cast<float4*>(outb)[g + 8 * j] = make_float4(sn, sn, sn, sn);
   }
   __syncwarp();
 #pragma unroll
-  for (int i = 0; i < 16; ++i) outb[pos[i]] = sv[i];           // pos in [0, 192) whatever the data
+  for (int i = 0; i < NPL; ++i) outb[pos[i]] = sv[i];          // pos in [0, 64 + NI) whatever the data
   __syncwarp();
-  // each lane takes 24 consecutive slots (six float4 at 6g .. 6g+5).  Lanes g and g+4 would meet in the same 16-byte
-  // bank group, so the upper half of the group walks its six float4 one step ahead (j+1 mod 6): conflict-free
-  float v[24];
+  // each lane takes 4 NF consecutive slots (NF float4 at NF g .. NF g + NF - 1).  Lanes whose first float4 falls into
+  // the same 16-byte bank group (NF = 6: g and g + 4; NF = 4: g, g + 2, g + 4, g + 6) walk their float4 in rotated
+  // order, step j reads float4 (j + rot) mod NF: conflict-free
+  constexpr int NROT = NF == 6 ? 2 : 4;
+  const int rot = NF == 6 ? (hi ? 1 : 0) : (g >> 1);
+  float v[4 * NF];
   {
-    float4 t[6];
+    float4 t[NF];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) t[j] = reinterpret_cast<const float4*>(outb)[6 * g + (hi ? (j + 1) % 6 : j)];
+    for (int j = 0; j < NF; ++j) {
+      int sl = j + rot; sl = sl >= NF ? sl - NF : sl;
+      t[j] = reinterpret_cast<const float4*>(outb)[NF * g + sl];
+    }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {                              // t[j] of an upper lane is its float4 (j+1) % 6
-      const float4 a = t[j], b = t[(j + 5) % 6];
-      v[4 * j] = hi ? b.x : a.x; v[4 * j + 1] = hi ? b.y : a.y; v[4 * j + 2] = hi ? b.z : a.z; v[4 * j + 3] = hi ? b.w : a.w;
+    for (int j = 0; j < NF; ++j) {                             // float4 j of the lane was read at step (j - rot) mod NF
+      float4 a = t[j];
+#pragma unroll
+      for (int rr_ = 1; rr_ < NROT; ++rr_) {
+        const float4 b = t[(j - rr_ + NF) % NF];
+        if (rot == rr_) a = b;
+      }
+      v[4 * j] = a.x; v[4 * j + 1] = a.y; v[4 * j + 2] = a.z; v[4 * j + 3] = a.w;
     }
   }
   int ns = 0;
 #pragma unroll
-  for (int j = 0; j < 24; ++j) ns += (__float_as_int(v[j]) != SENT) ? 1 : 0;
+  for (int j = 0; j < 4 * NF; ++j) ns += (__float_as_int(v[j]) != SENT) ? 1 : 0;
   int before = ns;
 #pragma unroll
   for (int o = 1; o < 8; o <<= 1) {
     const int t = __shfl_up_sync(full, before, o, 8);
     if (g >= o) before += t;
   }
-  int zi = 24 * g - (before - ns);                             // next z_val to place; stays inside the row on bad rays
+  int zi = 4 * NF * g - (before - ns);                         // next z_val to place; stays inside the row on bad rays
 #pragma unroll
-  for (int j = 0; j < 24; ++j) {
+  for (int j = 0; j < 4 * NF; ++j) {
     if (__float_as_int(v[j]) == SENT) { v[j] = zsw[zi + (zi >> 3)]; ++zi; }
   }
   // population std of the samples (run.py:416), two-pass
   float s1 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) s1 += sv[i];
+  for (int i = 0; i < NPL; ++i) s1 += sv[i];
   s1 += __shfl_xor_sync(full, s1, 1);
   s1 += __shfl_xor_sync(full, s1, 2);
   s1 += __shfl_xor_sync(full, s1, 4);
   const float mean = s1 / (float)Ni;
   float s2 = 0.f;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) { const float d = sv[i] - mean; s2 += d * d; }
+  for (int i = 0; i < NPL; ++i) { const float d = sv[i] - mean; s2 += d * d; }
   s2 += __shfl_xor_sync(full, s2, 1);
   s2 += __shfl_xor_sync(full, s2, 2);
   s2 += __shfl_xor_sync(full, s2, 4);
   // the row goes back to shared memory (same rotated order) so that the global stores are 128-byte runs per ray
 #pragma unroll
-  for (int j = 0; j < 6; ++j) {
-    const int a = 4 * j, b = 4 * ((j + 1) % 6);
-    reinterpret_cast<float4*>(outb)[6 * g + (hi ? (j + 1) % 6 : j)] =
-        make_float4(hi ? v[b] : v[a], hi ? v[b + 1] : v[a + 1], hi ? v[b + 2] : v[a + 2], hi ? v[b + 3] : v[a + 3]);
+  for (int j = 0; j < NF; ++j) {
+    int sl = j + rot; sl = sl >= NF ? sl - NF : sl;            // step j writes float4 (j + rot) mod NF of the lane
+    float4 a = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+#pragma unroll
+    for (int rr_ = 1; rr_ < NROT; ++rr_) {
+      const int q4 = 4 * ((j + rr_) % NF);
+      if (rot == rr_) a = make_float4(v[q4], v[q4 + 1], v[q4 + 2], v[q4 + 3]);
+    }
+    reinterpret_cast<float4*>(outb)[NF * g + sl] = a;
   }
   __syncwarp();
   if (st_ok) {
@@ -1072,11 +1093,11 @@ resample64q_kernel(const float* __restrict__ z_vals, const float* __restrict__ w
     if (z_samples) {
       float* zo = z_samples + r * Ni + g;                      // 32-B runs per ray and instruction
 #pragma unroll
-      for (int i = 0; i < 16; ++i) zo[8 * i] = sv[i];
+      for (int i = 0; i < NPL; ++i) zo[8 * i] = sv[i];
     }
     float4* fo = reinterpret_cast<float4*>(z_fine + r * (S + Ni));
 #pragma unroll
-    for (int j = 0; j < 6; ++j) fo[g + 8 * j] = reinterpret_cast<const float4*>(outb)[g + 8 * j];
+    for (int j = 0; j < NF; ++j) fo[g + 8 * j] = reinterpret_cast<const float4*>(outb)[g + 8 * j];
   }
   if (okmask == full) return;
   // rays that failed a check: the exact generic routine, one ray at a time on the whole warp
@@ -1257,18 +1278,24 @@ int swnerf_resample(const float* z_vals, const float* weights, const float* u, i
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(resample_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const bool al = aligned16(z_vals) && aligned16(weights) && (det || aligned16(u)) && (!z_samples || aligned16(z_samples));
-  if (n_samples == 64 && n_importance == 128 && al && aligned16(z_fine) && g_resample_variant != 0) {
-    // eight lanes per ray, four rays per warp
+  if (n_samples == 64 && (n_importance == 128 || n_importance == 64) && al && aligned16(z_fine) && g_resample_variant != 0) {
+    // eight lanes per ray, four rays per warp: the two shapes of the reference's configs (64 + 128, 64 + 64)
     const size_t qsmem = (size_t)kQWarps * 4 * kQRow * sizeof(float);
     if (once_per_device(ONCE_RESAMPLE64Q)) {
       cudaFuncSetAttribute(resample64q_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
       cudaFuncSetAttribute(resample64q_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      cudaFuncSetAttribute(resample64q_kernel<false, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+      cudaFuncSetAttribute(resample64q_kernel<true, false, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
     }
     const unsigned qblocks = (unsigned)((n_rays + 4 * kQWarps - 1) / (4 * kQWarps));
-    if (det) resample64q_kernel<false><<<qblocks, kQWarps * 32, qsmem, (cudaStream_t)stream>>>(
-                 z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);
-    else resample64q_kernel<true><<<qblocks, kQWarps * 32, qsmem, (cudaStream_t)stream>>>(
-             z_vals, weights, u, n_rays, z_samples, z_fine, z_std);
+    cudaStream_t qs = (cudaStream_t)stream;
+    if (n_importance == 128) {
+      if (det) resample64q_kernel<false><<<qblocks, kQWarps * 32, qsmem, qs>>>(z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);
+      else resample64q_kernel<true><<<qblocks, kQWarps * 32, qsmem, qs>>>(z_vals, weights, u, n_rays, z_samples, z_fine, z_std);
+    } else {
+      if (det) resample64q_kernel<false, false, 64><<<qblocks, kQWarps * 32, qsmem, qs>>>(z_vals, weights, nullptr, n_rays, z_samples, z_fine, z_std);
+      else resample64q_kernel<true, false, 64><<<qblocks, kQWarps * 32, qsmem, qs>>>(z_vals, weights, u, n_rays, z_samples, z_fine, z_std);
+    }
     return check_launch("resample");
   }
   if (n_samples == 64 && n_importance == 128 && al) {

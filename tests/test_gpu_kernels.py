@@ -169,11 +169,12 @@ def test_sample_pdf_from_weights(golden):
 
 
 @pytest.mark.parametrize("N,S_,Ni,det", [(513, 64, 128, True), (513, 64, 128, False), (77, 64, 64, False),
+                                        (513, 64, 64, True), (4099, 64, 64, False),          # the LLFF configs' 64 + 64
                                         (33, 16, 7, False), (4096, 64, 128, False)])
 @pytest.mark.parametrize("variant", [1, 0])
 def test_resample(N, S_, Ni, det, variant):
-    """variant: kernel of the 64+128 shape (1 = eight lanes per ray, the default; 0 = one warp per ray); other
-    shapes always run the generic kernel."""
+    """variant: 1 = eight lanes per ray (the default; serves 64 + 128 and 64 + 64), 0 = one warp per ray (64 + 128)
+    / the generic kernel; other shapes always run the generic kernel."""
     if variant == 0 and (S_, Ni) != (64, 128):
         pytest.skip("variant only concerns the 64+128 shape")
     rs = np.random.RandomState(N + Ni)
